@@ -1,0 +1,157 @@
+/*
+ * pdab.h — C ABI of libpdab.so: B200-native (sm_100a) kernels for the PDA-SSD
+ * point-backbone hot path of Geo3DSmart/PDANet.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function of the
+ * reference's two pybind11 extension modules; the citation after "replaces:"
+ * is the reference interface (paths relative to the reference root,
+ * PB = pcdet/ops/pointnet2/pointnet2_batch, IOU = pcdet/ops/iou3d_nms).
+ *
+ * Conventions (same as the reference unless stated):
+ *   - all pointers are DEVICE pointers to contiguous row-major arrays, except
+ *     where a parameter is named *_host;
+ *   - the CALLER allocates every output (PB/pointnet2_utils.py:25-26,83,200,246);
+ *   - fp32 data, int32 indices, int64 NMS keep lists;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     the reference always launches on the legacy default stream;
+ *   - nothing allocates, synchronises or touches global state unless stated;
+ *   - return value: 0 on success, a positive cudaError_t value on a CUDA error,
+ *     a negative PDAB_E* code on a bad argument.  The library never aborts the
+ *     process (the reference calls exit(-1) on launch failure,
+ *     PB/src/sampling_gpu.cu:39-43).
+ */
+#ifndef PDAB_H_
+#define PDAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDAB_EINVAL (-1)      /* bad size / null pointer */
+#define PDAB_EUNSUPPORTED (-2) /* size outside what the kernels cover */
+
+typedef void *pdab_stream_t;
+
+/* Library / device info. */
+const char *pdab_version(void);
+/* Human-readable text for a return code of any function below. */
+const char *pdab_error_string(int code);
+
+/* ---- pointnet2_batch_cuda -------------------------------------------------- */
+
+/* Distance farthest-point sampling.
+ * replaces: farthest_point_sampling_wrapper, PB/src/pointnet2_api.cpp:22,
+ *           PB/src/sampling.cpp:34-43, kernel PB/src/sampling_gpu.cu:93-253.
+ * xyz (B,N,3); temp (B,N) in/out: running min-distances, caller pre-fills 1e10
+ * (values must be >= 0), holds the final min-distances on return as in the
+ * reference; idx (B,m) out.  idx[.,0] = 0.  Ties at the maximum resolve exactly
+ * as the reference's 1024-thread tree does: argmin over tied k of
+ * (bitrev_L(k mod BS), k), BS = largest power of two <= min(N,1024), L = log2 BS.
+ * N <= 262144. */
+int pdab_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, pdab_stream_t stream);
+
+/* Farthest-point sampling on a precomputed (B,N,N) distance matrix (F-FPS).
+ * replaces: furthest_point_sampling_with_dist_wrapper, PB/src/pointnet2_api.cpp:23,
+ *           PB/src/sampling.cpp:46-56, kernel PB/src/sampling_gpu.cu:256-416.
+ * N <= 16384. */
+int pdab_fps_with_dist(int b, int n, int m, const float *dist, float *temp, int *idx, pdab_stream_t stream);
+
+/* out[b,c,j] = points[b,c,idx[b,j]].
+ * replaces: gather_points_wrapper, PB/src/pointnet2_api.cpp:19, PB/src/sampling_gpu.cu:8-44. */
+int pdab_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                       pdab_stream_t stream);
+/* grad_points[b,c,idx[b,j]] += grad_out[b,c,j]   (grad_points pre-zeroed by the caller).
+ * replaces: gather_points_grad_wrapper, PB/src/pointnet2_api.cpp:20, PB/src/sampling_gpu.cu:46-83. */
+int pdab_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                            float *grad_points, pdab_stream_t stream);
+
+/* Ball query: first `nsample` points (in index order) with |p - c|^2 < radius^2;
+ * unfilled slots repeat the first hit; a ball with no hit leaves its row untouched
+ * (the caller pre-zeroes idx, PB/pointnet2_utils.py:246).
+ * replaces: ball_query_wrapper, PB/src/pointnet2_api.cpp:13, PB/src/ball_query_gpu.cu:9-67.
+ * new_xyz (B,M,3), xyz (B,N,3), idx (B,M,nsample).  nsample <= 256. */
+int pdab_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                    int *idx, pdab_stream_t stream);
+/* replaces: ball_query_dilated_wrapper, PB/src/pointnet2_api.cpp:14, PB/src/ball_query_gpu.cu:70-139. */
+int pdab_ball_query_dilated(int b, int n, int m, float max_radius, float min_radius, int nsample,
+                            const float *new_xyz, const float *xyz, int *idx, pdab_stream_t stream);
+
+/* out[b,c,j,s] = points[b,c,idx[b,j,s]].
+ * replaces: group_points_wrapper, PB/src/pointnet2_api.cpp:16, PB/src/group_points_gpu.cu:53-92. */
+int pdab_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                      float *out, pdab_stream_t stream);
+/* replaces: group_points_grad_wrapper, PB/src/pointnet2_api.cpp:17, PB/src/group_points_gpu.cu:14-50. */
+int pdab_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points, pdab_stream_t stream);
+
+/* ---- fused ops (additive; no reference native unit, they replace Python glue) ---- */
+
+/* Class-aware ("ctr_aware") sampling: idx[b,:] = indices of the npoint largest
+ * max_c cls[b,k,c], ordered by (value desc, index asc).
+ * replaces: cls.max(-1) -> sigmoid -> torch.topk -> .int(), PB/pointnet2_modules.py:761-770.
+ * cls (B,N,C) fp32, idx (B,npoint).  N <= 65536. */
+int pdab_topk_ctr(int b, int n, int c, int npoint, const float *cls, int *idx, pdab_stream_t stream);
+
+/* PDA grouper: ball query + grouping + Gaussian density + direction encoding in one pass.
+ * replaces: QueryAndGroup_alone_grouped_density_directional.forward, PB/pointnet2_utils.py:567-614.
+ * xyz (B,N,3), new_xyz (B,M,3), features (B,C,N), out (B,7+C,M,nsample) with channels
+ * [xyz(3, not centred), density, direction(3), features(C)];
+ * idx_out (B,M,nsample) optional (may be NULL), written in full. */
+int pdab_pda_group(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                   const float *features, float *out, int *idx_out, pdab_stream_t stream);
+
+/* Fused plain set-abstraction scale: ball query -> group (xyz centred) -> shared MLP
+ * (1x1 conv with eval-mode BatchNorm folded in, ReLU) x nlayers -> max over nsample.
+ * The grouped tensor never reaches HBM.
+ * replaces: QueryAndGroup.forward + mlps[i] + max_pool2d, PB/pointnet2_utils.py:681-704,
+ *           PB/pointnet2_modules.py:1655-1672.
+ * features (B,C,N) or NULL (C=0); dims[0] = 3+C, dims[l+1] = cout of layer l;
+ * weights[l] device (dims[l+1], dims[l]) row-major, biases[l] device (dims[l+1]);
+ * `weights` / `biases` / `dims` themselves are HOST arrays of length nlayers (+1).
+ * out (B, dims[nlayers], M).  nlayers <= 4, nsample <= 64. */
+int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                  const float *features, int nlayers, const int *dims_host, const float *const *weights_host,
+                  const float *const *biases_host, float *out, pdab_stream_t stream);
+
+/* ---- iou3d_nms_cuda -------------------------------------------------------- */
+
+/* Bytes of device workspace pdab_nms_device needs for n boxes. */
+size_t pdab_nms_workspace_bytes(int n);
+
+/* Rotated-BEV NMS, entirely on the device: boxes (n,7) [x,y,z,dx,dy,dz,heading]
+ * already sorted by descending score; keep (n) int64 receives positions into that
+ * order, num_keep (1) int32 the count.  Same bitmask + greedy result as the reference.
+ * replaces: nms_gpu, IOU/src/iou3d_nms_api.cpp:14, IOU/src/iou3d_nms.cpp:90-136,
+ *           kernel IOU/src/iou3d_nms_kernel.cu:267-311. */
+int pdab_nms_device(const float *boxes, int n, float thresh, int64_t *keep, int *num_keep, void *workspace,
+                    pdab_stream_t stream);
+
+/* Batched form: nscenes box lists stored back to back with row stride `stride`
+ * boxes each; counts[s] boxes valid in scene s (device int32); outputs
+ * keep (nscenes,stride) and num_keep (nscenes).  workspace:
+ * nscenes * pdab_nms_workspace_bytes(stride) bytes.  One launch for the batch. */
+int pdab_nms_batched(const float *boxes, const int *counts, int nscenes, int stride, float thresh, int64_t *keep,
+                     int *num_keep, void *workspace, pdab_stream_t stream);
+
+/* Drop-in for the reference pybind signature: device boxes, HOST keep list,
+ * returns num_to_keep (>= 0) or a negative error.  Allocates/frees its own
+ * workspace through the stream-ordered allocator and synchronises `stream`
+ * (the reference does cudaMalloc + blocking cudaMemcpy + cudaFree here).
+ * `normal` != 0 selects the axis-aligned variant (nms_normal_gpu,
+ * IOU/src/iou3d_nms.cpp:139-185, kernel IOU/src/iou3d_nms_kernel.cu:328-372). */
+int pdab_nms_host(const float *boxes, int n, float thresh, int64_t *keep_host, int normal, pdab_stream_t stream);
+
+/* Pairwise rotated BEV overlap area / IoU: out (na, nb).
+ * replaces: boxes_overlap_bev_gpu / boxes_iou_bev_gpu, IOU/src/iou3d_nms_api.cpp:12-13,
+ *           IOU/src/iou3d_nms.cpp:46-88, kernels IOU/src/iou3d_nms_kernel.cu:236-265. */
+int pdab_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *out,
+                           pdab_stream_t stream);
+int pdab_boxes_iou_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *out, pdab_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDAB_H_ */

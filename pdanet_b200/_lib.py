@@ -1,0 +1,90 @@
+"""Loader for libpdab.so — the C-ABI product library (include/pdab.h).
+
+There is no fallback of any kind: if the library is missing or a call fails the
+caller gets an exception.  `build()` compiles it in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libpdab.so"
+CSRC = _PKG / "csrc"
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pdab.h one to one
+_SIGNATURES = {
+    "pdab_version": (C.c_char_p, []),
+    "pdab_error_string": (C.c_char_p, [_i]),
+    "pdab_fps": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_fps_with_dist": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_gather_points": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_gather_points_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_ball_query": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "pdab_ball_query_dilated": (_i, [_i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
+    "pdab_group_points": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_group_points_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_topk_ctr": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdab_pda_group": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_nms_workspace_bytes": (_sz, [_i]),
+    "pdab_nms_device": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "pdab_nms_batched": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "pdab_nms_host": (_i, [_vp, _i, _f, _vp, _i, _vp]),
+    "pdab_boxes_overlap_bev": (_i, [_i, _vp, _i, _vp, _vp, _vp]),
+    "pdab_boxes_iou_bev": (_i, [_i, _vp, _i, _vp, _vp, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+PDAB_EUNSUPPORTED = -2
+
+
+class PdabError(RuntimeError):
+    def __init__(self, fn: str, code: int, text: str):
+        super().__init__(f"{fn} failed with code {code}: {text}")
+        self.code = code
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile pdanet_b200/csrc/*.cu into pdanet_b200/libpdab.so (nvcc, sm_100a, -lineinfo)."""
+    if force:
+        subprocess.check_call(["make", "-C", str(CSRC), "clean"], stdout=subprocess.DEVNULL)
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", str(CSRC), f"-j{min(8, os.cpu_count() or 2)}"], stdout=out)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises if it has not been built (no CPU or eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). pdanet_b200 has no fallback path.")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(fn: str, code: int) -> int:
+    if code != 0:
+        raise PdabError(fn, code, lib().pdab_error_string(code).decode())
+    return code
+
+
+def call(fn: str, *args) -> int:
+    """Invoke an int-returning entry point and raise PdabError on a non-zero code."""
+    return check(fn, getattr(lib(), fn)(*args))

@@ -1,0 +1,38 @@
+// Shared helpers for libpdab.so kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pdab.h"
+
+#define PDAB_LAUNCH_CHECK()                          \
+    do {                                             \
+        cudaError_t e__ = cudaGetLastError();        \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+#define PDAB_CUDA(call)                              \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+namespace pdab {
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+static inline cudaStream_t to_stream(pdab_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Squared distance in the op order nvcc emits for the reference expression
+// (a-b)^2 summed x,y,z: t = rn(dy*dy); t = fma(dx,dx,t); d = fma(dz,dz,t)
+// (PB/src/sampling_gpu.cu:132, PB/src/ball_query_gpu.cu:34; checked in SASS).
+// Written with explicit intrinsics so no compiler version can reorder it.
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    float t = __fmul_rn(dy, dy);
+    t = __fmaf_rn(dx, dx, t);
+    return __fmaf_rn(dz, dz, t);
+}
+
+}  // namespace pdab

@@ -1,0 +1,253 @@
+// Farthest-point sampling for sm_100a.
+//
+// One CTA of 1024 threads per scene keeps the whole point set in shared memory
+// (SoA, up to 16384 points = 192 KB) and the running min-distances in
+// registers (<= 16 per thread); larger clouds use a thread-block cluster of
+// 2..16 CTAs per scene that exchange one 32-byte candidate per iteration
+// through distributed shared memory.  The per-iteration argmax is two REDUX
+// warp reductions + one block barrier (+ one cluster barrier when clustered)
+// instead of the reference's 10-level shared-memory tree
+// (PB/src/sampling_gpu.cu:143-203).
+//
+// Exactness contract (include/pdab.h, pdab_fps): distances in the reference's
+// compiled fp32 op order, and the reference's tie rule — among points tied at
+// the maximum the winner is argmin (bitrev_L(k mod BS), k).  Both are folded
+// into ONE 64-bit key per candidate: [ fp32 bits of dist | ~tiekey(k) ], so a
+// plain unsigned max picks the reference's winner.
+#include <cooperative_groups.h>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kMaxCluster = 16;
+
+struct __align__(16) Candidate {
+    unsigned long long key;  // [dist bits | ~tiekey]; 0 = no candidate
+    float x, y, z;
+    float pad;
+};
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// tiekey(k): top L bits = bit-reversed (k mod 2^L), low 32-L bits = k >> L.
+__device__ __forceinline__ unsigned tie_key(int k, int L) {
+    if (L == 0) return (unsigned)k;
+    return __brev((unsigned)k & ((1u << L) - 1u)) | ((unsigned)k >> L);
+}
+__device__ __forceinline__ int tie_key_decode(unsigned key, int L) {
+    if (L == 0) return (int)key;
+    const unsigned lowmask = (1u << (32 - L)) - 1u;
+    return (int)(((key & lowmask) << L) | __brev(key & ~lowmask));
+}
+
+// P: points per thread.  MATRIX: distances come from row `old` of a (N,N)
+// matrix (F-FPS, PB/src/sampling_gpu.cu:294) instead of coordinates.
+template <int P, bool MATRIX>
+__global__ void __launch_bounds__(kThreads, 1)
+fps_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idxs, int L,
+           int CL) {
+    extern __shared__ float smem[];
+    __shared__ unsigned long long red[2][32];
+    __shared__ Candidate xchg[2][kMaxCluster];
+
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const int rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const int scene = blockIdx.x / CL;
+    constexpr int cap = P * kThreads;
+    float *sx = smem, *sy = smem + cap, *sz = smem + 2 * cap;
+
+    const float *xyz = MATRIX ? nullptr : src + (size_t)scene * n * 3;
+    const float *mat = MATRIX ? src + (size_t)scene * n * n : nullptr;
+    temp += (size_t)scene * n;
+    idxs += (size_t)scene * m;
+
+    // thread t of CTA `rank` owns points k = t + 1024 * (rank + CL * j), j < P
+    float dist[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        const int k = t + kThreads * (rank + CL * j);
+        if (k < n) {
+            dist[j] = temp[k];
+            if (!MATRIX) {
+                sx[j * kThreads + t] = xyz[k * 3 + 0];
+                sy[j * kThreads + t] = xyz[k * 3 + 1];
+                sz[j * kThreads + t] = xyz[k * 3 + 2];
+            }
+        } else {
+            dist[j] = -1.0f;  // never a candidate: real distances are >= 0
+            if (!MATRIX) {
+                sx[j * kThreads + t] = 0.f;
+                sy[j * kThreads + t] = 0.f;
+                sz[j * kThreads + t] = 0.f;
+            }
+        }
+    }
+    if (CL > 1) cg::this_cluster().sync();  // peers must be resident before any DSMEM store
+    else __syncthreads();
+
+    int old = 0;
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+    if (!MATRIX) {
+        x1 = xyz[0];
+        y1 = xyz[1];
+        z1 = xyz[2];
+    }
+    if (t == 0 && rank == 0) idxs[0] = 0;
+
+    int buf = 0;
+    for (int it = 1; it < m; it++) {
+        float bestv = -1.0f;
+        int bestj = -1;
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            float d;
+            if (MATRIX) {
+                const int k = t + kThreads * j;
+                d = k < n ? __ldg(mat + (size_t)old * n + k) : 0.f;
+            } else {
+                d = pdab::sqdist3(sx[j * kThreads + t], sy[j * kThreads + t], sz[j * kThreads + t], x1, y1, z1);
+            }
+            const float dd = fminf(d, dist[j]);
+            dist[j] = dd;
+            if (dd > bestv) {  // strict: lowest j (= lowest k of this thread) wins ties
+                bestv = dd;
+                bestj = j;
+            }
+        }
+        unsigned long long cand = 0ull;
+        if (bestj >= 0) {
+            const int k = t + kThreads * (rank + CL * bestj);
+            cand = ((unsigned long long)__float_as_uint(bestv) << 32) | (unsigned long long)(~tie_key(k, L));
+        }
+        cand = warp_max_u64(cand);
+        if (lane == 0) red[buf][warp] = cand;
+        __syncthreads();
+        cand = warp_max_u64(red[buf][lane]);  // every warp redoes the final 32 -> 1: no second barrier
+
+        if (CL == 1) {
+            old = tie_key_decode(~(unsigned)cand, L);
+            if (!MATRIX) {
+                const int slot = (old >> 10) * kThreads + (old & (kThreads - 1));
+                x1 = sx[slot];
+                y1 = sy[slot];
+                z1 = sz[slot];
+            }
+        } else {
+            if (t < CL) {
+                Candidate c;
+                c.key = cand;
+                c.x = c.y = c.z = c.pad = 0.f;
+                if (cand != 0ull) {
+                    const int k = tie_key_decode(~(unsigned)cand, L);
+                    const int slot = ((k >> 10) / CL) * kThreads + (k & (kThreads - 1));
+                    c.x = sx[slot];
+                    c.y = sy[slot];
+                    c.z = sz[slot];
+                }
+                Candidate *remote = cg::this_cluster().map_shared_rank(&xchg[buf][rank], t);
+                *remote = c;
+            }
+            cg::this_cluster().sync();
+            unsigned long long w = 0ull;
+            int wi = 0;
+#pragma unroll 1
+            for (int i = 0; i < CL; i++) {
+                const unsigned long long v = xchg[buf][i].key;
+                if (v > w) {
+                    w = v;
+                    wi = i;
+                }
+            }
+            old = tie_key_decode(~(unsigned)w, L);
+            x1 = xchg[buf][wi].x;
+            y1 = xchg[buf][wi].y;
+            z1 = xchg[buf][wi].z;
+        }
+        if (t == 0 && rank == 0) idxs[it] = old;
+        buf ^= 1;
+    }
+
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        const int k = t + kThreads * (rank + CL * j);
+        if (k < n) temp[k] = dist[j];
+    }
+}
+
+template <int P, bool MATRIX>
+int launch(int b, int n, int m, const float *src, float *temp, int *idx, int L, int CL, cudaStream_t stream) {
+    const size_t smem = MATRIX ? 0 : (size_t)3 * P * kThreads * sizeof(float);
+    auto kern = fps_kernel<P, MATRIX>;
+    static bool configured = false;  // benign race: the attribute calls are idempotent
+    if (!configured) {
+        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(b * CL);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PDAB_CUDA(cudaLaunchKernelEx(&cfg, kern, n, m, src, temp, idx, L, CL));
+    return 0;
+}
+
+// log2 of the reference's block size, PB/src/cuda_utils.h:10-14 (same double
+// arithmetic, including its truncation).
+int ref_log2_block(int n) {
+    const int pow_2 = (int)(std::log((double)n) / std::log(2.0));
+    int L = pow_2;
+    if (L > 10) L = 10;
+    if (L < 0) L = 0;
+    return L;
+}
+
+template <bool MATRIX>
+int dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t stream) {
+    if (b < 0 || n < 1 || m < 0 || !src || !temp || !idx) return PDAB_EINVAL;
+    if (b == 0 || m == 0) return 0;
+    int CL = 1;
+    int per = pdab::div_up(n, kThreads);
+    while (per > 16 && CL < kMaxCluster) {
+        CL *= 2;
+        per = pdab::div_up(n, kThreads * CL);
+    }
+    if (per > 16 || (MATRIX && CL > 1)) return PDAB_EUNSUPPORTED;
+    const int L = ref_log2_block(n);
+    if (per <= 1) return launch<1, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
+    if (per <= 2) return launch<2, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
+    if (per <= 4) return launch<4, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
+    if (per <= 8) return launch<8, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
+    return launch<16, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
+}
+
+}  // namespace
+
+extern "C" int pdab_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, pdab_stream_t stream) {
+    return dispatch<false>(b, n, m, xyz, temp, idx, pdab::to_stream(stream));
+}
+
+extern "C" int pdab_fps_with_dist(int b, int n, int m, const float *dist, float *temp, int *idx,
+                                  pdab_stream_t stream) {
+    return dispatch<true>(b, n, m, dist, temp, idx, pdab::to_stream(stream));
+}

@@ -1,0 +1,158 @@
+// Fused plain set-abstraction scale for sm_100a:
+//   ball query -> gather (xyz centred, features) -> 3 x (1x1 conv + folded BN + ReLU)
+//   -> max over nsample,  one kernel, grouped tensor and activations never in HBM.
+// Replaces, per scale, 1 ball-query + 2 group + cat + 3 x (conv, BN, ReLU) + max-pool
+// launches of the reference (PB/pointnet2_utils.py:681-704,
+// PB/pointnet2_modules.py:1655-1672).
+//
+// This file holds the CUDA-core variant for NARROW layers (first SA layer of
+// PDA-SSD: 4 -> 16 -> 16 -> 32 and 4 -> 32 -> 32 -> 64): contraction depth 4..32
+// is too shallow to feed tcgen05 tiles, the layer is bound by the neighbour
+// search and gather, not by FLOPs.  One thread owns one query centre: it scans
+// the cloud (ball_scan.cuh), then pushes its nsample neighbours through the MLP
+// with the weights broadcast from shared memory (LDS.128: four weights per load,
+// four FMAs per load) and keeps the running channel maxima in registers.
+// Wide layers (centroid aggregation, 259 -> 256 -> ... -> 1024) are served by the
+// tensor-core variant; unsupported shapes return PDAB_EUNSUPPORTED and the host
+// layer composes the unfused CUDA ops instead.
+#include "ball_scan.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kStride = kThreads + 1;
+
+template <int CIN, int COUT, bool RELU_TO_ARRAY>
+__device__ __forceinline__ void dense(const float *__restrict__ W, const float *__restrict__ bias,
+                                      const float (&in)[CIN], float (&out)[COUT]) {
+    static_assert(CIN % 4 == 0, "rows are read as float4");
+#pragma unroll
+    for (int r = 0; r < COUT; r++) {
+        float acc = bias[r];
+        const float4 *w4 = reinterpret_cast<const float4 *>(W + r * CIN);
+#pragma unroll
+        for (int q = 0; q < CIN / 4; q++) {
+            const float4 w = w4[q];
+            acc = fmaf(w.x, in[4 * q + 0], acc);
+            acc = fmaf(w.y, in[4 * q + 1], acc);
+            acc = fmaf(w.z, in[4 * q + 2], acc);
+            acc = fmaf(w.w, in[4 * q + 3], acc);
+        }
+        if (RELU_TO_ARRAY)
+            out[r] = fmaxf(acc, 0.f);
+        else
+            out[r] = fmaxf(out[r], acc);  // running max; out starts at 0 == ReLU floor
+    }
+}
+
+// C0P: input width padded to a multiple of 4 (3 + C real channels, rest zero weights/inputs)
+template <int C0P, int C1, int C2, int C3>
+__global__ void __launch_bounds__(kThreads)
+sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *__restrict__ xyz,
+                       const float *__restrict__ new_xyz, const float *__restrict__ features,
+                       const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ W2,
+                       const float *__restrict__ b2, const float *__restrict__ W3, const float *__restrict__ b3,
+                       float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);
+    float *sW1 = reinterpret_cast<float *>(tile + pdab::kScanTile);  // C1 x C0P
+    float *sW2 = sW1 + C1 * C0P;                                      // C2 x C1
+    float *sW3 = sW2 + C2 * C1;                                       // C3 x C2
+    float *sb1 = sW3 + C3 * C2;
+    float *sb2 = sb1 + C1;
+    float *sb3 = sb2 + C2;
+    int *sidx = reinterpret_cast<int *>(sb3 + C3);  // nsample x kStride
+
+    const int scene = blockIdx.y;
+    const int t = threadIdx.x;
+    const int j = blockIdx.x * kThreads + t;
+    const bool active = j < m;
+    const int c0 = 3 + c;
+    xyz += (size_t)scene * n * 3;
+    if (c > 0) features += (size_t)scene * c * n;
+
+    for (int i = t; i < C1 * C0P; i += kThreads) {
+        const int r = i / C0P, q = i - r * C0P;
+        sW1[i] = q < c0 ? W1[r * c0 + q] : 0.f;
+    }
+    for (int i = t; i < C2 * C1; i += kThreads) sW2[i] = W2[i];
+    for (int i = t; i < C3 * C2; i += kThreads) sW3[i] = W3[i];
+    for (int i = t; i < C1; i += kThreads) sb1[i] = b1[i];
+    for (int i = t; i < C2; i += kThreads) sb2[i] = b2[i];
+    for (int i = t; i < C3; i += kThreads) sb3[i] = b3[i];
+
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (active) {
+        const float *ctr = new_xyz + ((size_t)scene * m + j) * 3;
+        cx = ctr[0];
+        cy = ctr[1];
+        cz = ctr[2];
+    }
+    pdab::ball_scan_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2, nsample, tile, sidx);
+    if (!active) return;
+
+    float mx[C3];
+#pragma unroll
+    for (int r = 0; r < C3; r++) mx[r] = 0.f;
+
+    for (int s = 0; s < nsample; s++) {
+        const int k = sidx[s * kStride + t];
+        float in[C0P];
+        in[0] = __ldg(xyz + (size_t)k * 3 + 0) - cx;  // grouped_xyz -= new_xyz (PB/pointnet2_utils.py:692)
+        in[1] = __ldg(xyz + (size_t)k * 3 + 1) - cy;
+        in[2] = __ldg(xyz + (size_t)k * 3 + 2) - cz;
+#pragma unroll
+        for (int q = 3; q < C0P; q++) in[q] = (q - 3 < c) ? __ldg(features + (size_t)(q - 3) * n + k) : 0.f;
+        float h1[C1], h2[C2];
+        dense<C0P, C1, true>(sW1, sb1, in, h1);
+        dense<C1, C2, true>(sW2, sb2, h1, h2);
+        dense<C2, C3, false>(sW3, sb3, h2, mx);
+    }
+    float *o = out + (size_t)scene * C3 * m + j;
+#pragma unroll
+    for (int r = 0; r < C3; r++) __stcs(o + (size_t)r * m, mx[r]);
+}
+
+template <int C0P, int C1, int C2, int C3>
+int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                  const float *features, const float *const *W, const float *const *B, float *out,
+                  cudaStream_t stream) {
+    const size_t smem = sizeof(float4) * pdab::kScanTile +
+                        sizeof(float) * (C1 * C0P + C2 * C1 + C3 * C2 + C1 + C2 + C3) +
+                        sizeof(int) * (size_t)nsample * kStride;
+    auto kern = sa_fused_narrow_kernel<C0P, C1, C2, C3>;
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(pdab::div_up(m, kThreads), b);
+    kern<<<grid, kThreads, smem, stream>>>(c, n, m, radius * radius, nsample, xyz, new_xyz, features, W[0], B[0], W[1],
+                                           B[1], W[2], B[2], out);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsample, const float *xyz,
+                             const float *new_xyz, const float *features, int nlayers, const int *dims_host,
+                             const float *const *weights_host, const float *const *biases_host, float *out,
+                             pdab_stream_t stream) {
+    if (b < 0 || c < 0 || n < 1 || m < 0 || nsample < 1 || !xyz || !new_xyz || !out || !dims_host || !weights_host ||
+        !biases_host || (c > 0 && !features))
+        return PDAB_EINVAL;
+    if (b == 0 || m == 0) return 0;
+    if (dims_host[0] != 3 + c) return PDAB_EINVAL;
+    if (nlayers != 3 || nsample > 64 || b > 65535) return PDAB_EUNSUPPORTED;
+    for (int l = 0; l < 3; l++)
+        if (!weights_host[l] || !biases_host[l]) return PDAB_EINVAL;
+    cudaStream_t s = pdab::to_stream(stream);
+    const int d0 = dims_host[0], d1 = dims_host[1], d2 = dims_host[2], d3 = dims_host[3];
+#define PDAB_NARROW(C0P, C1, C2, C3)                                                                              \
+    if (d0 <= C0P && d0 > C0P - 4 && d1 == C1 && d2 == C2 && d3 == C3)                                            \
+        return launch_narrow<C0P, C1, C2, C3>(b, c, n, m, radius, nsample, xyz, new_xyz, features, weights_host,  \
+                                              biases_host, out, s);
+    PDAB_NARROW(4, 16, 16, 32)
+    PDAB_NARROW(4, 32, 32, 64)
+    PDAB_NARROW(8, 16, 16, 32)
+    PDAB_NARROW(8, 32, 32, 64)
+#undef PDAB_NARROW
+    return PDAB_EUNSUPPORTED;
+}

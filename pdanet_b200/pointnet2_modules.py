@@ -1,0 +1,408 @@
+"""Set-abstraction modules of PDA-SSD on top of the B200 ops.
+
+Host-side mirror of the three module classes the reference's IASSD backbone instantiates
+(PB/pointnet2_modules.py): `PointnetSAModuleMSG_WithSampling` (:1417, plain SA),
+`PointnetSAModuleMSG_WithSampling_Ellipsoid` (:541, PDA SA) and `Vote_layer` (:1689), plus
+their helpers `DensityNet` / `PointConvDensitySetAbstraction` (:958-1006) and
+`TransformerEncoderLayerPreNorm` (PB/PointFormer.py).  Class names, constructor arguments,
+forward signatures / return tuples and sub-module attribute names are the reference's, so a
+reference checkpoint loads with `load_state_dict(strict=True)`.
+
+What is different underneath (eval mode, no autograd):
+  * `ctr_aware` sampling is one radix-select kernel instead of max -> sigmoid -> topk -> int;
+  * each plain-SA scale whose MLP shape the fused kernel covers runs as ONE kernel
+    (ball query -> group -> BN-folded MLP -> max-pool) and never materialises the grouped tensor;
+  * the PDA grouper (ball query, 2 x group, density, direction, cat) is one kernel.
+With autograd enabled the modules compose the elementary differentiable ops exactly like the
+reference does.
+
+`ops` (constructor keyword, default = pdanet_b200.pointnet2_utils) is the namespace the
+point ops are taken from.  The product always uses the default; tests and bench.py's CPU
+baseline pass the oracle's CPU namespace to time/check the same module code without a GPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils as _cuda_ops
+
+
+def fold_conv_bn(conv: nn.Module, bn: nn.Module):
+    """(W, b) of the affine map y = BN_eval(conv(x)) for a 1x1 conv / linear layer."""
+    w = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    bias = bn.bias.detach() - bn.running_mean * scale
+    if getattr(conv, "bias", None) is not None:
+        bias = bias + conv.bias.detach() * scale
+    return (w * scale[:, None]).contiguous(), bias.contiguous()
+
+
+class TransformerEncoderLayerPreNorm(nn.Module):
+    """PB/PointFormer.py:7-38.  Note the reference's residuals are taken AFTER each LayerNorm."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu"):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout, inplace=True)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout, inplace=True)
+        self.dropout2 = nn.Dropout(dropout, inplace=True)
+        self.activation = nn.ReLU(inplace=True)
+
+    def forward(self, src, src_mask=None, src_key_padding_mask=None):
+        src = self.norm1(src)  # (K, B*N, C)
+        src2, _ = self.self_attn(src, src, src, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)
+        src = src + self.dropout1(src2)
+        src = self.norm2(src)
+        src2 = self.linear2(self.dropout(self.activation(self.linear1(src))))
+        return src + self.dropout2(src2)
+
+
+class DensityNet(nn.Module):
+    """PB/pointnet2_modules.py:958-981.  The reference's sigmoid branch is unreachable
+    (`i == len(self.mlp_convs)` never holds), so all three layers end in ReLU."""
+
+    def __init__(self, hidden_unit=(16, 8)):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        self.mlp_convs.append(nn.Conv2d(1, hidden_unit[0], 1))
+        self.mlp_bns.append(nn.BatchNorm2d(hidden_unit[0]))
+        for i in range(1, len(hidden_unit)):
+            self.mlp_convs.append(nn.Conv2d(hidden_unit[i - 1], hidden_unit[i], 1))
+            self.mlp_bns.append(nn.BatchNorm2d(hidden_unit[i]))
+        self.mlp_convs.append(nn.Conv2d(hidden_unit[-1], 1, 1))
+        self.mlp_bns.append(nn.BatchNorm2d(1))
+
+    def forward(self, density_scale):
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            density_scale = F.relu(bn(conv(density_scale)))
+        return density_scale
+
+
+class PointConvDensitySetAbstraction(nn.Module):
+    """PB/pointnet2_modules.py:983-1006: normalise each group's density by its maximum, then DensityNet."""
+
+    def __init__(self, bandwidth):
+        super().__init__()
+        self.densitynet = DensityNet()
+        self.bandwidth = bandwidth
+
+    def forward(self, grouped_density):  # (B, 1, M, ns)
+        return self.densitynet(grouped_density / grouped_density.max(dim=3, keepdim=True)[0])
+
+
+def _conv_bn_relu_1d(cin: int, widths: List[int]):
+    layers, c = [], cin
+    for w in widths:
+        layers += [nn.Conv1d(c, w, kernel_size=1, bias=False), nn.BatchNorm1d(w), nn.ReLU()]
+        c = w
+    return layers, c
+
+
+class _SamplingSABase(nn.Module):
+    """Sampling stage shared by the plain and the PDA SA module
+    (PB/pointnet2_modules.py:741-843 and :1543-1646 are the same code in the reference)."""
+
+    def _init_common(self, npoint_list, sample_range_list, sample_type_list, dilated_group, ops):
+        self.npoint_list = npoint_list
+        self.sample_range_list = sample_range_list
+        self.sample_type_list = sample_type_list
+        self.dilated_group = dilated_group
+        self.ops = ops if ops is not None else _cuda_ops
+
+    def _make_heads(self, out_channels, aggregation_mlp, confidence_mlp, num_class, have_scales):
+        if aggregation_mlp and have_scales:
+            layers, out_channels = _conv_bn_relu_1d(out_channels, aggregation_mlp)
+            self.aggregation_layer = nn.Sequential(*layers)
+        else:
+            self.aggregation_layer = None
+        if confidence_mlp:
+            layers, c = _conv_bn_relu_1d(out_channels, confidence_mlp)
+            layers.append(nn.Conv1d(c, num_class, kernel_size=1, bias=True))
+            self.confidence_layers = nn.Sequential(*layers)
+        else:
+            self.confidence_layers = None
+        return out_channels
+
+    @staticmethod
+    def calc_square_dist(a, b):
+        """Pairwise squared distance a (B,n,c) vs b (B,m,c): |a|^2 + |b|^2 - 2 a.b  (PB/pointnet2_modules.py:21-45)."""
+        a_sq = torch.sum(a * a, dim=-1, keepdim=True)
+        b_sq = torch.sum(b * b, dim=-1).unsqueeze(1)
+        return a_sq + b_sq - 2.0 * torch.matmul(a, b.transpose(1, 2))
+
+    def _sample(self, xyz, features, cls_features):
+        ops = self.ops
+        picked = []
+        start = 0
+        for sample_type, sample_range, npoint in zip(self.sample_type_list, self.sample_range_list, self.npoint_list):
+            if npoint <= 0:
+                continue
+            if sample_range == -1:
+                sl = slice(start, None)
+            else:
+                sl = slice(start, sample_range)
+            xyz_tmp = xyz[:, sl, :].contiguous()
+            cls_tmp = cls_features[:, sl, :] if cls_features is not None else None
+            if sample_range != -1:
+                start += sample_range
+
+            n_here = xyz_tmp.shape[1]
+            if n_here <= npoint:  # no downsampling
+                idx = torch.arange(n_here, device=xyz.device, dtype=torch.int32).repeat(xyz.shape[0], 1)
+            elif "cls" in sample_type or "ctr" in sample_type:
+                if torch.is_grad_enabled() and cls_tmp.requires_grad:
+                    score = torch.sigmoid(cls_tmp.max(dim=-1)[0])
+                    idx = torch.topk(score, npoint, dim=-1)[1].int()
+                else:
+                    idx = ops.topk_ctr_sample(cls_tmp, npoint)
+            elif "D-FPS" in sample_type or "DFS" in sample_type:
+                idx = ops.furthest_point_sample(xyz_tmp, npoint)
+            elif "F-FPS" in sample_type or "FFS" in sample_type or sample_type == "FS":
+                feat_tmp = features.transpose(1, 2)[:, sl, :]
+                joint = torch.cat([xyz_tmp, feat_tmp], dim=-1)
+                dist = self.calc_square_dist(joint, joint).contiguous()
+                idx = ops.furthest_point_sample_with_dist(dist, npoint)
+                if sample_type == "FS":
+                    idx = torch.cat([idx, ops.furthest_point_sample(xyz_tmp, npoint)], dim=-1)
+            elif "Rand" in sample_type:
+                idx = torch.randperm(n_here, device=xyz.device)[None, :npoint].int().repeat(xyz.shape[0], 1)
+            else:
+                raise NotImplementedError(f"sampling method {sample_type!r} is not used by PDA-SSD and not built")
+            picked.append(idx)
+        return torch.cat(picked, dim=-1).contiguous()
+
+
+class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
+    """Plain SA layer with sampling and multi-scale grouping (reference PB/pointnet2_modules.py:1417-1686)."""
+
+    def __init__(self, *, npoint_list: List[int], sample_range_list: List[int], sample_type_list: List[str],
+                 radii: List[float], nsamples: List[int], mlps: List[List[int]], use_xyz: bool = True,
+                 dilated_group=False, pool_method="max_pool", aggregation_mlp: List[int],
+                 confidence_mlp: List[int], num_class, ops=None):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self._init_common(npoint_list, sample_range_list, sample_type_list, dilated_group, ops)
+        self.radii, self.nsamples, self.use_xyz = list(radii), list(nsamples), use_xyz
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        out_channels = 0
+        for i, (radius, nsample) in enumerate(zip(radii, nsamples)):
+            if npoint_list is None:
+                self.groupers.append(self.ops.GroupAll(use_xyz))
+            elif dilated_group:
+                self.groupers.append(self.ops.QueryDilatedAndGroup(radius, 0.0 if i == 0 else radii[i - 1], nsample,
+                                                                   use_xyz=use_xyz))
+            else:
+                self.groupers.append(self.ops.QueryAndGroup(radius, nsample, use_xyz=use_xyz))
+            spec = list(mlps[i])
+            if use_xyz:
+                spec[0] += 3
+            layers = []
+            for k in range(len(spec) - 1):
+                layers += [nn.Conv2d(spec[k], spec[k + 1], kernel_size=1, bias=False), nn.BatchNorm2d(spec[k + 1]),
+                           nn.ReLU()]
+            self.mlps.append(nn.Sequential(*layers))
+            out_channels += spec[-1]
+        self.pool_method = pool_method
+        self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.mlps) > 0)
+        self._folded = None  # BN-folded MLP parameters, built lazily in eval mode
+
+    def train(self, mode: bool = True):
+        self._folded = None
+        return super().train(mode)
+
+    def _folded_params(self, i):
+        if self._folded is None:
+            self._folded = {}
+        if i not in self._folded:
+            seq = self.mlps[i]
+            pairs = [fold_conv_bn(seq[3 * k], seq[3 * k + 1]) for k in range(len(seq) // 3)]
+            self._folded[i] = ([p[0] for p in pairs], [p[1] for p in pairs])
+        return self._folded[i]
+
+    def _scale(self, i, xyz, new_xyz, features):
+        fused_ok = (
+            not self.training and not torch.is_grad_enabled() and self.pool_method == "max_pool"
+            and not self.dilated_group and self.use_xyz and self.npoint_list is not None
+            and hasattr(self.ops, "sa_fused")
+        )
+        if fused_ok:
+            seq = self.mlps[i]
+            widths = [seq[3 * k].out_channels for k in range(len(seq) // 3)]
+            c0 = seq[0].in_channels
+            if self.ops.sa_fused_supported(c0, widths, self.nsamples[i]):
+                w, b = self._folded_params(i)
+                return self.ops.sa_fused(self.radii[i], self.nsamples[i], xyz, new_xyz, features, w, b)
+        grouped = self.groupers[i](xyz, new_xyz, features)  # (B, C+3, npoint, nsample)
+        y = self.mlps[i](grouped)
+        if self.pool_method == "max_pool":
+            y = F.max_pool2d(y, kernel_size=[1, y.size(3)])
+        elif self.pool_method == "avg_pool":
+            y = F.avg_pool2d(y, kernel_size=[1, y.size(3)])
+        else:
+            raise NotImplementedError
+        return y.squeeze(-1)
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, cls_features: torch.Tensor = None,
+                new_xyz=None, ctr_xyz=None):
+        """xyz (B,N,3), features (B,C,N), cls_features (B,N,num_class) ->
+        (new_xyz (B,npoint,3), new_features (B,C',npoint), cls_features (B,npoint,num_class) | None, sampled_idx)."""
+        ops = self.ops
+        sampled_idx = []
+        if ctr_xyz is None:
+            sampled_idx = self._sample(xyz, features, cls_features)
+            xyz_flipped = xyz.transpose(1, 2).contiguous()
+            new_xyz = ops.gather_operation(xyz_flipped, sampled_idx).transpose(1, 2).contiguous()
+        else:
+            new_xyz = ctr_xyz
+
+        if len(self.groupers) > 0:
+            outs = [self._scale(i, xyz, new_xyz, features) for i in range(len(self.groupers))]
+            new_features = torch.cat(outs, dim=1)
+            if self.aggregation_layer is not None:
+                new_features = self.aggregation_layer(new_features)
+        else:
+            new_features = ops.gather_operation(features, sampled_idx).contiguous()
+
+        cls_out = self.confidence_layers(new_features).transpose(1, 2) if self.confidence_layers is not None else None
+        return new_xyz, new_features, cls_out, sampled_idx
+
+
+class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
+    """PDA SA layer (reference PB/pointnet2_modules.py:541-955): distribution-aware grouping
+    (density + direction), relative position encoding, density re-weighting, a pre-norm
+    transformer over each neighbourhood, max-pool and a 2-layer output MLP per scale.
+    Only mlp_spec[0] and mlp_spec[-1] of each scale are used, as in the reference (:628-671)."""
+
+    def __init__(self, *, npoint_list: List[int], sample_range_list: List[int], sample_type_list: List[str],
+                 radii: List[float], nsamples: List[int], mlps: List[List[int]], use_xyz: bool = True,
+                 dilated_group=False, pool_method="max_pool", aggregation_mlp: List[int],
+                 confidence_mlp: List[int], num_class, ops=None):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self._init_common(npoint_list, sample_range_list, sample_type_list, dilated_group, ops)
+        self.nsamples = nsamples
+        self.groupers = nn.ModuleList()
+        self.groupers_global = nn.ModuleList()
+        self.point_density = nn.ModuleList()
+        self.position_mlp = nn.ModuleList()
+        self.Local_pointformer = nn.ModuleList()
+        self.fin_conv = nn.ModuleList()
+        self.global_mlps = nn.ModuleList()
+
+        def block2d(cin, cmid, cout):
+            return nn.Sequential(nn.Conv2d(cin, cmid, kernel_size=1, bias=False), nn.BatchNorm2d(cmid), nn.ReLU(),
+                                 nn.Conv2d(cmid, cout, kernel_size=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU())
+
+        out_channels = 0
+        for i, (radius, nsample) in enumerate(zip(radii, nsamples)):
+            if npoint_list is None:
+                self.groupers.append(self.ops.GroupAll(use_xyz))
+            elif dilated_group:
+                self.groupers.append(self.ops.QueryDilatedAndGroup(radius, 0.0 if i == 0 else radii[i - 1], nsample,
+                                                                   use_xyz=use_xyz))
+            else:
+                self.groupers.append(
+                    self.ops.QueryAndGroup_alone_grouped_density_directional(radius, nsample, use_xyz=use_xyz))
+            c = mlps[i][0]
+            self.Local_pointformer.append(
+                TransformerEncoderLayerPreNorm(d_model=c * 4, dim_feedforward=2 * c, dropout=0.0, nhead=4))
+            self.position_mlp.append(block2d(9 + 3, c // 2, c))
+            self.global_mlps.append(block2d(c + 3, c, c))
+            self.point_density.append(PointConvDensitySetAbstraction(radius))
+            self.fin_conv.append(block2d(4 * c, 2 * c, mlps[i][-1]))
+            out_channels += mlps[i][-1]
+        self.pool_method = pool_method
+        self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.fin_conv) > 0)
+
+    def _scale(self, i, xyz, new_xyz, features, global_feature):
+        B, M, _ = new_xyz.shape
+        ns = self.nsamples[i]
+        g = self.groupers[i](xyz, new_xyz, features)  # (B, 7+C, M, ns): xyz | density | direction | features
+        nbr_xyz = g[:, 0:3].permute(0, 2, 3, 1)        # (B, M, ns, 3), not centred
+        density = g[:, 3:4]
+        direction = g[:, 4:7].permute(0, 2, 3, 1)
+        nbr_feat = g[:, 7:]                             # (B, C, M, ns)
+
+        global_k = self.global_mlps[i](global_feature).expand(-1, -1, -1, ns)
+        weighted = nbr_feat * self.point_density[i](density.contiguous())
+
+        centre = new_xyz.unsqueeze(-2).expand(B, M, ns, 3)
+        rppe = torch.cat([centre, nbr_xyz, centre - nbr_xyz, direction], dim=-1)  # (B, M, ns, 12)
+        rppe = self.position_mlp[i](rppe.permute(0, 3, 1, 2).contiguous())         # (B, C, M, ns)
+
+        tokens = torch.cat([rppe, weighted, nbr_feat, global_k], dim=1)            # (B, 4C, M, ns)
+        D = tokens.shape[1]
+        tokens = tokens.permute(3, 0, 2, 1).reshape(ns, B * M, D)                  # (ns, B*M, 4C)
+        tokens = self.Local_pointformer[i](tokens)
+        pooled = tokens.max(dim=0)[0].reshape(B, M, D).permute(0, 2, 1).unsqueeze(-1)  # (B, 4C, M, 1)
+        return self.fin_conv[i](pooled.contiguous()).squeeze(-1)                   # (B, C_out, M)
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, cls_features: torch.Tensor = None,
+                new_xyz=None, ctr_xyz=None):
+        ops = self.ops
+        sampled_idx = []
+        centre_feature = None
+        if ctr_xyz is None:
+            sampled_idx = self._sample(xyz, features, cls_features)
+            xyz_flipped = xyz.transpose(1, 2).contiguous()
+            new_xyz = ops.gather_operation(xyz_flipped, sampled_idx).transpose(1, 2).contiguous()
+            centre_feature = ops.gather_operation(features, sampled_idx)  # (B, C, M)
+        else:
+            new_xyz = ctr_xyz
+
+        if len(self.groupers) > 0:
+            # the reference needs the sampled centres' own features here, i.e. ctr_xyz must be None (:848-856)
+            assert centre_feature is not None, "PDA SA layers take their centres from sampling (CTR_INDEX = -1)"
+            global_feature = torch.cat([new_xyz.transpose(1, 2), centre_feature], dim=1).unsqueeze(-1)  # (B,3+C,M,1)
+            outs = [self._scale(i, xyz, new_xyz, features, global_feature) for i in range(len(self.groupers))]
+            new_features = torch.cat(outs, dim=1)
+            if self.aggregation_layer is not None:
+                new_features = self.aggregation_layer(new_features)
+        else:
+            new_features = ops.gather_operation(features, sampled_idx).contiguous()
+
+        cls_out = self.confidence_layers(new_features).transpose(1, 2) if self.confidence_layers is not None else None
+        return new_xyz, new_features, cls_out, sampled_idx
+
+
+class Vote_layer(nn.Module):
+    """Light voting module with a clamped offset (reference PB/pointnet2_modules.py:1689-1753)."""
+
+    def __init__(self, mlp_list, pre_channel, max_translate_range):
+        super().__init__()
+        self.mlp_list = mlp_list
+        if len(mlp_list) > 0:
+            # the reference re-creates `shared_mlps` per entry and keeps only the last one (:1695-1704)
+            layers = None
+            for width in mlp_list:
+                layers = [nn.Conv1d(pre_channel, width, kernel_size=1, bias=False), nn.BatchNorm1d(width), nn.ReLU()]
+                pre_channel = width
+            self.mlp_modules = nn.Sequential(*layers)
+        else:
+            self.mlp_modules = None
+        self.ctr_reg = nn.Conv1d(pre_channel, 3, kernel_size=1)
+        self.max_offset_limit = (torch.tensor(max_translate_range).float()
+                                 if max_translate_range is not None else None)
+
+    def forward(self, xyz, features):
+        new_features = self.mlp_modules(features) if self.mlp_modules is not None else features
+        offsets = self.ctr_reg(new_features).transpose(1, 2)  # (B, M, 3)
+        feat_offsets = offsets[..., 3:]                       # empty: ctr_reg has 3 outputs
+        ctr_offsets = offsets[..., :3]
+        if self.max_offset_limit is not None:
+            lim = self.max_offset_limit.to(xyz.device).view(1, 1, 3)
+            limited = torch.minimum(torch.maximum(ctr_offsets, -lim), lim)
+            vote_xyz = xyz + limited
+        else:
+            vote_xyz = xyz + ctr_offsets
+        return vote_xyz, feat_offsets, xyz, ctr_offsets

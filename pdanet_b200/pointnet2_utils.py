@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's `pointnet2_utils` API over libpdab.so.
+
+Keeps the reference's public surface — furthest_point_sample, furthest_point_sample_with_dist,
+gather_operation, grouping_operation, ball_query, ball_query_dilated, QueryAndGroup,
+QueryAndGroup_alone_grouped_density_directional, QueryDilatedAndGroup, GroupAll
+(PB/pointnet2_utils.py:36,65,101,225,256,287,671,557,706,743) — with the same argument
+order, tensor layouts, dtypes (int32 indices) and differentiability, and adds the fused
+entry points that have no reference counterpart (topk_ctr_sample, pda_group, sa_fused).
+
+Every op runs on the CUDA device of its inputs through `pointnet2_batch_cuda`
+(our C-ABI shim); CPU tensors are rejected — there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib
+from . import pointnet2_batch_cuda as pointnet2
+
+
+class FarthestPointSampling(Function):
+    """xyz (B,N,3) fp32 -> idx (B,npoint) int32.  PB/pointnet2_utils.py:10-33."""
+
+    @staticmethod
+    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        output = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
+        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+        pointnet2.farthest_point_sampling_wrapper(B, N, npoint, xyz, temp, output)
+        ctx.mark_non_differentiable(output)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None
+
+
+farthest_point_sample = furthest_point_sample = FarthestPointSampling.apply
+
+
+class FurthestPointSamplingWithDist(Function):
+    """dist (B,N,N) fp32 -> idx (B,npoint) int32.  PB/pointnet2_utils.py:39-62."""
+
+    @staticmethod
+    def forward(ctx, dist: torch.Tensor, npoint: int) -> torch.Tensor:
+        assert dist.is_contiguous()
+        B, N, _ = dist.size()
+        output = torch.empty(B, npoint, dtype=torch.int32, device=dist.device)
+        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=dist.device)
+        pointnet2.furthest_point_sampling_with_dist_wrapper(B, N, npoint, dist, temp, output)
+        ctx.mark_non_differentiable(output)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None
+
+
+furthest_point_sample_with_dist = FurthestPointSamplingWithDist.apply
+
+
+class GatherOperation(Function):
+    """features (B,C,N), idx (B,npoint) -> (B,C,npoint).  PB/pointnet2_utils.py:67-98."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        B, npoint = idx.size()
+        _, C, N = features.size()
+        output = torch.empty(B, C, npoint, dtype=torch.float32, device=features.device)
+        pointnet2.gather_points_wrapper(B, C, N, npoint, features, idx, output)
+        ctx.for_backwards = (idx, C, N)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, C, N = ctx.for_backwards
+        B, npoint = idx.size()
+        grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+        pointnet2.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+gather_operation = GatherOperation.apply
+
+
+class GroupingOperation(Function):
+    """features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample).  PB/pointnet2_utils.py:184-222."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        B, nfeatures, nsample = idx.size()
+        _, C, N = features.size()
+        output = torch.empty(B, C, nfeatures, nsample, dtype=torch.float32, device=features.device)
+        pointnet2.group_points_wrapper(B, C, N, nfeatures, nsample, features, idx, output)
+        ctx.for_backwards = (idx, N)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, N = ctx.for_backwards
+        B, C, npoint, nsample = grad_out.size()
+        grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+        pointnet2.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+class BallQuery(Function):
+    """(radius, nsample, xyz (B,N,3), new_xyz (B,M,3)) -> idx (B,M,nsample) int32.  PB/pointnet2_utils.py:228-253."""
+
+    @staticmethod
+    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+        assert new_xyz.is_contiguous()
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        npoint = new_xyz.size(1)
+        idx = torch.zeros(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
+        pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+ball_query = BallQuery.apply
+
+
+class BallQueryDilated(Function):
+    """PB/pointnet2_utils.py:258-284."""
+
+    @staticmethod
+    def forward(ctx, max_radius: float, min_radius: float, nsample: int, xyz: torch.Tensor,
+                new_xyz: torch.Tensor) -> torch.Tensor:
+        assert new_xyz.is_contiguous()
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        npoint = new_xyz.size(1)
+        idx = torch.zeros(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
+        pointnet2.ball_query_dilated_wrapper(B, N, npoint, max_radius, min_radius, nsample, new_xyz, xyz, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None, None
+
+
+ball_query_dilated = BallQueryDilated.apply
+
+
+# --------------------------------------------------------------------------- fused entry points
+
+def topk_ctr_sample(cls_features: torch.Tensor, npoint: int) -> torch.Tensor:
+    """Class-aware sampling: cls_features (B,N,num_class) -> idx (B,npoint) int32 ordered by
+    (max-class logit desc, index asc).  One kernel for cls.max(-1) -> sigmoid -> topk -> .int()
+    (PB/pointnet2_modules.py:761-770)."""
+    if not cls_features.is_cuda:
+        raise RuntimeError("cls_features must be a CUDA tensor")
+    cls_features = cls_features.contiguous().float()
+    B, N, C = cls_features.shape
+    idx = torch.empty(B, npoint, dtype=torch.int32, device=cls_features.device)
+    with torch.cuda.device(cls_features.device):
+        _lib.call("pdab_topk_ctr", B, N, C, npoint, cls_features.data_ptr(), idx.data_ptr(),
+                  torch.cuda.current_stream(cls_features.device).cuda_stream)
+    return idx
+
+
+def pda_group(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor,
+              return_idx: bool = False):
+    """Fused PDA grouper (forward only): (B, 7+C, M, nsample) with channels
+    [xyz, density, direction, features] — PB/pointnet2_utils.py:567-614 in one kernel."""
+    for t in (xyz, new_xyz, features):
+        if not t.is_cuda:
+            raise RuntimeError("pda_group needs CUDA tensors")
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and features.is_contiguous()
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = features.shape[1]
+    out = torch.empty(B, 7 + C, M, nsample, dtype=torch.float32, device=xyz.device)
+    idx = torch.empty(B, M, nsample, dtype=torch.int32, device=xyz.device) if return_idx else None
+    with torch.cuda.device(xyz.device):
+        _lib.call("pdab_pda_group", B, C, N, M, float(radius), nsample, xyz.data_ptr(), new_xyz.data_ptr(),
+                  features.data_ptr(), out.data_ptr(), idx.data_ptr() if return_idx else None,
+                  torch.cuda.current_stream(xyz.device).cuda_stream)
+    return (out, idx) if return_idx else out
+
+
+def sa_fused_supported(c0: int, dims: Sequence[int], nsample: int) -> bool:
+    """Shapes the fused plain-SA kernel covers (see csrc/sa_fused.cu)."""
+    return len(dims) == 3 and nsample <= 64 and c0 <= 8 and tuple(dims) in ((16, 16, 32), (32, 32, 64))
+
+
+def sa_fused(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
+             features: Optional[torch.Tensor], weights: List[torch.Tensor], biases: List[torch.Tensor]) -> torch.Tensor:
+    """Fused plain-SA scale (forward only): ball query -> group -> folded (conv,BN,ReLU) x L -> max-pool.
+    weights[l] (cout_l, cin_l), biases[l] (cout_l) are the BN-folded parameters.  Returns (B, cout_last, M)."""
+    assert xyz.is_cuda and xyz.is_contiguous() and new_xyz.is_contiguous()
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = 0 if features is None else features.shape[1]
+    if features is not None:
+        assert features.is_contiguous()
+    L = len(weights)
+    dims = [3 + C] + [int(w.shape[0]) for w in weights]
+    for l, (w, bvec) in enumerate(zip(weights, biases)):
+        assert w.is_cuda and w.is_contiguous() and w.dtype == torch.float32 and tuple(w.shape) == (dims[l + 1], dims[l])
+        assert bvec.is_cuda and bvec.is_contiguous() and bvec.dtype == torch.float32 and bvec.numel() == dims[l + 1]
+    out = torch.empty(B, dims[-1], M, dtype=torch.float32, device=xyz.device)
+    dims_a = (ctypes.c_int * (L + 1))(*dims)
+    w_a = (ctypes.c_void_p * L)(*[w.data_ptr() for w in weights])
+    b_a = (ctypes.c_void_p * L)(*[x.data_ptr() for x in biases])
+    with torch.cuda.device(xyz.device):
+        _lib.call("pdab_sa_fused", B, C, N, M, float(radius), nsample, xyz.data_ptr(), new_xyz.data_ptr(),
+                  features.data_ptr() if features is not None else None, L, dims_a, w_a, b_a, out.data_ptr(),
+                  torch.cuda.current_stream(xyz.device).cuda_stream)
+    return out
+
+
+# --------------------------------------------------------------------------- grouper modules
+
+class QueryAndGroup(nn.Module):
+    """Ball query + grouping with centred xyz.  PB/pointnet2_utils.py:671-704."""
+
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        xyz_trans = xyz.transpose(1, 2).contiguous()
+        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
+        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is not None:
+            grouped_features = grouping_operation(features, idx)
+            return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        return grouped_xyz
+
+
+class QueryDilatedAndGroup(nn.Module):
+    """PB/pointnet2_utils.py:706-741 (argument order radius_in, radius_out kept as in the reference,
+    which forwards them to ball_query_dilated(max_radius, min_radius, ...) in that order)."""
+
+    def __init__(self, radius_in: float, radius_out: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius_in, self.radius_out, self.nsample, self.use_xyz = radius_in, radius_out, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        idx = ball_query_dilated(self.radius_in, self.radius_out, self.nsample, xyz, new_xyz)
+        xyz_trans = xyz.transpose(1, 2).contiguous()
+        grouped_xyz = grouping_operation(xyz_trans, idx)
+        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is not None:
+            grouped_features = grouping_operation(features, idx)
+            return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        return grouped_xyz
+
+
+class QueryAndGroup_alone_grouped_density_directional(nn.Module):
+    """PDA grouper: [xyz (not centred), Gaussian density, direction, features].
+    PB/pointnet2_utils.py:557-614.  Inference (no grad) uses the fused kernel; with autograd
+    enabled the differentiable composition of the elementary ops is used."""
+
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        if features is not None and self.use_xyz and not (torch.is_grad_enabled() and features.requires_grad):
+            return pda_group(self.radius, self.nsample, xyz, new_xyz, features.contiguous())
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
+        centre = new_xyz.transpose(1, 2).unsqueeze(-1)
+        offset = grouped_xyz - centre
+        distances = torch.norm(offset, dim=1, keepdim=True)
+        density = torch.exp(-distances ** 2 / (2 * self.radius ** 2)) / (2.5 * self.radius)
+        direction = offset / self.radius
+        if features is not None:
+            grouped_features = grouping_operation(features, idx)
+            if self.use_xyz:
+                return torch.cat([grouped_xyz, density, direction, grouped_features], dim=1)
+            return grouped_features
+        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        return grouped_xyz
+
+
+class GroupAll(nn.Module):
+    """PB/pointnet2_utils.py:743-766."""
+
+    def __init__(self, use_xyz: bool = True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is not None:
+            grouped_features = features.unsqueeze(2)
+            return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        return grouped_xyz
