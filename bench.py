@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — PDA-SSD scenes/sec on synthetic KITTI-shape point clouds (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl pdab|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one full inference pass (backbone + vote + centroid aggregation + head + 3D NMS) over one batch
+of 16 synthetic 16384-point scenes per GPU (BASELINE.json configs[1]); scenes are sharded by GPU with no
+data-path collective (weak scaling).  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "PDA-SSD scenes/sec @16384 pts (KITTI cfg, full inference)"
+UNIT = "scenes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pdab", choices=["pdab", "reference"])
+    ap.add_argument("--config", default="kitti", choices=["kitti", "once"])
+    ap.add_argument("--batch", type=int, default=None, help="scenes per GPU per step (default 16 kitti / 4 once)")
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+
+def cpu_model(cfg):
+    from oracle import torch_ops
+    from pdanet_b200.iassd import build_model
+    torch.manual_seed(0)
+    return build_model(cfg, ops=torch_ops, nms_utils=torch_ops.nms_utils, batched_post_processing=False).eval()
+
+
+def time_cpu(cfg, n_points, scenes, warmup=1):
+    """The oracle port of the path (C restatement of FPS / ball query / group / NMS + the same module code on
+    torch CPU) on the host cores: `scenes` single-scene batches, returns (scenes/s, threads, per-scene seconds)."""
+    from pdanet_b200.synthetic import make_batch
+    model = cpu_model(cfg)
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    with torch.no_grad():
+        for s in range(warmup + scenes):
+            batch = make_batch(1, n_points, cfg.POINT_CLOUD_RANGE, first_scene=s)
+            t0 = time.perf_counter()
+            model(batch)
+            if s >= warmup:
+                times.append(time.perf_counter() - t0)
+    return len(times) / sum(times), torch.get_num_threads(), times
+
+
+def run_reference_arm(args, cfg, n_points, batch):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    per_step = max(1, min(2, batch))  # bounded sample: scenes per step
+    sps, threads, times = time_cpu(cfg, n_points, scenes=per_step * args.steps, warmup=max(1, args.warmup))
+    sample = f"{per_step} scene(s)/step x {args.steps} steps, one {n_points}-point scene per forward, batch 1"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PDA-SSD {args.config} cfg full inference, {n_points} pts/scene, CPU oracle port",
+                   "scenes_per_step": per_step},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+
+def algorithmic_bytes(key: str, batch: int):
+    """HBM bytes one launch must move (SURVEY.md §8d / DESIGN.md 'Kernels'); key = 'entry(sizes...)'."""
+    name, _, rest = key.partition("(")
+    a = [int(x) for x in rest.strip(")").split(",") if x.strip()]
+    if name == "pdab_fps":
+        b, n, m = a[:3]
+        return b * (12 * n + 4 * n * 2 + 4 * m)      # xyz read, temp read + written back, idx written
+    if name == "pdab_ball_query":
+        b, n, m, ns = a[0], a[1], a[2], a[3]
+        return b * (12 * n + 12 * m + 4 * m * ns)
+    if name in ("pdab_group_points", "pdab_gather_points"):
+        b, c, n = a[:3]
+        e = a[3] * (a[4] if name == "pdab_group_points" else 1)
+        return b * (4 * c * e * 2 + 4 * e)          # gathered elements read + written, idx read
+    if name == "pdab_pda_group":
+        b, c, n, m, ns = a[:5]
+        return b * (12 * n + 4 * c * n + 12 * m + 4 * (7 + c) * m * ns)
+    if name == "pdab_sa_fused":
+        b, c, n, m, ns = a[:5]
+        return b * (12 * n + 4 * c * n + 12 * m)    # + output, added by the caller (needs cout)
+    if name == "pdab_topk_ctr":
+        b, n, c, k = a[:4]
+        return b * (4 * n * c + 4 * k)
+    if name == "pdab_nms_batched":
+        s, stride = a[:2]
+        return s * (28 * stride + 8 * stride * ((stride + 63) // 64) + 8 * stride)
+    return None
+
+
+def run_gpu_arm(args, cfg, n_points, batch):
+    from pdanet_b200 import _lib
+    from pdanet_b200.runner import SceneRunner
+    from pdanet_b200.synthetic import make_batch
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    assert torch.cuda.is_available(), "bench.py --impl pdab needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    _lib.lib()  # fail loudly if the extension is missing
+
+    runner = SceneRunner(cfg, device=dev, batch_size=batch, num_points=n_points, seed=0)
+    # weak scaling: every rank owns its own `batch` scenes (global scene ids rank*batch ...)
+    host = make_batch(batch, n_points, cfg.POINT_CLOUD_RANGE, first_scene=rank * batch)["points"].pin_memory()
+    dev_points = host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        runner.infer_device(dev_points)
+        runner.infer(host)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- leg 1: device-resident inputs, per-step CUDA events, L2 flushed between steps
+    _lib.launch_counts.clear()
+    _lib.enable_timing(True)
+    step_ms = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        preds = runner.infer_device(dev_points)
+        e.record()
+        e.synchronize()
+        step_ms.append(s.elapsed_time(e))
+    barrier()
+    kernel_ms = _lib.timings_ms()
+    _lib.enable_timing(False)
+    launches = sum(_lib.launch_counts.values())
+    total_ms = max_over_ranks(sum(step_ms))
+    value = world * batch * args.steps / (total_ms / 1e3)
+
+    # ---- leg 2: end to end through SceneRunner.infer — pinned host input, H2D + D2H inside the timed region
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = runner.infer(host)
+        e.record()
+        e.synchronize()
+        e2e_ms.append(s.elapsed_time(e))
+    barrier()
+    e2e_total = max_over_ranks(sum(e2e_ms))
+    e2e_value = world * batch * args.steps / (e2e_total / 1e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel among ours (by time inside the timed steps)
+    hbm_peak, peak_src = peaks()
+    per_kernel = []
+    for key, ms in kernel_ms.items():
+        if not ms:
+            continue
+        avg = sum(ms) / len(ms)
+        nbytes = algorithmic_bytes(key, batch)
+        per_kernel.append({"kernel": key, "calls_per_step": len(ms) / args.steps, "avg_ms": round(avg, 4),
+                           "ms_per_step": round(sum(ms) / args.steps, 4),
+                           "algorithmic_GBps": round(nbytes / avg / 1e6, 2) if nbytes else None})
+    per_kernel.sort(key=lambda r: -r["ms_per_step"])
+    top = per_kernel[0] if per_kernel else None
+    roofline = None
+    if top:
+        achieved = top["algorithmic_GBps"] or 0.0
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": top["avg_ms"],
+                    "share_of_step": round(top["ms_per_step"] / (sum(step_ms) / args.steps), 4)}
+        if top["kernel"].startswith("pdab_fps"):
+            a = [int(x) for x in top["kernel"].partition("(")[2].strip(")").split(",") if x.strip()]
+            b_, n_, m_ = a[:3]
+            roofline["note"] = ("FPS is a serial chain bound by on-chip ALU/shared-memory throughput, not HBM "
+                                "(SURVEY.md §8d); on-chip point-updates/s given beside the HBM figure")
+            roofline["onchip_updates_per_s"] = round(b_ * n_ * (m_ - 1) / (top["avg_ms"] / 1e3), 0)
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        sps, threads, times = time_cpu(cfg, n_points, scenes=args.cpu_scenes)
+        cpu = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_scenes} of the workload's scenes, one {n_points}-point scene per forward "
+                         f"(batch 1), {sum(times):.1f} s of CPU work"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PDA-SSD {args.config} cfg full inference (backbone+vote+centroid aggregation+head+3D NMS), "
+                               f"batch {batch} x {n_points} pts per GPU, random-init weights",
+                   "scenes_per_gpu_per_step": batch, "points_per_scene": n_points, "parallelism": f"scene-sharded x{world}",
+                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
+                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_total / args.steps},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "kernels": per_kernel[:12],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from pdanet_b200.config import load_config
+    cfg = load_config(args.config)
+    n_points = args.points or cfg.NUM_POINTS
+    batch = args.batch or (16 if args.config == "kitti" else 4)
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, n_points, batch)
+    else:
+        run_gpu_arm(args, cfg, n_points, batch)
+
+
+if __name__ == "__main__":
+    main()

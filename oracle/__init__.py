@@ -48,7 +48,7 @@ def _np(t, dtype):
     if isinstance(t, torch.Tensor):
         assert t.device.type == "cpu", "oracle works on CPU tensors"
         assert t.is_contiguous()
-        a = t.numpy()
+        a = t.detach().numpy()
     else:
         a = t
     assert a.dtype == dtype, (a.dtype, dtype)

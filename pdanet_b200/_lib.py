@@ -85,6 +85,40 @@ def check(fn: str, code: int) -> int:
     return code
 
 
+# kernels launched by one call of each entry point (for bench.py's `gpu_launches` count)
+KERNELS_PER_CALL = {"pdab_nms_device": 2, "pdab_nms_batched": 2, "pdab_nms_host": 2}
+
+launch_counts: dict = {}      # entry point -> number of kernels launched through `call`
+_timing = None                # when enabled: entry point -> list of (start_event, end_event)
+
+
+def enable_timing(on: bool = True):
+    """Bracket every C-ABI call with CUDA events on the launching stream (bench.py roofline leg)."""
+    global _timing
+    _timing = {} if on else None
+
+
+def timings_ms() -> dict:
+    """'entry_point(sizes...)' -> list of per-call durations in ms (the events must have completed)."""
+    out = {}
+    for name, pairs in (_timing or {}).items():
+        out[name] = [a.elapsed_time(b) for a, b in pairs]
+    return out
+
+
 def call(fn: str, *args) -> int:
-    """Invoke an int-returning entry point and raise PdabError on a non-zero code."""
-    return check(fn, getattr(lib(), fn)(*args))
+    """Invoke an int-returning entry point and raise PdabError on a non-zero code.
+    By convention the last argument is the cudaStream_t the kernels go to."""
+    f = getattr(lib(), fn)
+    launch_counts[fn] = launch_counts.get(fn, 0) + KERNELS_PER_CALL.get(fn, 1)
+    if _timing is None:
+        return check(fn, f(*args))
+    import torch
+    stream = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.current_stream()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    rc = f(*args)
+    end.record(stream)
+    key = fn + str(tuple(a for a in args[:6] if isinstance(a, int) and 0 <= a < (1 << 24)))  # fn + leading sizes
+    _timing.setdefault(key, []).append((start, end))
+    return check(fn, rc)

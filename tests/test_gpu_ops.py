@@ -1,0 +1,367 @@
+"""GPU parity tests: every op is called through the C ABI (libpdab.so) and compared, on identical
+seeded inputs, with (1) the CPU oracle, (2) the reference's own CUDA kernels rebuilt for sm_100a
+(oracle/_ref) and (3) committed golden vectors.  Indices / copies / keep lists: bit-exact.
+Floating-point features: 1e-3 relative (BASELINE.json north_star), written next to each check."""
+import ctypes as C
+import math
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import torch_ops
+from conftest import GOLDEN
+from util import adversarial_boxes, random_boxes, scene_xyz
+
+pytestmark = pytest.mark.gpu
+
+FEATURE_RTOL = 1e-3  # north_star: "features and box regressions must be within 1e-3 relative"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pdanet_b200 import pointnet2_utils
+    return pointnet2_utils
+
+
+@pytest.fixture(scope="module")
+def nms_utils():
+    from pdanet_b200 import iou3d_nms_utils
+    return iou3d_nms_utils
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def seed_of(tag):
+    return zlib.crc32(tag.encode()) % 1000
+
+
+# ------------------------------------------------------------------ reference-kernel helpers (oracle/_ref)
+
+def ref_fps(lib, xyz, m):
+    B, N, _ = xyz.shape
+    x = dev(xyz)
+    temp = torch.full((B, N), 1e10, device="cuda")
+    idx = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    assert lib.ref_fps(B, N, m, C.c_void_p(x.data_ptr()), C.c_void_p(temp.data_ptr()), C.c_void_p(idx.data_ptr())) == 0
+    return idx.cpu(), temp.cpu()
+
+
+def ref_ball_query(lib, r, ns, xyz, new_xyz):
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    x, c = dev(xyz), dev(new_xyz)
+    idx = torch.zeros(B, M, ns, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    assert lib.ref_ball_query(B, N, M, C.c_float(r), ns, C.c_void_p(c.data_ptr()), C.c_void_p(x.data_ptr()),
+                              C.c_void_p(idx.data_ptr())) == 0
+    return idx.cpu()
+
+
+# ------------------------------------------------------------------ FPS
+
+FPS_CASES = [
+    # (tag, B, N, m, kwargs)
+    ("kitti_L1", 2, 4096, 1024, {}),
+    ("kitti_L0_small_m", 2, 16384, 512, {}),
+    ("duplicates", 2, 4096, 512, dict(duplicate_frac=0.3)),
+    ("grid_ties", 2, 2048, 600, dict(quantize=2.0, duplicate_frac=0.1)),
+    ("ragged_1500", 1, 1500, 300, dict(quantize=1.0)),
+    ("ragged_1000_bs512", 2, 1000, 200, dict(quantize=1.0)),
+    ("tiny_37", 3, 37, 37, dict(quantize=4.0)),
+    ("all_equal", 1, 2048, 64, dict(lo=(1.0, 1.0, 1.0), hi=(1.0, 1.0, 1.0))),
+    ("n_equals_m", 1, 256, 256, {}),
+    ("cluster2_20000", 1, 20000, 256, dict(duplicate_frac=0.05)),
+    ("cluster4_once", 1, 65536, 128, {}),
+]
+
+
+@pytest.mark.parametrize("tag,B,N,m,kw", FPS_CASES, ids=[c[0] for c in FPS_CASES])
+def test_fps_bit_exact_vs_oracle(ops, tag, B, N, m, kw):
+    xyz = scene_xyz(seed_of(tag), B, N, **kw)
+    want = oracle.fps(xyz, m)
+    got = ops.furthest_point_sample(dev(xyz), m).cpu()
+    assert got.dtype == torch.int32
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("tag,B,N,m,kw", FPS_CASES, ids=[c[0] for c in FPS_CASES])
+def test_fps_bit_exact_vs_reference_kernel(ops, ref_pointnet2, tag, B, N, m, kw):
+    from pdanet_b200 import pointnet2_batch_cuda
+    xyz = scene_xyz(seed_of(tag), B, N, **kw)
+    want_idx, want_temp = ref_fps(ref_pointnet2, xyz, m)
+    x = dev(xyz)
+    temp = torch.full((B, N), 1e10, device="cuda")
+    idx = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    pointnet2_batch_cuda.farthest_point_sampling_wrapper(B, N, m, x, temp, idx)
+    assert torch.equal(idx.cpu(), want_idx)
+    assert torch.equal(temp.cpu(), want_temp)  # the scratch buffer ends in the same state too
+
+
+def test_fps_full_kitti_and_once_sizes_properties(ops):
+    """At BASELINE sizes the oracle is too slow to run per test: check size-independent properties —
+    first index 0, all distinct, non-increasing selection distance, and agreement of the prefix with the oracle."""
+    for N, m, prefix in [(16384, 4096, 96), (65536, 16384, 24)]:
+        xyz = scene_xyz(N, 1, N)
+        idx = ops.furthest_point_sample(dev(xyz), m).cpu()[0].long()
+        assert idx[0] == 0 and idx.unique().numel() == m
+        assert torch.equal(idx[:prefix].int(), oracle.fps(xyz, prefix)[0])
+        p = xyz[0][idx][:2048].double().cuda()
+        d = torch.cdist(p, p)
+        d = d + torch.triu(torch.full_like(d, 1e30))
+        mins = d[1:].min(dim=1)[0].cpu()
+        assert (mins[:-1] >= mins[1:] - 1e-9).all()
+
+
+def test_fps_with_dist_bit_exact(ops):
+    g = torch.Generator().manual_seed(5)
+    pts = torch.randn(2, 700, 6, generator=g)
+    dist = torch.cdist(pts, pts).pow(2).contiguous()
+    want = oracle.fps_with_dist(dist, 128)
+    got = ops.furthest_point_sample_with_dist(dev(dist), 128).cpu()
+    assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------ ball query / group / gather
+
+BQ_CASES = [
+    ("kitti_L0_r0.2", 2, 16384, 1024, 0.2, 16, {}),
+    ("kitti_L0_r0.8", 2, 16384, 512, 0.8, 32, {}),
+    ("dense_r4.8", 2, 1024, 512, 4.8, 32, {}),
+    ("ns64", 1, 2048, 300, 12.8, 64, {}),
+    ("ragged", 3, 1000, 77, 2.0, 16, dict(quantize=0.5)),
+    ("ties_on_radius", 2, 1500, 130, 2.0, 8, dict(quantize=1.0)),
+    ("duplicates", 2, 2048, 128, 1.0, 16, dict(duplicate_frac=0.4)),
+]
+
+
+@pytest.mark.parametrize("tag,B,N,M,r,ns,kw", BQ_CASES, ids=[c[0] for c in BQ_CASES])
+def test_ball_query_bit_exact(ops, tag, B, N, M, r, ns, kw):
+    xyz = scene_xyz(seed_of(tag), B, N, **kw)
+    new_xyz = xyz[:, torch.randperm(N, generator=torch.Generator().manual_seed(1))[:M]].contiguous()
+    new_xyz[:, -1] = 1e4  # one empty ball per scene
+    want = oracle.ball_query(r, ns, xyz, new_xyz)
+    got = ops.ball_query(r, ns, dev(xyz), dev(new_xyz)).cpu()
+    assert torch.equal(got, want)
+    assert (got[:, -1] == 0).all()
+
+
+@pytest.mark.parametrize("tag,B,N,M,r,ns,kw", BQ_CASES[:4], ids=[c[0] for c in BQ_CASES[:4]])
+def test_ball_query_bit_exact_vs_reference_kernel(ops, ref_pointnet2, tag, B, N, M, r, ns, kw):
+    xyz = scene_xyz(seed_of(tag), B, N, **kw)
+    new_xyz = xyz[:, :M].contiguous()
+    want = ref_ball_query(ref_pointnet2, r, ns, xyz, new_xyz)
+    got = ops.ball_query(r, ns, dev(xyz), dev(new_xyz)).cpu()
+    assert torch.equal(got, want)
+
+
+def test_ball_query_dilated_bit_exact(ops):
+    xyz = scene_xyz(21, 2, 1200, quantize=0.5)
+    new_xyz = xyz[:, :100].contiguous()
+    want = oracle.ball_query_dilated(3.0, 1.0, 16, xyz, new_xyz)
+    got = ops.ball_query_dilated(3.0, 1.0, 16, dev(xyz), dev(new_xyz)).cpu()
+    assert torch.equal(got, want)
+
+
+def test_group_gather_exact_and_backward(ops):
+    g = torch.Generator().manual_seed(7)
+    for B, Cc, N, M, ns in [(2, 3, 4096, 1024, 16), (2, 67, 1000, 130, 32), (1, 256, 512, 256, 32)]:
+        feats = torch.randn(B, Cc, N, generator=g)
+        idx3 = torch.randint(0, N, (B, M, ns), generator=g, dtype=torch.int32)
+        idx2 = torch.randint(0, N, (B, M), generator=g, dtype=torch.int32)
+        f = dev(feats).requires_grad_(True)
+        out = ops.grouping_operation(f, dev(idx3))
+        assert torch.equal(out.detach().cpu(), oracle.group(feats, idx3))
+        out.backward(torch.ones_like(out))
+        want = torch.zeros(B, Cc, N)
+        oracle.group_points_grad_wrapper(B, Cc, N, M, ns, torch.ones(B, Cc, M, ns), idx3, want)
+        assert torch.allclose(f.grad.cpu(), want)
+        f2 = dev(feats).requires_grad_(True)
+        out2 = ops.gather_operation(f2, dev(idx2))
+        assert torch.equal(out2.detach().cpu(), oracle.gather(feats, idx2))
+        out2.sum().backward()
+        want2 = torch.zeros(B, Cc, N)
+        oracle.gather_points_grad_wrapper(B, Cc, N, M, torch.ones(B, Cc, M), idx2, want2)
+        assert torch.allclose(f2.grad.cpu(), want2)
+
+
+def test_query_and_group_module_matches_oracle(ops):
+    xyz = scene_xyz(31, 2, 2048, hi=(20.0, 20.0, 1.0), lo=(0.0, 0.0, -1.0))
+    feats = torch.randn(2, 5, 2048, generator=torch.Generator().manual_seed(1))
+    new_xyz = xyz[:, :200].contiguous()
+    want = torch_ops.QueryAndGroup(1.6, 16)(xyz, new_xyz, feats)
+    got = ops.QueryAndGroup(1.6, 16)(dev(xyz), dev(new_xyz), dev(feats)).cpu()
+    assert torch.equal(got, want)  # gathers and one fp32 subtraction: exact
+
+
+# ------------------------------------------------------------------ fused ops
+
+def test_topk_ctr_bit_exact(ops):
+    g = torch.Generator().manual_seed(2)
+    for B, N, Cc, k in [(4, 1024, 3, 512), (4, 512, 3, 256), (2, 4096, 5, 2048), (1, 777, 1, 100), (2, 300, 3, 300)]:
+        cls = torch.randn(B, N, Cc, generator=g) * 3
+        cls[:, ::7] = 5.0  # heavy ties, some of them straddling the k-th place
+        want = oracle.topk_ctr(cls, k)
+        got = ops.topk_ctr_sample(dev(cls), k).cpu()
+        assert torch.equal(got, want)
+        score = torch.sigmoid(cls.max(-1)[0])
+        assert torch.equal(torch.gather(score, 1, got.long()), torch.topk(score, k, dim=-1)[0])
+
+
+def test_pda_group_matches_oracle(ops):
+    for B, Cc, N, M, r, ns in [(2, 64, 4096, 1024, 0.8, 16), (2, 128, 1024, 512, 4.8, 32), (1, 6, 700, 130, 1.6, 16)]:
+        xyz = scene_xyz(N + M, B, N, hi=(30.0, 30.0, 1.0), lo=(0.0, 0.0, -1.0))
+        feats = torch.randn(B, Cc, N, generator=torch.Generator().manual_seed(3))
+        new_xyz = xyz[:, :M].contiguous()
+        want, want_idx = oracle.pda_group(r, ns, xyz, new_xyz, feats)
+        got, got_idx = ops.pda_group(r, ns, dev(xyz), dev(new_xyz), dev(feats), return_idx=True)
+        got, got_idx = got.cpu(), got_idx.cpu()
+        assert torch.equal(got_idx, want_idx)
+        assert torch.equal(got[:, :3], want[:, :3]) and torch.equal(got[:, 7:], want[:, 7:])  # pure gathers
+        assert torch.allclose(got[:, 3:7], want[:, 3:7], rtol=FEATURE_RTOL, atol=1e-7)
+        module = ops.QueryAndGroup_alone_grouped_density_directional(r, ns)
+        with torch.no_grad():
+            assert torch.equal(module(dev(xyz), dev(new_xyz), dev(feats)).cpu(), got)
+
+
+def test_sa_fused_matches_oracle(ops):
+    g = torch.Generator().manual_seed(4)
+    for dims, ns, r in [([4, 16, 16, 32], 16, 0.8), ([4, 32, 32, 64], 32, 1.6)]:
+        B, N, M = 2, 4096, 700
+        xyz = scene_xyz(M, B, N, hi=(20.0, 20.0, 1.0), lo=(0.0, 0.0, -1.0))
+        feats = torch.rand(B, 1, N, generator=g)
+        new_xyz = xyz[:, :M].contiguous()
+        new_xyz[:, -1] = 1e4  # empty ball: groups point 0
+        ws = [torch.randn(dims[i + 1], dims[i], generator=g) / math.sqrt(dims[i]) for i in range(3)]
+        bs = [torch.randn(dims[i + 1], generator=g) * 0.1 for i in range(3)]
+        assert ops.sa_fused_supported(dims[0], dims[1:], ns)
+        want = oracle.sa_mlp_maxpool(r, ns, xyz, new_xyz, feats, ws, bs)
+        got = ops.sa_fused(r, ns, dev(xyz), dev(new_xyz), dev(feats), [dev(w) for w in ws], [dev(b) for b in bs]).cpu()
+        assert torch.allclose(got, want, rtol=FEATURE_RTOL, atol=1e-5)
+
+
+# ------------------------------------------------------------------ IoU / NMS
+
+NMS_CASES = [("kitti_256", random_boxes, 256, 0.01, (40.0, 40.0, 2.0)), ("once_1024", random_boxes, 1024, 0.1, (60.0, 60.0, 2.0)),
+             ("ragged_1000", random_boxes, 1000, 0.1, (30.0, 30.0, 2.0)), ("dense_4096", random_boxes, 4096, 0.25, (80.0, 80.0, 2.0)),
+             ("tiny_3", random_boxes, 3, 0.1, (2.0, 2.0, 1.0)), ("adversarial_512", adversarial_boxes, 512, 0.1, None)]
+
+
+def _boxes(maker, n, extent, seed):
+    return maker(seed, n) if extent is None else maker(seed, n, extent=extent)
+
+
+@pytest.mark.parametrize("tag,maker,n,thresh,extent", NMS_CASES, ids=[c[0] for c in NMS_CASES])
+def test_iou_and_nms_bit_exact_vs_reference_kernel(nms_utils, ref_iou3d, tag, maker, n, thresh, extent):
+    boxes = _boxes(maker, n, extent, 40 + n)
+    scores = torch.rand(n, generator=torch.Generator().manual_seed(n))
+    b = dev(boxes)
+    if n <= 1024:
+        want_iou = torch.zeros(n, n, device="cuda")
+        ref_iou3d.boxes_iou_bev_gpu(b, b, want_iou)
+        got_iou = nms_utils.boxes_iou_bev(b, b)
+        assert torch.equal(torch.nan_to_num(got_iou, nan=-1.0), torch.nan_to_num(want_iou, nan=-1.0))
+    order = scores.sort(dim=0, descending=True, stable=True)[1]
+    sb = dev(boxes[order])
+    keep = torch.zeros(n, dtype=torch.int64)
+    num = ref_iou3d.nms_gpu(sb, keep, thresh)
+    want = order[keep[:num]]
+    got, _ = nms_utils.nms_gpu(b, dev(scores), thresh)
+    assert torch.equal(got.cpu(), want)
+    assert 0 < num <= n
+
+
+@pytest.mark.parametrize("tag,maker,n,thresh,extent", NMS_CASES, ids=[c[0] for c in NMS_CASES])
+def test_iou_close_to_oracle_and_nms_equal_when_clear_of_threshold(nms_utils, tag, maker, n, thresh, extent):
+    boxes = _boxes(maker, n, extent, 40 + n)[: min(n, 600)].contiguous()
+    n = boxes.shape[0]
+    want_iou = torch.zeros(n, n)
+    oracle.boxes_iou_bev_cpu(boxes, boxes, want_iou)
+    got_iou = nms_utils.boxes_iou_bev(dev(boxes), dev(boxes)).cpu()
+    assert torch.allclose(got_iou, want_iou, atol=2e-5)  # libm vs libdevice trig, FMA contraction on the GPU
+    if ((want_iou - thresh).abs() < 1e-4).any():
+        return  # a borderline pair may legitimately flip between CPU and GPU arithmetic
+    scores = torch.rand(n, generator=torch.Generator().manual_seed(n))
+    want = oracle.nms(boxes, scores, thresh)
+    got, _ = nms_utils.nms_gpu(dev(boxes), dev(scores), thresh)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_nms_batched_equals_per_scene(nms_utils):
+    S, stride, thresh = 5, 300, 0.1
+    counts = torch.tensor([300, 256, 1, 0, 129], dtype=torch.int32)
+    boxes = torch.stack([random_boxes(70 + s, stride, extent=(25.0, 25.0, 2.0)) for s in range(S)])
+    keep, num = nms_utils.nms_batched(dev(boxes), counts.cuda(), thresh)
+    keep, num = keep.cpu(), num.cpu()
+    for s in range(S):
+        c = int(counts[s])
+        k = torch.zeros(max(c, 1), dtype=torch.int64)
+        want_num = oracle.nms_gpu(boxes[s, :c].contiguous(), k, thresh) if c else 0
+        if ((oracle.torch_ops.nms_utils.boxes_iou_bev(boxes[s, :c], boxes[s, :c]) - thresh).abs() < 1e-4).any():
+            continue
+        assert int(num[s]) == want_num
+        assert keep[s, :want_num].tolist() == k[:want_num].tolist()
+
+
+def test_nms_normal_and_empty(nms_utils):
+    boxes = random_boxes(9, 200, extent=(15.0, 15.0, 1.0), heading=False)
+    scores = torch.rand(200, generator=torch.Generator().manual_seed(1))
+    want = torch_ops.nms_utils.nms_normal_gpu(boxes, scores, 0.3)[0]
+    got, _ = nms_utils.nms_normal_gpu(dev(boxes), dev(scores), 0.3)
+    assert torch.equal(got.cpu(), want)
+    got, _ = nms_utils.nms_gpu(torch.zeros(0, 7, device="cuda"), torch.zeros(0, device="cuda"), 0.1)
+    assert got.numel() == 0
+
+
+# ------------------------------------------------------------------ error behaviour at the boundary
+
+def test_boundary_rejects_bad_tensors():
+    from pdanet_b200 import pointnet2_batch_cuda as pn
+    xyz = torch.rand(1, 64, 3)
+    with pytest.raises(RuntimeError):  # CPU tensor: the reference would exit(-1) (PB/src/ball_query.cpp:17-29)
+        pn.farthest_point_sampling_wrapper(1, 64, 8, xyz, torch.zeros(1, 64), torch.zeros(1, 8, dtype=torch.int32))
+    x = xyz.cuda()
+    with pytest.raises(RuntimeError):  # wrong index dtype
+        pn.farthest_point_sampling_wrapper(1, 64, 8, x, torch.zeros(1, 64).cuda(), torch.zeros(1, 8).long().cuda())
+    with pytest.raises(RuntimeError):  # non-contiguous
+        pn.ball_query_wrapper(1, 64, 64, 0.5, 4, x.transpose(1, 2), x, torch.zeros(1, 64, 4, dtype=torch.int32).cuda())
+
+
+# ------------------------------------------------------------------ golden vectors made by the reference kernels
+
+def test_fps_and_ball_query_equal_committed_reference_golden(ops):
+    for name in ("ref_fps.npz", "ref_ball_group.npz"):
+        if not (GOLDEN / name).exists():
+            pytest.skip("golden vectors not generated yet")
+    z = np.load(GOLDEN / "ref_fps.npz")
+    for tag in [k[4:] for k in z.files if k.startswith("xyz_")]:
+        xyz = torch.from_numpy(z[f"xyz_{tag}"])
+        want = torch.from_numpy(z[f"idx_{tag}"])
+        assert torch.equal(ops.furthest_point_sample(dev(xyz), want.shape[1]).cpu(), want), tag
+    z = np.load(GOLDEN / "ref_ball_group.npz")
+    for tag in [k[4:] for k in z.files if k.startswith("xyz_")]:
+        xyz, new_xyz = torch.from_numpy(z[f"xyz_{tag}"]), torch.from_numpy(z[f"new_{tag}"])
+        idx = ops.ball_query(float(z[f"radius_{tag}"]), int(z[f"nsample_{tag}"]), dev(xyz), dev(new_xyz))
+        assert torch.equal(idx.cpu(), torch.from_numpy(z[f"idx_{tag}"])), tag
+        grouped = ops.grouping_operation(dev(torch.from_numpy(z[f"feat_{tag}"])), idx)
+        assert torch.equal(grouped.cpu(), torch.from_numpy(z[f"grouped_{tag}"])), tag
+
+
+def test_nms_equals_committed_reference_golden(nms_utils):
+    if not (GOLDEN / "ref_nms.npz").exists():
+        pytest.skip("golden vectors not generated yet")
+    z = np.load(GOLDEN / "ref_nms.npz")
+    for tag in [k[6:] for k in z.files if k.startswith("boxes_")]:
+        boxes = dev(torch.from_numpy(z[f"boxes_{tag}"]))  # already sorted by score
+        n = boxes.shape[0]
+        scores = torch.arange(n, 0, -1, dtype=torch.float32, device="cuda")
+        got, _ = nms_utils.nms_gpu(boxes, scores, float(z[f"thresh_{tag}"]))
+        assert got.cpu().tolist() == z[f"keep_{tag}"].tolist(), tag
+        iou = nms_utils.boxes_iou_bev(boxes, boxes).cpu()
+        assert torch.equal(iou, torch.from_numpy(z[f"iou_{tag}"])), tag
