@@ -22,6 +22,10 @@
 
 namespace cg = cooperative_groups;
 
+namespace pdab {
+int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream);
+}
+
 namespace {
 
 constexpr int kThreads = 1024;
@@ -234,6 +238,11 @@ int dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaS
     }
     if (per > 16 || (MATRIX && CL > 1)) return PDAB_EUNSUPPORTED;
     const int L = ref_log2_block(n);
+    if (!MATRIX && n >= 1024 && n <= 16384 && m > 64) {
+        // spatially pruned variant: same results, ~N ln m instead of N m point updates
+        const int rc = pdab::fps_pruned(b, n, m, src, temp, idx, L, stream);
+        if (rc != PDAB_EUNSUPPORTED) return rc;
+    }
     if (per <= 1) return launch<1, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
     if (per <= 2) return launch<2, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
     if (per <= 4) return launch<4, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);

@@ -1,0 +1,304 @@
+// Pruned farthest-point sampling for sm_100a (N <= 16384 per scene, one CTA per scene).
+//
+// FPS is a serial chain of m-1 steps; the plain kernel (fps.cu) touches all N points in every
+// step although a new sample only lowers the min-distance of the points in its own neighbourhood
+// (about N/j of them at step j).  Here the points of a scene are Morton-sorted once into buckets
+// of 32 spatially coherent points (one warp-wide register each); every step
+//   1. tests each bucket's bounding box against the new sample: if the box is provably farther
+//      than the bucket's largest min-distance, no point in it can change and the bucket is skipped;
+//   2. updates only the surviving buckets (coordinates from shared memory, min-distances in
+//      registers) and refreshes their cached (max, tie-key, slot) candidate with two REDUX;
+//   3. reduces the 8 warps' cached candidates (REDUX + one named barrier) to the next sample.
+// Total work drops from N*m to about N*ln(m) point updates; what remains per step is the fixed
+// cost of the box tests and of the 2-level argmax.
+//
+// Exactness (same contract as fps.cu / include/pdab.h): every distance that IS evaluated uses the
+// reference's compiled fp32 op order; skipping is conservative — a bucket is skipped only when
+// fl(LB)*(1-2^-20) >= max min-distance of the bucket, where LB is the squared distance to the box;
+// the fp32 evaluation errors of LB and of a point distance are each below 4*2^-24 relative, so a
+// skipped point satisfies fl(d) >= its stored min-distance and fminf would have left it unchanged.
+// The argmax key [dist bits | ~tiekey(k)] is the one fps.cu uses, on ORIGINAL point indices, so
+// the reference's tie rule (argmin (bitrev_L(k mod BS), k) over maxima) is preserved under the
+// permutation.  Preconditions: finite coordinates, temp >= 0 (the caller fills 1e10).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;            // warps that run the main loop
+constexpr int kLoopThreads = kWarps * 32;
+constexpr int kInitThreads = kLoopThreads;  // the one-off Morton sort runs on the same 8 warps (keeps 255 regs/thread)
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+__device__ __forceinline__ unsigned tie_key(int k, int L) {
+    if (L == 0) return (unsigned)k;
+    return __brev((unsigned)k & ((1u << L) - 1u)) | ((unsigned)k >> L);
+}
+__device__ __forceinline__ int tie_key_decode(unsigned key, int L) {
+    if (L == 0) return (int)key;
+    const unsigned lowmask = (1u << (32 - L)) - 1u;
+    return (int)(((key & lowmask) << L) | __brev(key & ~lowmask));
+}
+
+__device__ __forceinline__ int ordered_int(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_int_inv(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__device__ __forceinline__ void loop_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kLoopThreads) : "memory"); }
+
+struct __align__(16) WarpBest {
+    unsigned long long key;
+    int slot;
+    int pad;
+};
+
+// BPW: buckets per warp.  Capacity = kWarps * BPW * 32 points.
+template <int BPW>
+__global__ void __launch_bounds__(kInitThreads, 1)
+fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
+                  int *__restrict__ idx_all, int L) {
+    constexpr int CAP = kWarps * BPW * 32;
+    constexpr int BPL = (BPW + 31) / 32;  // buckets tested per lane
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // region A: sort keys (CAP x u64), later the coordinates (3 x CAP x f32); region B: original index per slot
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *sx = reinterpret_cast<float *>(smem_raw), *sy = sx + CAP, *sz = sy + CAP;
+    unsigned short *sorig = reinterpret_cast<unsigned short *>(smem_raw + (size_t)12 * CAP);
+    __shared__ int sbox[6];
+    __shared__ WarpBest red[2][kWarps];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int scene = blockIdx.x;
+    const float *xyz = xyz_all + (size_t)scene * n * 3;
+    float *temp = temp_all + (size_t)scene * n;
+    int *idxs = idx_all + (size_t)scene * m;
+
+    // ---- 0. scene bounding box -------------------------------------------------------------
+    if (t < 3) sbox[t] = 0x7fffffff;
+    else if (t < 6) sbox[t] = (int)0x80000000;
+    __syncthreads();
+    {
+        float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        for (int k = t; k < n; k += kInitThreads)
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float v = __ldg(xyz + (size_t)k * 3 + a);
+                lo[a] = fminf(lo[a], v);
+                hi[a] = fmaxf(hi[a], v);
+            }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int l = __reduce_min_sync(0xffffffffu, ordered_int(lo[a]));
+            const int h = __reduce_max_sync(0xffffffffu, ordered_int(hi[a]));
+            if (lane == 0) {
+                atomicMin(&sbox[a], l);
+                atomicMax(&sbox[3 + a], h);
+            }
+        }
+    }
+    __syncthreads();
+    const float bx = ordered_int_inv(sbox[0]), by = ordered_int_inv(sbox[1]), bz = ordered_int_inv(sbox[2]);
+    const float ext = fmaxf(fmaxf(ordered_int_inv(sbox[3]) - bx, ordered_int_inv(sbox[4]) - by),
+                            ordered_int_inv(sbox[5]) - bz);
+    const float qscale = ext > 0.f ? 1023.0f / ext : 0.f;  // isotropic: buckets are compact in real space
+
+    // ---- 1. Morton keys + bitonic sort (ascending; padding keys sort last) ---------------------
+    for (int s = t; s < CAP; s += kInitThreads) {
+        unsigned long long key = ~0ull;
+        if (s < n) {
+            const unsigned qx = min(1023u, (unsigned)((__ldg(xyz + (size_t)s * 3 + 0) - bx) * qscale));
+            const unsigned qy = min(1023u, (unsigned)((__ldg(xyz + (size_t)s * 3 + 1) - by) * qscale));
+            const unsigned qz = min(1023u, (unsigned)((__ldg(xyz + (size_t)s * 3 + 2) - bz) * qscale));
+            const unsigned code = spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2);
+            key = ((unsigned long long)code << 32) | (unsigned)s;
+        }
+        skey[s] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= CAP; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = t; i < CAP / 2; i += kInitThreads) {
+                const int a = 2 * i - (i & (stride - 1));
+                const int b = a + stride;
+                const bool up = (a & size) == 0;
+                const unsigned long long ka = skey[a], kb = skey[b];
+                if ((ka > kb) == up) {
+                    skey[a] = kb;
+                    skey[b] = ka;
+                }
+            }
+            __syncthreads();
+        }
+    // ---- 2. slot -> original index, then coordinates in slot order (region A is reused) -------
+    int korig[CAP / kInitThreads];
+#pragma unroll
+    for (int q = 0; q < CAP / kInitThreads; q++) korig[q] = (int)(unsigned)skey[t + q * kInitThreads];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CAP / kInitThreads; q++) {
+        const int s = t + q * kInitThreads;
+        const bool valid = s < n;  // valid keys sort before the padding
+        sorig[s] = valid ? (unsigned short)korig[q] : (unsigned short)0;
+        sx[s] = valid ? __ldg(xyz + (size_t)korig[q] * 3 + 0) : 0.f;
+        sy[s] = valid ? __ldg(xyz + (size_t)korig[q] * 3 + 1) : 0.f;
+        sz[s] = valid ? __ldg(xyz + (size_t)korig[q] * 3 + 2) : 0.f;
+    }
+    __syncthreads();
+
+    // ---- 3. per-lane state: min-distances of one point of each owned bucket, cached bucket data -
+    // warp w owns buckets b = w + kWarps*i (interleaved: a neighbourhood's buckets spread over warps);
+    // lane l holds slot 32*b + l.  Bucket i is TESTED by lane (i % 32), register (i / 32).
+    float d[BPW];
+    float blo[BPL][3], bhi[BPL][3], bmax[BPL];
+    unsigned long long bkey[BPL];
+    int bslot[BPL];
+#pragma unroll
+    for (int r = 0; r < BPL; r++) {
+        bmax[r] = -1.f;
+        bkey[r] = 0ull;
+        bslot[r] = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) blo[r][a] = bhi[r][a] = 0.f;
+    }
+
+    auto refresh = [&](int i, float dv, int slot) {
+        // cached candidate of bucket i: largest min-distance, reference tie rule among equals
+        const bool valid = dv >= 0.f;
+        const unsigned hi = valid ? __float_as_uint(dv) : 0u;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const bool top = valid && hi == mh;
+        const unsigned lo = top ? ~tie_key((int)sorig[slot], L) : 0u;
+        const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+        const unsigned who = __ballot_sync(0xffffffffu, top && lo == ml);
+        if (lane == (i & 31)) {
+            const bool any = who != 0u;
+            bmax[i >> 5] = any ? __uint_as_float(mh) : -1.f;
+            bkey[i >> 5] = any ? (((unsigned long long)mh << 32) | ml) : 0ull;
+            bslot[i >> 5] = (slot & ~31) + (any ? __ffs(who) - 1 : 0);
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < BPW; i++) {
+        const int slot = 32 * (warp + kWarps * i) + lane;
+        const bool valid = slot < n;
+        d[i] = valid ? temp[sorig[slot]] : -1.f;
+        float lo[3], hi[3];
+        lo[0] = hi[0] = sx[slot];
+        lo[1] = hi[1] = sy[slot];
+        lo[2] = hi[2] = sz[slot];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int l = __reduce_min_sync(0xffffffffu, valid ? ordered_int(lo[a]) : 0x7fffffff);
+            const int h = __reduce_max_sync(0xffffffffu, valid ? ordered_int(hi[a]) : (int)0x80000000);
+            if (lane == (i & 31)) {
+                blo[i >> 5][a] = ordered_int_inv(l);
+                bhi[i >> 5][a] = ordered_int_inv(h);
+            }
+        }
+        refresh(i, d[i], slot);
+    }
+
+    int old = 0;
+    float x1 = __ldg(xyz + 0), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
+    if (t == 0) idxs[0] = 0;
+
+    int buf = 0;
+    for (int it = 1; it < m; it++) {
+        // -- box tests ---------------------------------------------------------------------------
+        unsigned active[BPL];
+#pragma unroll
+        for (int r = 0; r < BPL; r++) {
+            const float ex = fmaxf(fmaxf(blo[r][0] - x1, x1 - bhi[r][0]), 0.f);
+            const float ey = fmaxf(fmaxf(blo[r][1] - y1, y1 - bhi[r][1]), 0.f);
+            const float ez = fmaxf(fmaxf(blo[r][2] - z1, z1 - bhi[r][2]), 0.f);
+            const float lb = ex * ex + ey * ey + ez * ez;
+            // empty / unowned buckets carry bmax = -1 and are never active
+            active[r] = __ballot_sync(0xffffffffu, !(lb * 0.99999905f >= bmax[r]));
+        }
+        // -- update the surviving buckets -----------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < BPW; i++) {
+            if ((active[i >> 5] >> (i & 31)) & 1u) {  // warp-uniform
+                const int slot = 32 * (warp + kWarps * i) + lane;
+                if (d[i] >= 0.f) d[i] = fminf(pdab::sqdist3(sx[slot], sy[slot], sz[slot], x1, y1, z1), d[i]);
+                refresh(i, d[i], slot);
+            }
+        }
+        // -- argmax over cached candidates: lane -> warp -> CTA -------------------------------------
+        unsigned long long mykey = bkey[0];
+        int myslot = bslot[0];
+#pragma unroll
+        for (int r = 1; r < BPL; r++)
+            if (bkey[r] > mykey) {
+                mykey = bkey[r];
+                myslot = bslot[r];
+            }
+        const unsigned long long wkey = warp_max_u64(mykey);
+        const unsigned owner = __ballot_sync(0xffffffffu, mykey == wkey);
+        const int wslot = __shfl_sync(0xffffffffu, myslot, __ffs(owner) - 1);
+        if (lane == 0) {
+            red[buf][warp].key = wkey;
+            red[buf][warp].slot = wslot;
+        }
+        loop_barrier();
+        const unsigned long long rkey = lane < kWarps ? red[buf][lane].key : 0ull;
+        const int rslot = lane < kWarps ? red[buf][lane].slot : 0;
+        const unsigned long long best = warp_max_u64(rkey);
+        const unsigned src = __ballot_sync(0xffffffffu, rkey == best && lane < kWarps);
+        const int slot = __shfl_sync(0xffffffffu, rslot, __ffs(src) - 1);
+        old = tie_key_decode(~(unsigned)best, L);
+        x1 = sx[slot];
+        y1 = sy[slot];
+        z1 = sz[slot];
+        if (t == 0) idxs[it] = old;
+        buf ^= 1;
+    }
+
+#pragma unroll
+    for (int i = 0; i < BPW; i++) {
+        const int slot = 32 * (warp + kWarps * i) + lane;
+        if (slot < n) temp[sorig[slot]] = d[i];
+    }
+}
+
+template <int BPW>
+int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
+    constexpr int CAP = kWarps * BPW * 32;
+    const size_t smem = (size_t)12 * CAP + (size_t)2 * CAP;
+    auto kern = fps_pruned_kernel<BPW>;
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<b, kInitThreads, smem, stream>>>(n, m, xyz, temp, idx, L);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+namespace pdab {
+
+// Returns PDAB_EUNSUPPORTED when the pruned kernel does not cover the size (caller falls back to fps.cu).
+int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
+    if (n > 16384 || n < 1) return PDAB_EUNSUPPORTED;
+    if (n <= 2048) return launch<8>(b, n, m, xyz, temp, idx, L, stream);
+    if (n <= 4096) return launch<16>(b, n, m, xyz, temp, idx, L, stream);
+    if (n <= 8192) return launch<32>(b, n, m, xyz, temp, idx, L, stream);
+    return launch<64>(b, n, m, xyz, temp, idx, L, stream);
+}
+
+}  // namespace pdab

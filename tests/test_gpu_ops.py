@@ -77,6 +77,11 @@ FPS_CASES = [
     ("tiny_37", 3, 37, 37, dict(quantize=4.0)),
     ("all_equal", 1, 2048, 64, dict(lo=(1.0, 1.0, 1.0), hi=(1.0, 1.0, 1.0))),
     ("n_equals_m", 1, 256, 256, {}),
+    ("kitti_L0_full", 1, 16384, 4096, {}),
+    ("kitti_L0_dups", 1, 16384, 2048, dict(duplicate_frac=0.3)),
+    ("grid_8192", 1, 8192, 1500, dict(quantize=1.0)),
+    ("n_1024_m_900", 2, 1024, 900, dict(quantize=2.0)),
+    ("flat_plane", 1, 6000, 700, dict(lo=(0.0, -40.0, -1.7), hi=(70.4, 40.0, -1.7))),
     ("cluster2_20000", 1, 20000, 256, dict(duplicate_frac=0.05)),
     ("cluster4_once", 1, 65536, 128, {}),
 ]
