@@ -20,13 +20,12 @@
 // The argmax key [dist bits | ~tiekey(k)] is the one fps.cu uses, on ORIGINAL point indices, so
 // the reference's tie rule (argmin (bitrev_L(k mod BS), k) over maxima) is preserved under the
 // permutation.  Preconditions: finite coordinates, temp >= 0 (the caller fills 1e10).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kWarps = 8;            // warps that run the main loop
-constexpr int kLoopThreads = kWarps * 32;
-constexpr int kInitThreads = kLoopThreads;  // the one-off Morton sort runs on the same 8 warps (keeps 255 regs/thread)
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
     const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
@@ -59,7 +58,6 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every 
     return v;
 }
 
-__device__ __forceinline__ void loop_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kLoopThreads) : "memory"); }
 
 struct __align__(16) WarpBest {
     unsigned long long key;
@@ -67,13 +65,19 @@ struct __align__(16) WarpBest {
     int pad;
 };
 
-// BPW: buckets per warp.  Capacity = kWarps * BPW * 32 points.
-template <int BPW>
-__global__ void __launch_bounds__(kInitThreads, 1)
+// WARPS warps per CTA, BPW buckets per warp (BPW <= 32).  Capacity = WARPS * BPW * 32 points.
+// The per-bucket update is replicated BPW times in the loop body (the min-distances live in
+// registers and registers cannot be indexed dynamically), so BPW also sets the code size of the
+// loop: BPW = 64 on 8 warps measured 3.4 us/step because the 60 KB body thrashed the instruction
+// cache; 16 buckets on 32 warps keeps it near 14 KB.
+template <int WARPS, int BPW>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
                   int *__restrict__ idx_all, int L) {
+    constexpr int kWarps = WARPS, kInitThreads = WARPS * 32;
     constexpr int CAP = kWarps * BPW * 32;
-    constexpr int BPL = (BPW + 31) / 32;  // buckets tested per lane
+    constexpr int BPL = 1;  // buckets tested per lane
+    static_assert(BPW <= 32, "one tested bucket per lane");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // region A: sort keys (CAP x u64), later the coordinates (3 x CAP x f32); region B: original index per slot
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -193,24 +197,25 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
         }
     };
 
+#pragma unroll 1
+    for (int i = 0; i < BPW; i++) {  // bounding boxes (rolled: one-off, keeps the code small)
+        const int slot = 32 * (warp + kWarps * i) + lane;
+        const bool valid = slot < n;
+        const float p[3] = {sx[slot], sy[slot], sz[slot]};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int l = __reduce_min_sync(0xffffffffu, valid ? ordered_int(p[a]) : 0x7fffffff);
+            const int h = __reduce_max_sync(0xffffffffu, valid ? ordered_int(p[a]) : (int)0x80000000);
+            if (lane == i) {
+                blo[0][a] = ordered_int_inv(l);
+                bhi[0][a] = ordered_int_inv(h);
+            }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < BPW; i++) {
         const int slot = 32 * (warp + kWarps * i) + lane;
-        const bool valid = slot < n;
-        d[i] = valid ? temp[sorig[slot]] : -1.f;
-        float lo[3], hi[3];
-        lo[0] = hi[0] = sx[slot];
-        lo[1] = hi[1] = sy[slot];
-        lo[2] = hi[2] = sz[slot];
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const int l = __reduce_min_sync(0xffffffffu, valid ? ordered_int(lo[a]) : 0x7fffffff);
-            const int h = __reduce_max_sync(0xffffffffu, valid ? ordered_int(hi[a]) : (int)0x80000000);
-            if (lane == (i & 31)) {
-                blo[i >> 5][a] = ordered_int_inv(l);
-                bhi[i >> 5][a] = ordered_int_inv(h);
-            }
-        }
+        d[i] = slot < n ? temp[sorig[slot]] : -1.f;
         refresh(i, d[i], slot);
     }
 
@@ -256,7 +261,7 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
             red[buf][warp].key = wkey;
             red[buf][warp].slot = wslot;
         }
-        loop_barrier();
+        __syncthreads();
         const unsigned long long rkey = lane < kWarps ? red[buf][lane].key : 0ull;
         const int rslot = lane < kWarps ? red[buf][lane].slot : 0;
         const unsigned long long best = warp_max_u64(rkey);
@@ -277,11 +282,12 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     }
 }
 
-template <int BPW>
+template <int WARPS, int BPW>
 int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
-    constexpr int CAP = kWarps * BPW * 32;
+    constexpr int CAP = WARPS * BPW * 32;
+    constexpr int kInitThreads = WARPS * 32;
     const size_t smem = (size_t)12 * CAP + (size_t)2 * CAP;
-    auto kern = fps_pruned_kernel<BPW>;
+    auto kern = fps_pruned_kernel<WARPS, BPW>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<b, kInitThreads, smem, stream>>>(n, m, xyz, temp, idx, L);
     PDAB_LAUNCH_CHECK();
@@ -295,10 +301,16 @@ namespace pdab {
 // Returns PDAB_EUNSUPPORTED when the pruned kernel does not cover the size (caller falls back to fps.cu).
 int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
     if (n > 16384 || n < 1) return PDAB_EUNSUPPORTED;
-    if (n <= 2048) return launch<8>(b, n, m, xyz, temp, idx, L, stream);
-    if (n <= 4096) return launch<16>(b, n, m, xyz, temp, idx, L, stream);
-    if (n <= 8192) return launch<32>(b, n, m, xyz, temp, idx, L, stream);
-    return launch<64>(b, n, m, xyz, temp, idx, L, stream);
+    static const int variant = getenv("PDAB_FPS_VARIANT") ? atoi(getenv("PDAB_FPS_VARIANT")) : 0;  // tuning aid
+    if (variant == 1) {  // 16 warps x 32 buckets
+        if (n <= 4096) return launch<16, 8>(b, n, m, xyz, temp, idx, L, stream);
+        if (n <= 8192) return launch<16, 16>(b, n, m, xyz, temp, idx, L, stream);
+        return launch<16, 32>(b, n, m, xyz, temp, idx, L, stream);
+    }
+    if (n <= 2048) return launch<32, 2>(b, n, m, xyz, temp, idx, L, stream);
+    if (n <= 4096) return launch<32, 4>(b, n, m, xyz, temp, idx, L, stream);
+    if (n <= 8192) return launch<32, 8>(b, n, m, xyz, temp, idx, L, stream);
+    return launch<32, 16>(b, n, m, xyz, temp, idx, L, stream);
 }
 
 }  // namespace pdab
