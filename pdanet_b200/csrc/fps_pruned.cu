@@ -70,12 +70,13 @@ struct __align__(16) WarpBest {
 // registers and registers cannot be indexed dynamically), so BPW also sets the code size of the
 // loop: BPW = 64 on 8 warps measured 3.4 us/step because the 60 KB body thrashed the instruction
 // cache; 16 buckets on 32 warps keeps it near 14 KB.
-template <int WARPS, int BPW>
+// PPL points per lane per bucket: a bucket is 32*PPL Morton-consecutive points.
+template <int WARPS, int BPW, int PPL>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
                   int *__restrict__ idx_all, int L) {
     constexpr int kWarps = WARPS, kInitThreads = WARPS * 32;
-    constexpr int CAP = kWarps * BPW * 32;
+    constexpr int CAP = kWarps * BPW * 32 * PPL;
     constexpr int BPL = 1;  // buckets tested per lane
     static_assert(BPW <= 32, "one tested bucket per lane");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,7 +168,7 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     // ---- 3. per-lane state: min-distances of one point of each owned bucket, cached bucket data -
     // warp w owns buckets b = w + kWarps*i (interleaved: a neighbourhood's buckets spread over warps);
     // lane l holds slot 32*b + l.  Bucket i is TESTED by lane (i % 32), register (i / 32).
-    float d[BPW];
+    float d[BPW][PPL];
     float blo[BPL][3], bhi[BPL][3], bmax[BPL];
     unsigned long long bkey[BPL];
     int bslot[BPL];
@@ -180,32 +181,62 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
         for (int a = 0; a < 3; a++) blo[r][a] = bhi[r][a] = 0.f;
     }
 
-    auto refresh = [&](int i, float dv, int slot) {
+    // slot of (bucket i of this warp, row q, this lane)
+    auto slot_of = [&](int i, int q) { return ((warp + kWarps * i) * PPL + q) * 32 + lane; };
+
+    auto refresh = [&](int i, const float (&dv)[PPL]) {
         // cached candidate of bucket i: largest min-distance, reference tie rule among equals
-        const bool valid = dv >= 0.f;
-        const unsigned hi = valid ? __float_as_uint(dv) : 0u;
+        float mv = dv[0];
+#pragma unroll
+        for (int q = 1; q < PPL; q++) mv = fmaxf(mv, dv[q]);
+        const bool valid = mv >= 0.f;
+        const unsigned hi = valid ? __float_as_uint(mv) : 0u;
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
         const bool top = valid && hi == mh;
-        const unsigned lo = top ? ~tie_key((int)sorig[slot], L) : 0u;
+        unsigned lo = 0u;
+        int myq = 0;
+        if (top) {
+#pragma unroll
+            for (int q = 0; q < PPL; q++)
+                if (dv[q] == mv) {
+                    const unsigned c = ~tie_key((int)sorig[slot_of(i, q)], L);
+                    if (c > lo) {
+                        lo = c;
+                        myq = q;
+                    }
+                }
+        }
         const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
         const unsigned who = __ballot_sync(0xffffffffu, top && lo == ml);
-        if (lane == (i & 31)) {
+        const int wl = who ? __ffs(who) - 1 : 0;
+        const int wq = __shfl_sync(0xffffffffu, myq, wl);
+        if (lane == i) {
             const bool any = who != 0u;
-            bmax[i >> 5] = any ? __uint_as_float(mh) : -1.f;
-            bkey[i >> 5] = any ? (((unsigned long long)mh << 32) | ml) : 0ull;
-            bslot[i >> 5] = (slot & ~31) + (any ? __ffs(who) - 1 : 0);
+            bmax[0] = any ? __uint_as_float(mh) : -1.f;
+            bkey[0] = any ? (((unsigned long long)mh << 32) | ml) : 0ull;
+            bslot[0] = ((warp + kWarps * i) * PPL + wq) * 32 + wl;
         }
     };
 
 #pragma unroll 1
     for (int i = 0; i < BPW; i++) {  // bounding boxes (rolled: one-off, keeps the code small)
-        const int slot = 32 * (warp + kWarps * i) + lane;
-        const bool valid = slot < n;
-        const float p[3] = {sx[slot], sy[slot], sz[slot]};
+        int l3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        int h3[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+        for (int q = 0; q < PPL; q++) {
+            const int slot = slot_of(i, q);
+            if (slot < n) {
+                const float p[3] = {sx[slot], sy[slot], sz[slot]};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    l3[a] = min(l3[a], ordered_int(p[a]));
+                    h3[a] = max(h3[a], ordered_int(p[a]));
+                }
+            }
+        }
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const int l = __reduce_min_sync(0xffffffffu, valid ? ordered_int(p[a]) : 0x7fffffff);
-            const int h = __reduce_max_sync(0xffffffffu, valid ? ordered_int(p[a]) : (int)0x80000000);
+            const int l = __reduce_min_sync(0xffffffffu, l3[a]);
+            const int h = __reduce_max_sync(0xffffffffu, h3[a]);
             if (lane == i) {
                 blo[0][a] = ordered_int_inv(l);
                 bhi[0][a] = ordered_int_inv(h);
@@ -214,9 +245,12 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     }
 #pragma unroll
     for (int i = 0; i < BPW; i++) {
-        const int slot = 32 * (warp + kWarps * i) + lane;
-        d[i] = slot < n ? temp[sorig[slot]] : -1.f;
-        refresh(i, d[i], slot);
+#pragma unroll
+        for (int q = 0; q < PPL; q++) {
+            const int slot = slot_of(i, q);
+            d[i][q] = slot < n ? temp[sorig[slot]] : -1.f;
+        }
+        refresh(i, d[i]);
     }
 
     int old = 0;
@@ -237,12 +271,18 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
             active[r] = __ballot_sync(0xffffffffu, !(lb * 0.99999905f >= bmax[r]));
         }
         // -- update the surviving buckets -----------------------------------------------------------
+        if (active[0] != 0u) {  // most warps have nothing to do in most steps
 #pragma unroll
-        for (int i = 0; i < BPW; i++) {
-            if ((active[i >> 5] >> (i & 31)) & 1u) {  // warp-uniform
-                const int slot = 32 * (warp + kWarps * i) + lane;
-                if (d[i] >= 0.f) d[i] = fminf(pdab::sqdist3(sx[slot], sy[slot], sz[slot], x1, y1, z1), d[i]);
-                refresh(i, d[i], slot);
+            for (int i = 0; i < BPW; i++) {
+                if ((active[0] >> i) & 1u) {  // warp-uniform
+#pragma unroll
+                    for (int q = 0; q < PPL; q++) {
+                        const int slot = slot_of(i, q);
+                        if (d[i][q] >= 0.f)
+                            d[i][q] = fminf(pdab::sqdist3(sx[slot], sy[slot], sz[slot], x1, y1, z1), d[i][q]);
+                    }
+                    refresh(i, d[i]);
+                }
             }
         }
         // -- argmax over cached candidates: lane -> warp -> CTA -------------------------------------
@@ -276,18 +316,20 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     }
 
 #pragma unroll
-    for (int i = 0; i < BPW; i++) {
-        const int slot = 32 * (warp + kWarps * i) + lane;
-        if (slot < n) temp[sorig[slot]] = d[i];
-    }
+    for (int i = 0; i < BPW; i++)
+#pragma unroll
+        for (int q = 0; q < PPL; q++) {
+            const int slot = slot_of(i, q);
+            if (slot < n) temp[sorig[slot]] = d[i][q];
+        }
 }
 
-template <int WARPS, int BPW>
+template <int WARPS, int BPW, int PPL>
 int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
-    constexpr int CAP = WARPS * BPW * 32;
+    constexpr int CAP = WARPS * BPW * 32 * PPL;
     constexpr int kInitThreads = WARPS * 32;
     const size_t smem = (size_t)12 * CAP + (size_t)2 * CAP;
-    auto kern = fps_pruned_kernel<WARPS, BPW>;
+    auto kern = fps_pruned_kernel<WARPS, BPW, PPL>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<b, kInitThreads, smem, stream>>>(n, m, xyz, temp, idx, L);
     PDAB_LAUNCH_CHECK();
@@ -302,15 +344,22 @@ namespace pdab {
 int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
     if (n > 16384 || n < 1) return PDAB_EUNSUPPORTED;
     static const int variant = getenv("PDAB_FPS_VARIANT") ? atoi(getenv("PDAB_FPS_VARIANT")) : 0;  // tuning aid
-    if (variant == 1) {  // 16 warps x 32 buckets
-        if (n <= 4096) return launch<16, 8>(b, n, m, xyz, temp, idx, L, stream);
-        if (n <= 8192) return launch<16, 16>(b, n, m, xyz, temp, idx, L, stream);
-        return launch<16, 32>(b, n, m, xyz, temp, idx, L, stream);
+    const int sz = n <= 2048 ? 0 : n <= 4096 ? 1 : n <= 8192 ? 2 : 3;
+#define PDAB_FPS_CASE(V, W, B0, B1, B2, B3, P)                                        \
+    if (variant == V) {                                                                \
+        if (sz == 0) return launch<W, B0, P>(b, n, m, xyz, temp, idx, L, stream);      \
+        if (sz == 1) return launch<W, B1, P>(b, n, m, xyz, temp, idx, L, stream);      \
+        if (sz == 2) return launch<W, B2, P>(b, n, m, xyz, temp, idx, L, stream);      \
+        return launch<W, B3, P>(b, n, m, xyz, temp, idx, L, stream);                   \
     }
-    if (n <= 2048) return launch<32, 2>(b, n, m, xyz, temp, idx, L, stream);
-    if (n <= 4096) return launch<32, 4>(b, n, m, xyz, temp, idx, L, stream);
-    if (n <= 8192) return launch<32, 8>(b, n, m, xyz, temp, idx, L, stream);
-    return launch<32, 16>(b, n, m, xyz, temp, idx, L, stream);
+    PDAB_FPS_CASE(1, 32, 2, 4, 8, 16, 1)   // 32 warps, 32-point buckets
+    PDAB_FPS_CASE(2, 16, 2, 4, 8, 16, 2)   // 16 warps, 64-point buckets
+    PDAB_FPS_CASE(3, 8, 2, 4, 8, 16, 4)    // 8 warps, 128-point buckets
+    PDAB_FPS_CASE(4, 8, 4, 8, 16, 32, 2)   // 8 warps, 64-point buckets
+    PDAB_FPS_CASE(5, 16, 1, 2, 4, 8, 4)    // 16 warps, 128-point buckets
+    PDAB_FPS_CASE(0, 16, 2, 4, 8, 16, 2)   // default
+#undef PDAB_FPS_CASE
+    return PDAB_EUNSUPPORTED;
 }
 
 }  // namespace pdab

@@ -42,6 +42,7 @@ def vp(t):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--fps-only", action="store_true")
     args = ap.parse_args()
     pn, iou = load_ref_pointnet2(), load_ref_iou3d()
     B = 16
@@ -67,6 +68,8 @@ def main():
             rec.update(ref_ms=round(r_min, 4), speedup=round(r_min / t_min, 2), equal=bool(torch.equal(idx, ours())))
         print(json.dumps(rec), flush=True)
 
+    if args.fps_only:
+        return
     for N, M, r, ns in [(16384, 4096, 0.2, 16), (16384, 4096, 0.8, 32), (4096, 1024, 1.6, 32), (1024, 512, 4.8, 32),
                         (512, 256, 6.4, 32)] + ([] if args.quick else [(65536, 16384, 0.8, 32), (16384, 4096, 4.8, 64)]):
         xyz = scene_xyz(N + M, B, N).cuda()
