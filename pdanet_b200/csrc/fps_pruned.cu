@@ -78,7 +78,7 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     constexpr int kWarps = WARPS, kInitThreads = WARPS * 32;
     constexpr int CAP = kWarps * BPW * 32 * PPL;
     constexpr int BPL = 1;  // buckets tested per lane
-    static_assert(BPW <= 32, "one tested bucket per lane");
+    static_assert(BPW <= 16, "one tested bucket per lane, 16 switch cases");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // region A: sort keys (CAP x u64), later the coordinates (3 x CAP x f32); region B: original index per slot
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -271,19 +271,32 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
             active[r] = __ballot_sync(0xffffffffu, !(lb * 0.99999905f >= bmax[r]));
         }
         // -- update the surviving buckets -----------------------------------------------------------
-        if (active[0] != 0u) {  // most warps have nothing to do in most steps
-#pragma unroll
-            for (int i = 0; i < BPW; i++) {
-                if ((active[0] >> i) & 1u) {  // warp-uniform
-#pragma unroll
-                    for (int q = 0; q < PPL; q++) {
-                        const int slot = slot_of(i, q);
-                        if (d[i][q] >= 0.f)
-                            d[i][q] = fminf(pdab::sqdist3(sx[slot], sy[slot], sz[slot], x1, y1, z1), d[i][q]);
-                    }
-                    refresh(i, d[i]);
-                }
+        // most warps have nothing to do in most steps; busy ones jump straight to the bodies of their
+        // active buckets (indexed branch) instead of walking BPW bit tests spread over the whole loop body
+        unsigned todo = active[0];
+        while (todo) {
+            const int i = __ffs(todo) - 1;
+            todo &= todo - 1;
+#define PDAB_BUCKET_CASE(I)                                                                                   \
+    case I:                                                                                                   \
+        if (I < BPW) {                                                                                        \
+            _Pragma("unroll") for (int q = 0; q < PPL; q++) {                                                 \
+                const int slot = slot_of(I, q);                                                               \
+                if (d[I < BPW ? I : 0][q] >= 0.f)                                                             \
+                    d[I < BPW ? I : 0][q] =                                                                   \
+                        fminf(pdab::sqdist3(sx[slot], sy[slot], sz[slot], x1, y1, z1), d[I < BPW ? I : 0][q]); \
+            }                                                                                                 \
+            refresh(I, d[I < BPW ? I : 0]);                                                                   \
+        }                                                                                                     \
+        break;
+            switch (i) {
+                PDAB_BUCKET_CASE(0) PDAB_BUCKET_CASE(1) PDAB_BUCKET_CASE(2) PDAB_BUCKET_CASE(3)
+                PDAB_BUCKET_CASE(4) PDAB_BUCKET_CASE(5) PDAB_BUCKET_CASE(6) PDAB_BUCKET_CASE(7)
+                PDAB_BUCKET_CASE(8) PDAB_BUCKET_CASE(9) PDAB_BUCKET_CASE(10) PDAB_BUCKET_CASE(11)
+                PDAB_BUCKET_CASE(12) PDAB_BUCKET_CASE(13) PDAB_BUCKET_CASE(14) PDAB_BUCKET_CASE(15)
+                default: break;
             }
+#undef PDAB_BUCKET_CASE
         }
         // -- argmax over cached candidates: lane -> warp -> CTA -------------------------------------
         unsigned long long mykey = bkey[0];
@@ -355,7 +368,9 @@ int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int
     PDAB_FPS_CASE(1, 32, 2, 4, 8, 16, 1)   // 32 warps, 32-point buckets
     PDAB_FPS_CASE(2, 16, 2, 4, 8, 16, 2)   // 16 warps, 64-point buckets
     PDAB_FPS_CASE(3, 8, 2, 4, 8, 16, 4)    // 8 warps, 128-point buckets
-    PDAB_FPS_CASE(4, 8, 4, 8, 16, 32, 2)   // 8 warps, 64-point buckets
+    PDAB_FPS_CASE(4, 8, 1, 2, 4, 8, 8)     // 8 warps, 256-point buckets
+    PDAB_FPS_CASE(6, 16, 1, 1, 2, 4, 8)    // 16 warps, 256-point buckets
+    PDAB_FPS_CASE(7, 32, 1, 1, 2, 4, 4)    // 32 warps, 128-point buckets
     PDAB_FPS_CASE(5, 16, 1, 2, 4, 8, 4)    // 16 warps, 128-point buckets
     PDAB_FPS_CASE(0, 16, 2, 4, 8, 16, 2)   // default
 #undef PDAB_FPS_CASE

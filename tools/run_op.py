@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Run one op a few times (target for `ncu -k regex:...`).  python tools/run_op.py fps 16 16384 1024"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from util import scene_xyz  # noqa: E402
+from pdanet_b200 import pointnet2_utils as ops  # noqa: E402
+
+op = sys.argv[1]
+a = [float(x) if "." in x else int(x) for x in sys.argv[2:]]
+if op == "fps":
+    B, N, m = a
+    xyz = scene_xyz(N, B, N).cuda()
+    for _ in range(3):
+        ops.furthest_point_sample(xyz, m)
+elif op == "pda_group":
+    B, Cc, N, M, r, ns = a
+    xyz = scene_xyz(N + M, B, N).cuda()
+    feats = torch.randn(B, Cc, N, device="cuda")
+    for _ in range(3):
+        ops.pda_group(r, ns, xyz, xyz[:, :M].contiguous(), feats)
+elif op == "ball_query":
+    B, N, M, r, ns = a
+    xyz = scene_xyz(N + M, B, N).cuda()
+    for _ in range(3):
+        ops.ball_query(r, ns, xyz, xyz[:, :M].contiguous())
+torch.cuda.synchronize()
+print("done")
