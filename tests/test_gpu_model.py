@@ -133,3 +133,12 @@ def test_scene_sharding_is_a_pure_partition(models):
             parts += gpu({"batch_size": len(ids), "points": sub.reshape(-1, 5)})[0]
     for w, p in zip(whole, parts):
         assert torch.equal(w["pred_boxes"], p["pred_boxes"])
+
+
+def test_cuda_backbone_matches_reference_modules_golden():
+    """The CUDA path (fused kernels included) against outputs of the REFERENCE's own Python modules."""
+    from test_host_cpu import replay_reference_backbone_golden
+    from pdanet_b200 import pointnet2_utils
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    replay_reference_backbone_golden(pointnet2_utils, "cuda", rtol=RTOL)

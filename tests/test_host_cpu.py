@@ -95,3 +95,52 @@ def test_two_rank_scene_sharding_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD_OK" in out.stdout
+
+
+def _forced_ops(base, picks):
+    import types
+    ns = types.SimpleNamespace(**{k: getattr(base, k) for k in dir(base) if not k.startswith("_")})
+    queue = list(picks)
+    ns.topk_ctr_sample = lambda cls_features, npoint: queue.pop(0).to(cls_features.device).contiguous()
+    return ns
+
+
+def replay_reference_backbone_golden(ops_base, device, rtol):
+    """Our backbone vs tests/golden/ref_backbone_kitti.npz — outputs of the REFERENCE's own IASSD_Backbone /
+    pointnet2_modules.py run over the oracle ops (tests/golden/make_module_golden.py).  Weights come from the same
+    seed (the generator asserts the seeded state_dicts are identical); the class-aware layers replay the reference's
+    picks because torch.topk's tie order is unspecified."""
+    import numpy as np
+    from conftest import GOLDEN
+    from pdanet_b200.iassd_backbone import IASSD_Backbone
+    z = np.load(GOLDEN / "ref_backbone_kitti.npz")
+    cfg = load_config("kitti")
+    torch.manual_seed(int(z["seed"]))
+    bb = IASSD_Backbone(cfg.MODEL.BACKBONE_3D, num_class=3, input_channels=4, ops=ops_base).eval().to(device)
+    forced = _forced_ops(ops_base, [torch.from_numpy(z["sample_idx_L2"]), torch.from_numpy(z["sample_idx_L3"])])
+    for mod in bb.SA_modules:
+        if hasattr(mod, "ops"):
+            mod.ops = forced
+    batch = make_batch(int(z["batch"]), int(z["npoints"]), cfg.POINT_CLOUD_RANGE, duplicate_frac=float(z["duplicate_frac"]))
+    with torch.no_grad():
+        out = bb({"batch_size": batch["batch_size"], "points": batch["points"].to(device)})
+
+    def close(got, want, what):
+        got, want = got.detach().cpu(), torch.from_numpy(want)
+        err = (got - want).abs().max().item()
+        assert err <= rtol * (want.abs().max().item() + 1e-12), f"{what}: {err:.3e}"
+
+    for lvl in (0, 1):  # D-FPS layers: exact indices
+        assert torch.equal(out["sample_list_id"][lvl].cpu(), torch.from_numpy(z[f"sample_idx_L{lvl}"])), f"FPS L{lvl}"
+    close(out["centers"], z["centers"], "centers")
+    close(out["centers_origin"], z["centers_origin"], "centers_origin")
+    close(out["ctr_offsets"][:, 1:], z["ctr_offsets"][:, 1:], "ctr_offsets")
+    close(out["centers_features"][::4, ::8], z["centers_features_strided"], "centers_features")
+    close(out["sa_ins_preds"][1][:, ::8], z["cls_L1_strided"], "cls L1")
+    close(out["sa_ins_preds"][2][:, ::4], z["cls_L2_strided"], "cls L2")
+    for lvl in (0, 1, 2):
+        close(out["encoder_features"][lvl + 1][:, ::4, ::16], z[f"features_L{lvl}_strided"], f"features L{lvl}")
+
+
+def test_backbone_matches_reference_modules_golden():
+    replay_reference_backbone_golden(torch_ops, "cpu", rtol=1e-5)
