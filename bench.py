@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--matmul", default="ieee", choices=["ieee", "tf32"],
+                    help="fp32 matmul mode of the unchanged PyTorch layers (PDA transformer); our kernels are fp32 either way")
     return ap.parse_args()
 
 
@@ -180,6 +182,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
     dev = torch.device(f"cuda:{local}")
     _lib.lib()  # fail loudly if the extension is missing
 
+    torch.backends.cuda.matmul.allow_tf32 = args.matmul == "tf32"
     runner = SceneRunner(cfg, device=dev, batch_size=batch, num_points=n_points, seed=0)
     # weak scaling: every rank owns its own `batch` scenes (global scene ids rank*batch ...)
     host = make_batch(batch, n_points, cfg.POINT_CLOUD_RANGE, first_scene=rank * batch)["points"].pin_memory()
@@ -291,7 +294,8 @@ def run_gpu_arm(args, cfg, n_points, batch):
         "config": {"workload": f"PDA-SSD {args.config} cfg full inference (backbone+vote+centroid aggregation+head+3D NMS), "
                                f"batch {batch} x {n_points} pts per GPU, random-init weights",
                    "scenes_per_gpu_per_step": batch, "points_per_scene": n_points, "parallelism": f"scene-sharded x{world}",
-                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)"},
+                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)",
+                   "torch_layers": f"fp32 matmul mode {args.matmul}; cuDNN 1x1 convs TF32-allowed (torch default, as the reference)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
                 "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_total / args.steps},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
