@@ -103,6 +103,16 @@ int pdab_topk_ctr(int b, int n, int c, int npoint, const float *cls, int *idx, p
 int pdab_pda_group(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
                    const float *features, float *out, int *idx_out, pdab_stream_t stream);
 
+/* Token-major PDA grouper: same search and encoding as pdab_pda_group, laid out for the per-token consumers of the
+ * PDA block.  features_t (B,N,C) is the POINT-major copy of the features; out (B,M,nsample,pitch) holds one row per
+ * (centre, neighbour): [0..2] xyz, [3] density, [4..6] direction, [7] 0, [8..8+C) features.
+ * pitch >= 8+C, pitch % 4 == 0, C % 4 == 0.  idx_out optional.
+ * replaces: the same Python grouper + the permute/contiguous copies that feed the transformer,
+ *           PB/pointnet2_utils.py:567-614, PB/pointnet2_modules.py:879-927. */
+int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, int nsample, int pitch, const float *xyz,
+                          const float *new_xyz, const float *features_t, float *out, int *idx_out,
+                          pdab_stream_t stream);
+
 /* Fused plain set-abstraction scale: ball query -> group (xyz centred) -> shared MLP
  * (1x1 conv with eval-mode BatchNorm folded in, ReLU) x nlayers -> max over nsample.
  * The grouped tensor never reaches HBM.

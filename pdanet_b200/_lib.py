@@ -30,6 +30,7 @@ _SIGNATURES = {
     "pdab_group_points_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pdab_topk_ctr": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_pda_group": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_pda_group_tokens": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_nms_workspace_bytes": (_sz, [_i]),
     "pdab_nms_device": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),

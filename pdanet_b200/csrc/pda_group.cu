@@ -97,7 +97,93 @@ pda_group_kernel(int c, int n, int m, float radius, float r2, float two_r2, floa
     }
 }
 
+// ---- token-major variant --------------------------------------------------------------------------
+// Same search and encoding, but the output is laid out for the consumers that follow in the PDA block
+// (per-token MLPs and a transformer over each neighbourhood): out (B, M, nsample, pitch) with one
+// contiguous row per (centre, neighbour) token:
+//   [0..2] neighbour xyz (not centred), [3] Gaussian density, [4..6] direction, [7] 0, [8..8+C) features
+// and the features are read from a POINT-major copy (B, N, C), so a token is one coalesced read of its
+// neighbour's feature row and one coalesced, 16-byte aligned write (pitch % 4 == 0).  A warp moves one
+// token at a time; the CTA's whole output slab is one contiguous range.  HBM traffic is the output
+// (4 * pitch bytes per token) plus L2-resident gathers.
+__global__ void __launch_bounds__(kThreads)
+pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, float two_r2, float dens_norm,
+                        int nsample, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                        const float *__restrict__ features_t, float *__restrict__ out, int *__restrict__ idx_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);
+    float *sctr = reinterpret_cast<float *>(tile + pdab::kScanTile);
+    int *sidx = reinterpret_cast<int *>(sctr + 3 * kThreads);
+
+    const int scene = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int j0 = blockIdx.x * kThreads;
+    const int j = j0 + t;
+    const bool active = j < m;
+    xyz += (size_t)scene * n * 3;
+    features_t += (size_t)scene * n * c;
+
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (active) {
+        const float *ctr = new_xyz + ((size_t)scene * m + j) * 3;
+        cx = ctr[0];
+        cy = ctr[1];
+        cz = ctr[2];
+    }
+    sctr[t * 3 + 0] = cx;
+    sctr[t * 3 + 1] = cy;
+    sctr[t * 3 + 2] = cz;
+    pdab::ball_scan_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2, nsample, tile, sidx);
+
+    const int nctr = min(kThreads, m - j0);
+    const int ntok = nctr * nsample;
+    float *obase = out + ((size_t)scene * m + j0) * nsample * pitch;
+    int *ibase = idx_out ? idx_out + ((size_t)scene * m + j0) * nsample : nullptr;
+    const int c4 = c >> 2;  // float4 chunks per feature row (c % 4 == 0 checked by the host)
+
+    for (int tok = warp; tok < ntok; tok += kThreads / 32) {
+        const int jl = tok / nsample, s = tok - jl * nsample;
+        const int k = sidx[s * kStride + jl];
+        float4 *orow = reinterpret_cast<float4 *>(obase + (size_t)tok * pitch);
+        const float4 *frow = reinterpret_cast<const float4 *>(features_t + (size_t)k * c);
+        if (lane < 2) {
+            const float gx = __ldg(xyz + (size_t)k * 3 + 0), gy = __ldg(xyz + (size_t)k * 3 + 1),
+                        gz = __ldg(xyz + (size_t)k * 3 + 2);
+            const float dx = gx - sctr[jl * 3 + 0], dy = gy - sctr[jl * 3 + 1], dz = gz - sctr[jl * 3 + 2];
+            if (lane == 0) {
+                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float dens = expf(-(dist * dist) / two_r2) / dens_norm;
+                __stcs(orow, make_float4(gx, gy, gz, dens));
+                if (ibase) ibase[tok] = k;
+            } else {
+                __stcs(orow + 1, make_float4(dx / radius, dy / radius, dz / radius, 0.f));
+            }
+        }
+        for (int q = lane; q < c4; q += 32) __stcs(orow + 2 + q, __ldg(frow + q));
+    }
+}
+
 }  // namespace
+
+extern "C" int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, int nsample, int pitch,
+                                     const float *xyz, const float *new_xyz, const float *features_t, float *out,
+                                     int *idx_out, pdab_stream_t stream) {
+    if (b < 0 || c < 0 || n < 1 || m < 0 || nsample < 1 || !xyz || !new_xyz || !out || (c > 0 && !features_t))
+        return PDAB_EINVAL;
+    if (pitch < 8 + c || (pitch & 3) || (c & 3)) return PDAB_EINVAL;
+    if (b == 0 || m == 0) return 0;
+    if (nsample > 128 || b > 65535) return PDAB_EUNSUPPORTED;
+    const size_t smem = sizeof(float4) * pdab::kScanTile + sizeof(float) * 3 * kThreads +
+                        sizeof(int) * (size_t)nsample * kStride;
+    PDAB_CUDA(cudaFuncSetAttribute(pda_group_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float two_r2 = (float)(2.0 * (double)radius * (double)radius);
+    const float dens_norm = (float)(2.5 * (double)radius);
+    dim3 grid(pdab::div_up(m, kThreads), b);
+    pda_group_tokens_kernel<<<grid, kThreads, smem, pdab::to_stream(stream)>>>(
+        c, n, m, pitch, radius, radius * radius, two_r2, dens_norm, nsample, xyz, new_xyz, features_t, out, idx_out);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int pdab_pda_group(int b, int c, int n, int m, float radius, int nsample, const float *xyz,
                               const float *new_xyz, const float *features, float *out, int *idx_out,

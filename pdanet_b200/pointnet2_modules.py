@@ -323,6 +323,23 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
             out_channels += mlps[i][-1]
         self.pool_method = pool_method
         self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.fin_conv) > 0)
+        self.fast_eval = True   # token-major eval path (pda_block.py); False = the reference's statement order
+        self._plans = {}
+
+    def train(self, mode: bool = True):
+        self._plans = {}
+        return super().train(mode)
+
+    def _fast_path_ok(self, features):
+        return (self.fast_eval and not self.training and not torch.is_grad_enabled()
+                and hasattr(self.ops, "pda_group_tokens") and not self.dilated_group
+                and self.npoint_list is not None and features is not None and features.shape[1] % 4 == 0)
+
+    def _scale_fast(self, i, xyz, new_xyz, features_t, centre_feature_t):
+        from .pda_block import PDAScalePlan
+        if i not in self._plans:
+            self._plans[i] = PDAScalePlan(self, i)
+        return self._plans[i](self.ops, xyz, new_xyz, features_t, centre_feature_t)
 
     def _scale(self, i, xyz, new_xyz, features, global_feature):
         B, M, _ = new_xyz.shape
@@ -363,8 +380,13 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
         if len(self.groupers) > 0:
             # the reference needs the sampled centres' own features here, i.e. ctr_xyz must be None (:848-856)
             assert centre_feature is not None, "PDA SA layers take their centres from sampling (CTR_INDEX = -1)"
-            global_feature = torch.cat([new_xyz.transpose(1, 2), centre_feature], dim=1).unsqueeze(-1)  # (B,3+C,M,1)
-            outs = [self._scale(i, xyz, new_xyz, features, global_feature) for i in range(len(self.groupers))]
+            if self._fast_path_ok(features):
+                features_t = features.transpose(1, 2).contiguous()          # (B, N, C) point-major
+                centre_t = centre_feature.transpose(1, 2).contiguous()      # (B, M, C)
+                outs = [self._scale_fast(i, xyz, new_xyz, features_t, centre_t) for i in range(len(self.groupers))]
+            else:
+                global_feature = torch.cat([new_xyz.transpose(1, 2), centre_feature], dim=1).unsqueeze(-1)  # (B,3+C,M,1)
+                outs = [self._scale(i, xyz, new_xyz, features, global_feature) for i in range(len(self.groupers))]
             new_features = torch.cat(outs, dim=1)
             if self.aggregation_layer is not None:
                 new_features = self.aggregation_layer(new_features)

@@ -199,6 +199,27 @@ def pda_group(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Ten
     return (out, idx) if return_idx else out
 
 
+def pda_group_tokens(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
+                     features_t: torch.Tensor, return_idx: bool = False):
+    """Token-major fused PDA grouper (forward only).  features_t (B,N,C) point-major.  Returns
+    X (B, M, nsample, 8+C): [xyz(3), density, direction(3), 0, features(C)] per (centre, neighbour) token."""
+    for t in (xyz, new_xyz, features_t):
+        if not t.is_cuda:
+            raise RuntimeError("pda_group_tokens needs CUDA tensors")
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and features_t.is_contiguous()
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = features_t.shape[2]
+    pitch = 8 + C
+    out = torch.empty(B, M, nsample, pitch, dtype=torch.float32, device=xyz.device)
+    idx = torch.empty(B, M, nsample, dtype=torch.int32, device=xyz.device) if return_idx else None
+    with torch.cuda.device(xyz.device):
+        _lib.call("pdab_pda_group_tokens", B, C, N, M, float(radius), nsample, pitch, xyz.data_ptr(),
+                  new_xyz.data_ptr(), features_t.data_ptr(), out.data_ptr(), idx.data_ptr() if return_idx else None,
+                  torch.cuda.current_stream(xyz.device).cuda_stream)
+    return (out, idx) if return_idx else out
+
+
 def sa_fused_supported(c0: int, dims: Sequence[int], nsample: int) -> bool:
     """Shapes the fused plain-SA kernel covers (see csrc/sa_fused.cu)."""
     return len(dims) == 3 and nsample <= 64 and c0 <= 8 and tuple(dims) in ((16, 16, 32), (32, 32, 64))

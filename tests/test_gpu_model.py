@@ -142,3 +142,40 @@ def test_cuda_backbone_matches_reference_modules_golden():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     replay_reference_backbone_golden(pointnet2_utils, "cuda", rtol=RTOL)
+
+
+def test_pda_fast_path_equals_reference_statement_order(models):
+    """pda_block.py (token-major, folded BN, 3xTF32 projections) vs the module's reference-order forward, same inputs."""
+    cfg, gpu, _ = models
+    g = torch.Generator().manual_seed(11)
+    for layer, (N, C) in ((1, (4096, 64)), (2, (1024, 128))):
+        mod = gpu.backbone_3d.SA_modules[layer]
+        xyz = (torch.rand(2, N, 3, generator=g) * torch.tensor([30.0, 30.0, 2.0])).cuda()
+        feats = torch.randn(2, C, N, generator=g).cuda()
+        cls = torch.randn(2, N, 3, generator=g).cuda()
+        with torch.no_grad():
+            mod.fast_eval = True
+            fast = mod(xyz, feats, cls)
+            mod.fast_eval = False
+            slow = mod(xyz, feats, cls)
+            mod.fast_eval = True
+        assert torch.equal(fast[3], slow[3])
+        scale = slow[1].abs().max().item()
+        assert (fast[1] - slow[1]).abs().max().item() <= 1e-4 * scale
+        assert (fast[2] - slow[2]).abs().max().item() <= 1e-4 * slow[2].abs().max().item()
+
+
+def test_pda_group_tokens_matches_channel_major_grouper():
+    from pdanet_b200 import pointnet2_utils as ops
+    g = torch.Generator().manual_seed(5)
+    for B, C, N, M, r, ns in [(2, 64, 4096, 1024, 0.8, 16), (2, 128, 1024, 300, 4.8, 32)]:
+        xyz = (torch.rand(B, N, 3, generator=g) * torch.tensor([30.0, 30.0, 2.0])).cuda()
+        feats = torch.randn(B, C, N, generator=g).cuda()
+        new_xyz = xyz[:, :M].contiguous()
+        ref, ref_idx = ops.pda_group(r, ns, xyz, new_xyz, feats, return_idx=True)          # (B, 7+C, M, ns)
+        tok, idx = ops.pda_group_tokens(r, ns, xyz, new_xyz, feats.transpose(1, 2).contiguous(), return_idx=True)
+        assert torch.equal(idx, ref_idx)
+        ref = ref.permute(0, 2, 3, 1)                                                       # (B, M, ns, 7+C)
+        assert torch.equal(tok[..., 0:7], ref[..., 0:7])
+        assert torch.equal(tok[..., 8:], ref[..., 7:])
+        assert (tok[..., 7] == 0).all()
