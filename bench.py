@@ -154,6 +154,9 @@ def algorithmic_bytes(key: str, batch: int):
     if name == "pdab_pda_group":
         b, c, n, m, ns = a[:5]
         return b * (12 * n + 4 * c * n + 12 * m + 4 * (7 + c) * m * ns)
+    if name == "pdab_pda_group_tokens":
+        b, c, n, m, ns = a[:5]
+        return b * (12 * n + 4 * c * n + 12 * m + 4 * (8 + c) * m * ns)
     if name == "pdab_sa_fused":
         b, c, n, m, ns = a[:5]
         return b * (12 * n + 4 * c * n + 12 * m)    # + output, added by the caller (needs cout)

@@ -116,7 +116,7 @@ pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, 
     int *sidx = reinterpret_cast<int *>(sctr + 3 * kThreads);
 
     const int scene = blockIdx.y;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x;
     const int j0 = blockIdx.x * kThreads;
     const int j = j0 + t;
     const bool active = j < m;
@@ -139,27 +139,43 @@ pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, 
     const int ntok = nctr * nsample;
     float *obase = out + ((size_t)scene * m + j0) * nsample * pitch;
     int *ibase = idx_out ? idx_out + ((size_t)scene * m + j0) * nsample : nullptr;
-    const int c4 = c >> 2;  // float4 chunks per feature row (c % 4 == 0 checked by the host)
-
-    for (int tok = warp; tok < ntok; tok += kThreads / 32) {
-        const int jl = tok / nsample, s = tok - jl * nsample;
-        const int k = sidx[s * kStride + jl];
-        float4 *orow = reinterpret_cast<float4 *>(obase + (size_t)tok * pitch);
-        const float4 *frow = reinterpret_cast<const float4 *>(features_t + (size_t)k * c);
-        if (lane < 2) {
-            const float gx = __ldg(xyz + (size_t)k * 3 + 0), gy = __ldg(xyz + (size_t)k * 3 + 1),
-                        gz = __ldg(xyz + (size_t)k * 3 + 2);
-            const float dx = gx - sctr[jl * 3 + 0], dy = gy - sctr[jl * 3 + 1], dz = gz - sctr[jl * 3 + 2];
-            if (lane == 0) {
-                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
-                const float dens = expf(-(dist * dist) / two_r2) / dens_norm;
-                __stcs(orow, make_float4(gx, gy, gz, dens));
-                if (ibase) ibase[tok] = k;
-            } else {
-                __stcs(orow + 1, make_float4(dx / radius, dy / radius, dz / radius, 0.f));
+    // The CTA's slab is ntok rows of p4 = pitch/4 float4: one flat, fully coalesced sweep.  Each thread keeps
+    // kChunk independent 16-byte gathers in flight (the gathers hit L2; the stores stream to HBM).
+    const int p4 = pitch >> 2;
+    const int c4 = c >> 2;
+    const int total = ntok * p4;
+    float4 *o4 = reinterpret_cast<float4 *>(obase);
+    for (int e0 = 0; e0 < total; e0 += kThreads * kChunk) {
+        float4 v[kChunk];
+#pragma unroll
+        for (int u = 0; u < kChunk; u++) {
+            const int e = e0 + u * kThreads + t;
+            if (e < total) {
+                const int tok = e / p4, q = e - tok * p4;
+                const int jl = tok / nsample, s = tok - jl * nsample;
+                const int k = sidx[s * kStride + jl];
+                if (q >= 2) {
+                    v[u] = q - 2 < c4 ? __ldg(reinterpret_cast<const float4 *>(features_t + (size_t)k * c) + (q - 2))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const float gx = __ldg(xyz + (size_t)k * 3 + 0), gy = __ldg(xyz + (size_t)k * 3 + 1),
+                                gz = __ldg(xyz + (size_t)k * 3 + 2);
+                    const float dx = gx - sctr[jl * 3 + 0], dy = gy - sctr[jl * 3 + 1], dz = gz - sctr[jl * 3 + 2];
+                    if (q == 0) {
+                        const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.norm(...)**2, PB/pointnet2_utils.py:592
+                        v[u] = make_float4(gx, gy, gz, expf(-(dist * dist) / two_r2) / dens_norm);
+                        if (ibase) ibase[tok] = k;
+                    } else {
+                        v[u] = make_float4(dx / radius, dy / radius, dz / radius, 0.f);
+                    }
+                }
             }
         }
-        for (int q = lane; q < c4; q += 32) __stcs(orow + 2 + q, __ldg(frow + q));
+#pragma unroll
+        for (int u = 0; u < kChunk; u++) {
+            const int e = e0 + u * kThreads + t;
+            if (e < total) __stcs(o4 + e, v[u]);
+        }
     }
 }
 
