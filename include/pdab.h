@@ -121,7 +121,8 @@ int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, int nsample,
  * features (B,C,N) or NULL (C=0); dims[0] = 3+C, dims[l+1] = cout of layer l;
  * weights[l] device (dims[l+1], dims[l]) row-major, biases[l] device (dims[l+1]);
  * `weights` / `biases` / `dims` themselves are HOST arrays of length nlayers (+1).
- * out (B, dims[nlayers], M).  nlayers <= 4, nsample <= 64. */
+ * out (B, dims[nlayers], M).  Shapes covered in this round: 3 layers, dims[0] <= 8,
+ * (dims[1..3]) in {(16,16,32), (32,32,64)}, nsample <= 32; anything else returns PDAB_EUNSUPPORTED. */
 int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
                   const float *features, int nlayers, const int *dims_host, const float *const *weights_host,
                   const float *const *biases_host, float *out, pdab_stream_t stream);

@@ -106,7 +106,9 @@ pda_group_kernel(int c, int n, int m, float radius, float r2, float two_r2, floa
 // neighbour's feature row and one coalesced, 16-byte aligned write (pitch % 4 == 0).  A warp moves one
 // token at a time; the CTA's whole output slab is one contiguous range.  HBM traffic is the output
 // (4 * pitch bytes per token) plus L2-resident gathers.
-__global__ void __launch_bounds__(kThreads)
+constexpr int kTokThreads = 512;  // 128 scan threads + helpers: the sweep phase wants many loads in flight
+
+__global__ void __launch_bounds__(kTokThreads)
 pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, float two_r2, float dens_norm,
                         int nsample, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
                         const float *__restrict__ features_t, float *__restrict__ out, int *__restrict__ idx_out) {
@@ -119,7 +121,7 @@ pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, 
     const int t = threadIdx.x;
     const int j0 = blockIdx.x * kThreads;
     const int j = j0 + t;
-    const bool active = j < m;
+    const bool active = t < kThreads && j < m;
     xyz += (size_t)scene * n * 3;
     features_t += (size_t)scene * n * c;
 
@@ -130,51 +132,57 @@ pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, 
         cy = ctr[1];
         cz = ctr[2];
     }
-    sctr[t * 3 + 0] = cx;
-    sctr[t * 3 + 1] = cy;
-    sctr[t * 3 + 2] = cz;
+    if (t < kThreads) {
+        sctr[t * 3 + 0] = cx;
+        sctr[t * 3 + 1] = cy;
+        sctr[t * 3 + 2] = cz;
+    }
     pdab::ball_scan_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2, nsample, tile, sidx);
 
     const int nctr = min(kThreads, m - j0);
     const int ntok = nctr * nsample;
     float *obase = out + ((size_t)scene * m + j0) * nsample * pitch;
     int *ibase = idx_out ? idx_out + ((size_t)scene * m + j0) * nsample : nullptr;
-    // The CTA's slab is ntok rows of p4 = pitch/4 float4: one flat, fully coalesced sweep.  Each thread keeps
-    // kChunk independent 16-byte gathers in flight (the gathers hit L2; the stores stream to HBM).
     const int p4 = pitch >> 2;
     const int c4 = c >> 2;
-    const int total = ntok * p4;
     float4 *o4 = reinterpret_cast<float4 *>(obase);
-    for (int e0 = 0; e0 < total; e0 += kThreads * kChunk) {
+
+    // (a) geometry: one thread per token writes the two leading float4 of its row
+    for (int tok = t; tok < ntok; tok += kTokThreads) {
+        const int jl = tok / nsample, s = tok - jl * nsample;
+        const int k = sidx[s * kStride + jl];
+        const float gx = __ldg(xyz + (size_t)k * 3 + 0), gy = __ldg(xyz + (size_t)k * 3 + 1),
+                    gz = __ldg(xyz + (size_t)k * 3 + 2);
+        const float dx = gx - sctr[jl * 3 + 0], dy = gy - sctr[jl * 3 + 1], dz = gz - sctr[jl * 3 + 2];
+        const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.norm(...)**2, PB/pointnet2_utils.py:592-593
+        __stcs(o4 + (size_t)tok * p4, make_float4(gx, gy, gz, expf(-(dist * dist) / two_r2) / dens_norm));
+        __stcs(o4 + (size_t)tok * p4 + 1, make_float4(dx / radius, dy / radius, dz / radius, 0.f));
+        if (ibase) ibase[tok] = k;
+    }
+    // (b) features: flat sweep over (token, float4-of-row); lanes of a warp read consecutive 16-byte pieces of
+    // one neighbour's feature row and write consecutive pieces of the output row; kChunk gathers in flight / thread
+    const int f4 = p4 - 2;  // feature float4 per row incl. padding beyond c
+    const int total = ntok * f4;
+    for (int e0 = 0; e0 < total; e0 += kTokThreads * kChunk) {
         float4 v[kChunk];
 #pragma unroll
         for (int u = 0; u < kChunk; u++) {
-            const int e = e0 + u * kThreads + t;
+            const int e = e0 + u * kTokThreads + t;
             if (e < total) {
-                const int tok = e / p4, q = e - tok * p4;
+                const int tok = e / f4, q = e - tok * f4;
                 const int jl = tok / nsample, s = tok - jl * nsample;
                 const int k = sidx[s * kStride + jl];
-                if (q >= 2) {
-                    v[u] = q - 2 < c4 ? __ldg(reinterpret_cast<const float4 *>(features_t + (size_t)k * c) + (q - 2))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    const float gx = __ldg(xyz + (size_t)k * 3 + 0), gy = __ldg(xyz + (size_t)k * 3 + 1),
-                                gz = __ldg(xyz + (size_t)k * 3 + 2);
-                    const float dx = gx - sctr[jl * 3 + 0], dy = gy - sctr[jl * 3 + 1], dz = gz - sctr[jl * 3 + 2];
-                    if (q == 0) {
-                        const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.norm(...)**2, PB/pointnet2_utils.py:592
-                        v[u] = make_float4(gx, gy, gz, expf(-(dist * dist) / two_r2) / dens_norm);
-                        if (ibase) ibase[tok] = k;
-                    } else {
-                        v[u] = make_float4(dx / radius, dy / radius, dz / radius, 0.f);
-                    }
-                }
+                v[u] = q < c4 ? __ldg(reinterpret_cast<const float4 *>(features_t + (size_t)k * c) + q)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
         for (int u = 0; u < kChunk; u++) {
-            const int e = e0 + u * kThreads + t;
-            if (e < total) __stcs(o4 + e, v[u]);
+            const int e = e0 + u * kTokThreads + t;
+            if (e < total) {
+                const int tok = e / f4, q = e - tok * f4;
+                __stcs(o4 + (size_t)tok * p4 + 2 + q, v[u]);
+            }
         }
     }
 }
@@ -195,7 +203,7 @@ extern "C" int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, i
     const float two_r2 = (float)(2.0 * (double)radius * (double)radius);
     const float dens_norm = (float)(2.5 * (double)radius);
     dim3 grid(pdab::div_up(m, kThreads), b);
-    pda_group_tokens_kernel<<<grid, kThreads, smem, pdab::to_stream(stream)>>>(
+    pda_group_tokens_kernel<<<grid, kTokThreads, smem, pdab::to_stream(stream)>>>(
         c, n, m, pitch, radius, radius * radius, two_r2, dens_norm, nsample, xyz, new_xyz, features_t, out, idx_out);
     PDAB_LAUNCH_CHECK();
     return 0;

@@ -45,9 +45,18 @@ __device__ __forceinline__ void dense(const float *__restrict__ W, const float *
     }
 }
 
+constexpr int kMlpThreads = 256;  // 128 scan threads + 128 helpers; all 8 warps run the MLP phase
+
 // C0P: input width padded to a multiple of 4 (3 + C real channels, rest zero weights/inputs)
+//
+// Phase 1: threads 0..127 each scan the cloud for one centre (hit lists in shared memory).
+// Phase 2: one LANE per (centre, neighbour): a warp takes one centre (nsample = 32) or two (nsample = 16) at a
+// time, every lane pushes its neighbour through the three layers with the weights broadcast from shared memory,
+// and the channel maximum over the neighbourhood is a shuffle butterfly.  (One thread per centre, the first
+// version, left the FMA pipe idle: 2 warps per scheduler each on a 4-cycle dependent chain; per-sample lanes
+// give 8 resident warps per scheduler of independent work.)
 template <int C0P, int C1, int C2, int C3>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kMlpThreads, 2)
 sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *__restrict__ xyz,
                        const float *__restrict__ new_xyz, const float *__restrict__ features,
                        const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ W2,
@@ -61,25 +70,28 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     float *sb1 = sW3 + C3 * C2;
     float *sb2 = sb1 + C1;
     float *sb3 = sb2 + C2;
-    int *sidx = reinterpret_cast<int *>(sb3 + C3);  // nsample x kStride
+    float *sctr = sb3 + C3;                                           // 3 x kThreads
+    float *sout = sctr + 3 * kThreads;                                // C3 x (kThreads + 1)
+    int *sidx = reinterpret_cast<int *>(sout + C3 * kStride);         // nsample x kStride
 
     const int scene = blockIdx.y;
-    const int t = threadIdx.x;
-    const int j = blockIdx.x * kThreads + t;
-    const bool active = j < m;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int j0 = blockIdx.x * kThreads;
+    const int j = j0 + t;
+    const bool active = t < kThreads && j < m;
     const int c0 = 3 + c;
     xyz += (size_t)scene * n * 3;
     if (c > 0) features += (size_t)scene * c * n;
 
-    for (int i = t; i < C1 * C0P; i += kThreads) {
+    for (int i = t; i < C1 * C0P; i += kMlpThreads) {
         const int r = i / C0P, q = i - r * C0P;
         sW1[i] = q < c0 ? W1[r * c0 + q] : 0.f;
     }
-    for (int i = t; i < C2 * C1; i += kThreads) sW2[i] = W2[i];
-    for (int i = t; i < C3 * C2; i += kThreads) sW3[i] = W3[i];
-    for (int i = t; i < C1; i += kThreads) sb1[i] = b1[i];
-    for (int i = t; i < C2; i += kThreads) sb2[i] = b2[i];
-    for (int i = t; i < C3; i += kThreads) sb3[i] = b3[i];
+    for (int i = t; i < C2 * C1; i += kMlpThreads) sW2[i] = W2[i];
+    for (int i = t; i < C3 * C2; i += kMlpThreads) sW3[i] = W3[i];
+    for (int i = t; i < C1; i += kMlpThreads) sb1[i] = b1[i];
+    for (int i = t; i < C2; i += kMlpThreads) sb2[i] = b2[i];
+    for (int i = t; i < C3; i += kMlpThreads) sb3[i] = b3[i];
 
     float cx = 0.f, cy = 0.f, cz = 0.f;
     if (active) {
@@ -88,29 +100,54 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
         cy = ctr[1];
         cz = ctr[2];
     }
+    if (t < kThreads) {
+        sctr[t * 3 + 0] = cx;
+        sctr[t * 3 + 1] = cy;
+        sctr[t * 3 + 2] = cz;
+    }
     pdab::ball_scan_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2, nsample, tile, sidx);
-    if (!active) return;
 
-    float mx[C3];
-#pragma unroll
-    for (int r = 0; r < C3; r++) mx[r] = 0.f;
-
-    for (int s = 0; s < nsample; s++) {
-        const int k = sidx[s * kStride + t];
+    const int nctr = min(kThreads, m - j0);
+    // lanes per centre: 32 (nsample 17..32: idle lanes repeat sample 0, harmless for a max), 16, 8, ...
+    const int lpc = nsample > 16 ? 32 : (nsample > 8 ? 16 : 8);
+    const int cpw = 32 / lpc;                       // centres per warp pass
+    const int sub = lane / lpc, sl = lane % lpc;    // which centre of the pass, which sample lane
+    for (int base = warp * cpw; base < nctr; base += (kMlpThreads / 32) * cpw) {
+        const int jl = min(base + sub, nctr - 1);   // tail: duplicate the last centre (its store is idempotent)
+        const int s = min(sl, nsample - 1);         // nsample <= lpc <= 32: one neighbour per lane
+        const int k = sidx[s * kStride + jl];
         float in[C0P];
-        in[0] = __ldg(xyz + (size_t)k * 3 + 0) - cx;  // grouped_xyz -= new_xyz (PB/pointnet2_utils.py:692)
-        in[1] = __ldg(xyz + (size_t)k * 3 + 1) - cy;
-        in[2] = __ldg(xyz + (size_t)k * 3 + 2) - cz;
+        in[0] = __ldg(xyz + (size_t)k * 3 + 0) - sctr[jl * 3 + 0];  // grouped_xyz -= new_xyz (PB/pointnet2_utils.py:692)
+        in[1] = __ldg(xyz + (size_t)k * 3 + 1) - sctr[jl * 3 + 1];
+        in[2] = __ldg(xyz + (size_t)k * 3 + 2) - sctr[jl * 3 + 2];
 #pragma unroll
         for (int q = 3; q < C0P; q++) in[q] = (q - 3 < c) ? __ldg(features + (size_t)(q - 3) * n + k) : 0.f;
         float h1[C1], h2[C2];
         dense<C0P, C1, true>(sW1, sb1, in, h1);
         dense<C1, C2, true>(sW2, sb2, h1, h2);
-        dense<C2, C3, false>(sW3, sb3, h2, mx);
-    }
-    float *o = out + (size_t)scene * C3 * m + j;
+        // last layer: each output channel is reduced over the neighbourhood as soon as it is computed
+#pragma unroll 4
+        for (int r = 0; r < C3; r++) {
+            float acc = sb3[r];
+            const float4 *w4 = reinterpret_cast<const float4 *>(sW3 + r * C2);
 #pragma unroll
-    for (int r = 0; r < C3; r++) __stcs(o + (size_t)r * m, mx[r]);
+            for (int q = 0; q < C2 / 4; q++) {
+                const float4 w = w4[q];
+                acc = fmaf(w.x, h2[4 * q + 0], acc);
+                acc = fmaf(w.y, h2[4 * q + 1], acc);
+                acc = fmaf(w.z, h2[4 * q + 2], acc);
+                acc = fmaf(w.w, h2[4 * q + 3], acc);
+            }
+            float v = fmaxf(acc, 0.f);
+            for (int off = lpc >> 1; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+            if (sl == (r % lpc)) sout[r * kStride + jl] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < C3 * nctr; i += kMlpThreads) {
+        const int r = i / nctr, jl = i - r * nctr;
+        __stcs(out + ((size_t)scene * C3 + r) * m + j0 + jl, sout[r * kStride + jl]);
+    }
 }
 
 template <int C0P, int C1, int C2, int C3>
@@ -118,12 +155,12 @@ int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const f
                   const float *features, const float *const *W, const float *const *B, float *out,
                   cudaStream_t stream) {
     const size_t smem = sizeof(float4) * pdab::kScanTile +
-                        sizeof(float) * (C1 * C0P + C2 * C1 + C3 * C2 + C1 + C2 + C3) +
+                        sizeof(float) * (C1 * C0P + C2 * C1 + C3 * C2 + C1 + C2 + C3 + 3 * kThreads + C3 * kStride) +
                         sizeof(int) * (size_t)nsample * kStride;
     auto kern = sa_fused_narrow_kernel<C0P, C1, C2, C3>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(pdab::div_up(m, kThreads), b);
-    kern<<<grid, kThreads, smem, stream>>>(c, n, m, radius * radius, nsample, xyz, new_xyz, features, W[0], B[0], W[1],
+    kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, radius * radius, nsample, xyz, new_xyz, features, W[0], B[0], W[1],
                                            B[1], W[2], B[2], out);
     PDAB_LAUNCH_CHECK();
     return 0;
@@ -140,7 +177,7 @@ extern "C" int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsamp
         return PDAB_EINVAL;
     if (b == 0 || m == 0) return 0;
     if (dims_host[0] != 3 + c) return PDAB_EINVAL;
-    if (nlayers != 3 || nsample > 64 || b > 65535) return PDAB_EUNSUPPORTED;
+    if (nlayers != 3 || nsample > 32 || b > 65535) return PDAB_EUNSUPPORTED;
     for (int l = 0; l < 3; l++)
         if (!weights_host[l] || !biases_host[l]) return PDAB_EINVAL;
     cudaStream_t s = pdab::to_stream(stream);

@@ -222,7 +222,7 @@ def pda_group_tokens(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
 
 def sa_fused_supported(c0: int, dims: Sequence[int], nsample: int) -> bool:
     """Shapes the fused plain-SA kernel covers (see csrc/sa_fused.cu)."""
-    return len(dims) == 3 and nsample <= 64 and c0 <= 8 and tuple(dims) in ((16, 16, 32), (32, 32, 64))
+    return len(dims) == 3 and nsample <= 32 and c0 <= 8 and tuple(dims) in ((16, 16, 32), (32, 32, 64))
 
 
 def sa_fused(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
