@@ -113,6 +113,25 @@ int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, int nsample,
                           const float *new_xyz, const float *features_t, float *out, int *idx_out,
                           pdab_stream_t stream);
 
+/* Row-wise kernels of the PDA block, each fused with the hi/lo split (hi = top 19 bits, exactly representable in
+ * TF32; lo = value - hi) that feeds error-compensated 3xTF32 tensor-core projections.  `tokens` rows of e = 4c
+ * channels (e in {256, 512}); all tensors contiguous fp32.
+ * replaces: torch.cat / mul / copy / nn.LayerNorm / residual add / ReLU / max-pool launches of the PDA block,
+ *           PB/pointnet2_modules.py:893-931, PB/PointFormer.py:28-38. */
+/* row = LayerNorm(cat[pos (c), feat*scale (c), feat (c), glob[row / nsample] (c)]); feat = x[row, 8 : 8+c] with row
+ * pitch xpitch (the pdab_pda_group_tokens layout); pos (tokens,c), scale (tokens), glob (tokens/nsample, c). */
+int pdab_pda_assemble_ln_split(long long tokens, int nsample, int c, int xpitch, const float *pos, const float *x,
+                               const float *scale, const float *glob, const float *gamma, const float *beta,
+                               float eps, float *hi, float *lo, pdab_stream_t stream);
+/* (hi, lo) = split(LayerNorm((a_hi + a_lo) + o)) */
+int pdab_add_ln_split(long long tokens, int e, const float *a_hi, const float *a_lo, const float *o,
+                      const float *gamma, const float *beta, float eps, float *hi, float *lo, pdab_stream_t stream);
+/* (hi, lo) = split(relu(h)), n elements (n % 4 == 0) */
+int pdab_relu_split(long long n, const float *h, float *hi, float *lo, pdab_stream_t stream);
+/* out[g, :] = max over the nsample rows of group g of ((a_hi + a_lo) + f);  out (groups, e) */
+int pdab_add_maxpool(long long groups, int nsample, int e, const float *a_hi, const float *a_lo, const float *f,
+                     float *out, pdab_stream_t stream);
+
 /* Fused plain set-abstraction scale: ball query -> group (xyz centred) -> shared MLP
  * (1x1 conv with eval-mode BatchNorm folded in, ReLU) x nlayers -> max over nsample.
  * The grouped tensor never reaches HBM.

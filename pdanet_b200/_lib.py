@@ -31,6 +31,10 @@ _SIGNATURES = {
     "pdab_topk_ctr": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_pda_group": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_pda_group_tokens": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_pda_assemble_ln_split": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "pdab_add_ln_split": (_i, [C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "pdab_relu_split": (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
+    "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_nms_workspace_bytes": (_sz, [_i]),
     "pdab_nms_device": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),

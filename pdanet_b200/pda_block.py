@@ -54,7 +54,9 @@ class Linear3x:
         self.bias = bias.detach().float().contiguous()
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        x_hi, x_lo = _split_tf32(x)
+        return self.split_call(*_split_tf32(x))
+
+    def split_call(self, x_hi: torch.Tensor, x_lo: torch.Tensor) -> torch.Tensor:
         with _TF32(True):
             y = torch.addmm(self.bias, x_hi, self.w_hi)
             y.addmm_(x_hi, self.w_lo)
@@ -130,18 +132,14 @@ class PDAScalePlan:
         glob = torch.cat([new_xyz.reshape(G, 3), centre_feature_t.reshape(G, C)], dim=1)
         glob = F.relu_(self.global_[1](F.relu_(self.global_[0](glob))))
 
-        tokens = torch.empty(G, ns, 4 * C, dtype=torch.float32, device=X.device)
-        t2 = tokens.view(T, 4 * C)
-        t2[:, 0:C] = pos
-        torch.mul(feat, scale, out=t2[:, C:2 * C])
-        t2[:, 2 * C:3 * C] = feat
-        tokens[:, :, 3 * C:] = glob.unsqueeze(1)
-
-        # pre-norm transformer over each neighbourhood (PB/PointFormer.py:28-38); residuals follow the LayerNorms
+        # token assembly + LayerNorm 1 + hi/lo split in one pass (csrc/pda_elem.cu); the normalised tokens exist
+        # only as (hi, lo), which add back to the fp32 value exactly
         E, H = 4 * C, self.heads
         hd = E // H
-        y = self.norm1(t2)
-        qkv = self.in_proj(y).view(G, ns, 3, H, hd)
+        y_hi, y_lo = ops.pda_assemble_ln_split(pos, X, scale.reshape(T), glob, ns, self.norm1)
+
+        # pre-norm transformer over each neighbourhood (PB/PointFormer.py:28-38); residuals follow the LayerNorms
+        qkv = self.in_proj.split_call(y_hi, y_lo).view(G, ns, 3, H, hd)
         q = qkv[:, :, 0].permute(0, 2, 1, 3) * (1.0 / math.sqrt(hd))
         k = qkv[:, :, 1].permute(0, 2, 3, 1)
         v = qkv[:, :, 2].permute(0, 2, 1, 3)
@@ -149,10 +147,8 @@ class PDAScalePlan:
             att = torch.softmax(torch.matmul(q, k), dim=-1)
             ctx = torch.matmul(att, v)                       # (G, H, ns, hd)
         ctx = ctx.permute(0, 2, 1, 3).reshape(T, E)
-        y = y + self.out_proj(ctx)
-        y = self.norm2(y)
-        y = y + self.lin2(F.relu_(self.lin1(y)))
-
-        pooled = y.view(G, ns, E).max(dim=1)[0]                # max-pool over the neighbourhood (:931)
+        z_hi, z_lo = ops.add_ln_split(y_hi, y_lo, self.out_proj(ctx), self.norm2)   # LN2(y + attn)
+        h_hi, h_lo = ops.relu_split(self.lin1.split_call(z_hi, z_lo))
+        pooled = ops.add_maxpool(z_hi, z_lo, self.lin2.split_call(h_hi, h_lo), G, ns)  # max_s (z + ffn), (:931)
         out = F.relu_(self.fin[1](F.relu_(self.fin[0](pooled))))  # (G, C_out)
         return out.view(B, M, -1).permute(0, 2, 1)

@@ -29,5 +29,16 @@ elif op == "ball_query":
     xyz = scene_xyz(N + M, B, N).cuda()
     for _ in range(3):
         ops.ball_query(r, ns, xyz, xyz[:, :M].contiguous())
+elif op == "sa_fused":
+    import math
+    B, N, M, ns, c1, c2, c3 = a
+    r = 0.8 if ns > 16 else 0.2
+    xyz = scene_xyz(N + M, B, N).cuda()
+    feats = torch.rand(B, 1, N, device="cuda")
+    dims = [4, c1, c2, c3]
+    ws = [torch.randn(dims[i + 1], dims[i], device="cuda") / math.sqrt(dims[i]) for i in range(3)]
+    bs = [torch.randn(dims[i + 1], device="cuda") * 0.1 for i in range(3)]
+    for _ in range(3):
+        ops.sa_fused(r, ns, xyz, xyz[:, :M].contiguous(), feats, ws, bs)
 torch.cuda.synchronize()
 print("done")
