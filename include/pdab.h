@@ -146,6 +146,52 @@ int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsample, const f
                   const float *features, int nlayers, const int *dims_host, const float *const *weights_host,
                   const float *const *biases_host, float *out, pdab_stream_t stream);
 
+/* ---- tensor-core (tcgen05 / TMEM) contractions ---------------------------------- */
+
+/* Epilogues of pdab_tc_linear. */
+#define PDAB_EPI_STORE 0        /* out = acc + bias */
+#define PDAB_EPI_RELU 1         /* out = relu(acc + bias) */
+#define PDAB_EPI_ADD_LN 2       /* out = LayerNorm(acc + bias + residual) over the full row (nout in {256, 512}) */
+#define PDAB_EPI_ADD_MAXPOOL 3  /* out[g] = max over the nsample rows of group g of (acc + bias + residual) */
+#define PDAB_EPI_RELU_MAXPOOL 4 /* out[g] = max over the nsample rows of group g of relu(acc + bias) */
+
+/* out = epilogue(a (rows,k) . W (nout,k)^T + bias) on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+ * fp32 accumulation in TMEM).  npass = 1: operands rounded to TF32 (the precision class of the reference's cuDNN
+ * 1x1 convolutions); npass = 3: error-compensated 3xTF32 (hi/lo operand split, fp32-level results, what the
+ * reference's nn.Linear / nn.MultiheadAttention projections compute).
+ * replaces: the Conv2d(1x1)+BN+ReLU layers and max_pool2d of a plain SA scale, PB/pointnet2_modules.py:1478-1491,
+ *           1657-1672 (BN folded into W / bias by the caller), and the in_proj / out_proj / linear1 / linear2 GEMMs
+ *           of TransformerEncoderLayerPreNorm with the LayerNorm / residual / ReLU / max-pool between them,
+ *           PB/PointFormer.py:28-38, PB/pointnet2_modules.py:929-931.
+ * a (rows, lda) fp32; w_packed: W pre-packed by pdab_tc_pack_weights (bn = 128 or 256 columns per accumulator
+ * chunk); bias (nout) or NULL; residual (rows, ldr) for the ADD_* epilogues; gamma/beta/eps for ADD_LN;
+ * nsample in {16, 32} for the *_MAXPOOL epilogues (rows % nsample == 0; out has rows / nsample rows).
+ * k, lda, ldo, ldr, nout multiples of 4; all pointers 16-byte aligned. */
+int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilogue, const float *a, int lda,
+                   const float *w_packed, const float *bias, const float *residual, int ldr, const float *gamma,
+                   const float *beta, float eps, int nsample, float *out, int ldo, pdab_stream_t stream);
+
+/* Number of floats pdab_tc_pack_weights writes for a (nout, k) weight matrix. */
+size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn);
+/* Packs W (nout, k) row-major (device) into the shared-memory image the tensor-core kernels stream:
+ * [column chunk of bn][k-atom of 32][hi | lo][bn rows x 128 B, K-major, 128-byte swizzle], zero padded.
+ * npass = 3 writes the (hi, lo) TF32 split, npass = 1 the round-to-nearest TF32 value.  If xyz_last > 0 the first
+ * xyz_last input columns of W are moved behind the others (the gather prologue of pdab_tc_sa_gather_linear feeds
+ * [features, centred xyz] while the reference's Conv2d expects [xyz, features], PB/pointnet2_utils.py:692-699). */
+int pdab_tc_pack_weights(int nout, int k, int npass, int bn, int xyz_last, const float *w, float *packed,
+                         pdab_stream_t stream);
+
+/* First layer of a plain SA scale with the grouping fused into the GEMM prologue:
+ * out[(b,j,s), :] = relu(W . [features_t[b, idx[b,j,s], :], xyz[b, idx[b,j,s]] - new_xyz[b,j]] + bias).
+ * The grouped (B, 3+C, M, nsample) tensor of the reference never exists.
+ * replaces: grouping_operation x2 + centre subtraction + cat + first Conv2d/BN/ReLU,
+ *           PB/pointnet2_utils.py:689-704, PB/pointnet2_modules.py:1657-1658.
+ * idx (B,M,nsample) from pdab_ball_query; features_t (B,N,C) POINT-major; w_packed packed with bn = 256 and
+ * xyz_last = 3; out (B*M*nsample, ldo). */
+int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
+                             const float *features_t, const float *xyz, const float *new_xyz, const float *w_packed,
+                             const float *bias, float *out, int ldo, pdab_stream_t stream);
+
 /* ---- iou3d_nms_cuda -------------------------------------------------------- */
 
 /* Bytes of device workspace pdab_nms_device needs for n boxes. */

@@ -36,6 +36,10 @@ _SIGNATURES = {
     "pdab_relu_split": (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
     "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
+    "pdab_tc_packed_floats": (_sz, [_i, _i, _i, _i]),
+    "pdab_tc_pack_weights": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdab_tc_sa_gather_linear": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pdab_nms_workspace_bytes": (_sz, [_i]),
     "pdab_nms_device": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),
     "pdab_nms_batched": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),

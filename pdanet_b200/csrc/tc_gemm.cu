@@ -1,0 +1,693 @@
+// tcgen05 / TMEM GEMM for the dense contractions of the PDA-SSD hot path (sm_100a only).
+//
+//   out = epilogue( A[T,K] . W[Nout,K]^T + bias )
+//
+// with A produced on the fly by a fused PROLOGUE (plain rows, or the ball-query gather of a set-abstraction scale)
+// and the accumulator consumed in TMEM by a fused EPILOGUE (bias, ReLU, residual + LayerNorm, residual / ReLU +
+// neighbourhood max-pool).  It replaces, for the wide plain-SA scales, the reference's group_points -> cat ->
+// 3 x (cuDNN 1x1 conv, BN, ReLU) -> max_pool2d chain (PB/pointnet2_modules.py:1655-1672) and, for
+// the PDA block, the in_proj / out_proj / linear1 / linear2 GEMMs of TransformerEncoderLayerPreNorm with the
+// LayerNorm / residual / ReLU / max-pool launches between them (PB/PointFormer.py:28-38, PB/pointnet2_modules.py:929-933).
+//
+// Arithmetic.  kind::tf32 tensor-core products accumulated in fp32 in TMEM.
+//   NPASS = 1 : operands rounded to TF32 (cvt.rna) — the precision class of the reference's cuDNN convolutions.
+//   NPASS = 3 : error-compensated "3xTF32": x = x_hi + x_lo, w = w_hi + w_lo with the hi parts exactly representable
+//               in TF32 (top 19 bits), acc += x_hi w_lo + x_lo w_hi + x_hi w_hi.  The dropped x_lo w_lo term is
+//               O(2^-22) relative: fp32-level results (what nn.Linear computes in the reference) at 3 MMAs / k-step.
+//
+// Mapping to the SM.  One CTA per SM, persistent over (row tile, column group) work items; 10 warps:
+//   warp 0      W loader   : one lane issues cp.async.bulk (TMA engine, UBLKCP) of pre-packed weight tiles -> smem
+//   warp 1      MMA issuer : one lane issues tcgen05.mma (M=128, N=BN, K=8 per instruction), tcgen05.commit -> mbarriers
+//   warps 2-5   A producers: global -> registers -> (hi, lo) split -> 128B-swizzled K-major smem tiles
+//   warps 6-9   epilogue   : tcgen05.ld (TMEM -> registers) -> fused epilogue -> global
+// Tiles: 128 rows (= TMEM lanes) x BN columns (fp32 accumulator columns) x 32-float k-atoms (one 128-byte swizzle
+// row).  Smem ring of S stages {A_hi, A_lo, W_hi, W_lo}; TMEM holds two accumulator stages (or one 512-column full
+// row for the LayerNorm epilogue) so the epilogue of item i overlaps the main loop of item i+1.
+// Weights are packed once (host side, pdanet_b200/tc_pack.py) into the exact smem image of each (column chunk, k-atom)
+// tile — canonical K-major SWIZZLE_128B layout — so a stage's weights are ONE contiguous bulk copy.
+#include "common.cuh"
+
+namespace {
+
+using u32 = uint32_t;
+using u64 = uint64_t;
+
+constexpr int BM = 128;            // rows per tile (TMEM lanes)
+constexpr int BK = 32;             // floats per k-atom (128 B swizzle row)
+constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+constexpr int kThreads = 320;
+constexpr int kTmemCols = 512;
+
+enum ALoad { A_ROWS = 0, A_GATHER = 1 };
+enum Epi { E_STORE = 0, E_RELU = 1, E_ADD_LN = 2, E_ADD_MAXPOOL = 3, E_RELU_MAXPOOL = 4 };
+
+struct GemmParams {
+    // A operand
+    const float *A;      // (T, lda) rows                                   [A_ROWS]
+    int lda;
+    long long T;         // rows
+    int K;               // logical K (columns of A used)
+    int KA;              // k-atoms = ceil(K / 32)
+    // gather prologue [A_GATHER]: row t -> point idx[t] of scene t / (M*ns); A row = [feat_t[b, i, 0:C], xyz[b,i]-new_xyz[b,j]]
+    const int *idx;      // (B, M, ns) flat
+    const float *feat_t; // (B, Nsrc, C) point-major
+    const float *xyz;    // (B, Nsrc, 3)
+    const float *new_xyz;  // (B, M, 3)
+    int C, Nsrc, M, ns;
+    // weights
+    const float *Wp;     // packed tiles [chunk][k-atom][hi|lo][BN*32]
+    const float *bias;   // (Nout) or null
+    int Nout;            // logical output columns
+    int n_groups;        // column groups (each NCH chunks of BN)
+    // output
+    float *out;
+    int ldo;
+    // epilogue extras
+    const float *R;      // residual (T, ldr)
+    int ldr;
+    const float *gamma, *beta;
+    float eps;
+    long long n_items;
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u32 bar, u32 parity) {
+    u32 ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz; a healthy wait is microseconds
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(u32 dst_smem, u32 ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(u32 taddr, u32 ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, issued by ONE thread.
+__device__ __forceinline__ void umma_tf32(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on an mbarrier when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(u32 bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` of the warp gets columns [c, c+32) of TMEM lane (warp%4)*32+lane.
+__device__ __forceinline__ void tmem_ld32(u32 taddr, float (&v)[32]) {
+    u32 r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(u32 taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};\n"
+        "tcgen05.wait::st.sync.aligned;" ::"r"(__float_as_uint(v[0])),
+        "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+        "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])),
+        "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])),
+        "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
+        "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31])), "r"(taddr)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor, canonical K-major SWIZZLE_128B tile (rows of 128 B, 8-row groups 1024 B apart):
+// start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 >> 4 | version 1 (sm_100) | layout 2 (SW128).
+__device__ __forceinline__ u64 umma_desc(u32 smem_addr) {
+    return (u64)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128.
+template <int BN>
+__device__ __forceinline__ constexpr u32 umma_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_rna(float v) {
+    u32 r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------- kernel
+
+template <int NPASS, int BN>
+struct Cfg {
+    static constexpr int W_TILE_BYTES = BN * BK * 4;                       // one of {hi, lo}
+    static constexpr int STAGE_BYTES = (NPASS == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
+    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct Pipe {
+    int stage = 0;
+    u32 phase = 0;
+    template <int S>
+    __device__ __forceinline__ void advance() {
+        if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p) {
+    using C = Cfg<NPASS, BN>;
+    constexpr int S = C::STAGES;
+    constexpr int ACC_STAGES = (NCH * BN * 2 <= kTmemCols) ? 2 : 1;
+    constexpr int ACC_COLS = kTmemCols / ACC_STAGES;  // column stride between accumulator stages
+
+    extern __shared__ uint8_t smem_raw[];
+    const u32 smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const u32 bar_base = smem_base + S * C::STAGE_BYTES;
+    // barriers (8 B each): full_w[S], full_a[S], empty[S], acc_full[2], acc_empty[2]; then the TMEM base address
+    auto full_w = [&](int s) { return bar_base + 8u * s; };
+    auto full_a = [&](int s) { return bar_base + 8u * (S + s); };
+    auto empty = [&](int s) { return bar_base + 8u * (2 * S + s); };
+    auto acc_full = [&](int a) { return bar_base + 8u * (3 * S + a); };
+    auto acc_empty = [&](int a) { return bar_base + 8u * (3 * S + 2 + a); };
+    const u32 tmem_slot = bar_base + 8u * (3 * S + 4);
+    volatile u32 *tmem_slot_ptr = reinterpret_cast<volatile u32 *>(smem + S * C::STAGE_BYTES + 8 * (3 * S + 4));
+
+    auto a_hi = [&](int s) { return smem_base + (u32)s * C::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };                       // NPASS == 3 only
+    auto w_hi = [&](int s) { return a_hi(s) + (NPASS == 3 ? 2 : 1) * A_TILE_BYTES; };
+    auto w_lo = [&](int s) { return w_hi(s) + C::W_TILE_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(full_w(s), 1);
+            mbar_init(full_a(s), 4);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = *tmem_slot_ptr;
+
+    const int KA = p.KA;
+    const long long n_items = p.n_items;
+
+    if (warp == 0) {
+        // ===================================================================== W loader
+        if (lane == 0) {
+            Pipe pipe;
+            constexpr u32 BYTES = (NPASS == 3 ? 2 : 1) * C::W_TILE_BYTES;
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int n_group = (int)(item % p.n_groups);
+                for (int c = 0; c < NCH; c++) {
+                    const int chunk = n_group * NCH + c;
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(p.Wp) + (size_t)chunk * KA * BYTES;
+                    for (int ka = 0; ka < KA; ka++) {
+                        mbar_wait(empty(pipe.stage), pipe.phase ^ 1);
+                        mbar_arrive_expect_tx(full_w(pipe.stage), BYTES);
+                        bulk_g2s(w_hi(pipe.stage), src + (size_t)ka * BYTES, BYTES, full_w(pipe.stage));
+                        pipe.advance<S>();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            Pipe pipe;
+            int as = 0;
+            u32 aphase = 0;
+            constexpr u32 idesc = umma_idesc<BN>();
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                mbar_wait(acc_empty(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+                tc_fence_after();
+                for (int c = 0; c < NCH; c++) {
+                    const u32 d = tmem_base + (u32)(as * ACC_COLS + c * BN);
+                    for (int ka = 0; ka < KA; ka++) {
+                        mbar_wait(full_w(pipe.stage), pipe.phase);
+                        mbar_wait(full_a(pipe.stage), pipe.phase);
+                        tc_fence_after();
+                        // k-steps of 8 inside the atom; the last atom may be partially filled (zero padded)
+                        const int ksteps = (ka == KA - 1) ? ((p.K - ka * BK + 7) >> 3) : (BK / 8);
+                        for (int kk = 0; kk < ksteps; kk++) {
+                            const u32 acc = (ka | kk) ? 1u : 0u;
+                            const u64 ah = umma_desc(a_hi(pipe.stage) + kk * 32);
+                            const u64 wh = umma_desc(w_hi(pipe.stage) + kk * 32);
+                            if (NPASS == 3) {
+                                const u64 al = umma_desc(a_lo(pipe.stage) + kk * 32);
+                                const u64 wl = umma_desc(w_lo(pipe.stage) + kk * 32);
+                                umma_tf32(d, ah, wl, idesc, acc);   // small terms first
+                                umma_tf32(d, al, wh, idesc, 1u);
+                                umma_tf32(d, ah, wh, idesc, 1u);
+                            } else {
+                                umma_tf32(d, ah, wh, idesc, acc);
+                            }
+                        }
+                        umma_commit(empty(pipe.stage));  // frees the smem stage once these MMAs have read it
+                        pipe.advance<S>();
+                    }
+                }
+                umma_commit(acc_full(as));               // accumulator complete -> epilogue
+                if (ACC_STAGES == 2) {
+                    as ^= 1;
+                    if (as == 0) aphase ^= 1;
+                } else {
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================================================================== A producers (128 threads)
+        const int pt = threadIdx.x - 64;      // 0..127
+        const int chunk = pt & 7;             // 16-byte chunk inside the 128-byte row
+        const int r0 = pt >> 3;               // rows r0 + 16 i, i = 0..7
+        Pipe pipe;
+        float4 cur[8], nxt[8];
+        int src_row[8];                       // A_GATHER: flat source point row (b*Nsrc + i) per owned row, -1 = padding
+
+        auto load_rows_meta = [&](long long m0) {
+            if (ALOAD == A_GATHER) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const long long t = m0 + r0 + 16 * i;
+                    src_row[i] = -1;
+                    if (t < p.T) {
+                        const long long b = t / ((long long)p.M * p.ns);
+                        src_row[i] = (int)(b * p.Nsrc + __ldg(p.idx + t));
+                    }
+                }
+            }
+        };
+        auto load_atom = [&](long long m0, int ka, float4 (&v)[8]) {
+            const int k = ka * BK + chunk * 4;
+            if (ALOAD == A_ROWS) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const long long t = m0 + r0 + 16 * i;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t < p.T && k < p.K) v[i] = __ldg(reinterpret_cast<const float4 *>(p.A + t * p.lda + k));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src_row[i] >= 0) {
+                        if (k < p.C) {
+                            v[i] = __ldg(reinterpret_cast<const float4 *>(p.feat_t + (size_t)src_row[i] * p.C + k));
+                        } else if (k == p.C) {  // the three centred coordinates follow the C features
+                            const long long t = m0 + r0 + 16 * i;
+                            const long long g = t / p.ns;  // flat (b, centre)
+                            const float *q = p.xyz + (size_t)src_row[i] * 3;
+                            const float *c = p.new_xyz + g * 3;
+                            v[i] = make_float4(__ldg(q) - __ldg(c), __ldg(q + 1) - __ldg(c + 1),
+                                               __ldg(q + 2) - __ldg(c + 2), 0.f);
+                        }
+                    }
+                }
+            }
+        };
+
+        // flattened (item, chunk pass, k-atom) sequence with a one-step register prefetch
+        long long item = blockIdx.x;
+        int c = 0, ka = 0;
+        bool have = item < n_items;
+        if (have) {
+            load_rows_meta((item / p.n_groups) * BM);
+            load_atom((item / p.n_groups) * BM, 0, cur);
+        }
+        while (have) {
+            // advance to the next step and issue its loads before storing the current one
+            long long nitem = item;
+            int nc = c, nka = ka + 1;
+            if (nka == KA) {
+                nka = 0;
+                if (++nc == NCH) {
+                    nc = 0;
+                    nitem += gridDim.x;
+                }
+            }
+            const bool nhave = nitem < n_items;
+            if (nhave) {
+                if (nitem != item) load_rows_meta((nitem / p.n_groups) * BM);
+                load_atom((nitem / p.n_groups) * BM, nka, nxt);
+            }
+            mbar_wait(empty(pipe.stage), pipe.phase ^ 1);
+            uint8_t *ah = smem + (size_t)pipe.stage * C::STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = r0 + 16 * i;
+                const u32 off = (u32)r * 128u + (u32)((chunk ^ (r & 7)) << 4);
+                const float4 v = cur[i];
+                if (NPASS == 3) {
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    *reinterpret_cast<float4 *>(ah + off) = h;
+                    *reinterpret_cast<float4 *>(ah + A_TILE_BYTES + off) =
+                        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                } else {
+                    *reinterpret_cast<float4 *>(ah + off) =
+                        make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                }
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(pipe.stage));
+            pipe.advance<S>();
+#pragma unroll
+            for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+            item = nitem;
+            c = nc;
+            ka = nka;
+            have = nhave;
+        }
+    } else {
+        // ===================================================================== epilogue (128 threads, row per thread)
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+        const int row_in_tile = q * 32 + lane;
+        int as = 0;
+        u32 aphase = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const long long m0 = (item / p.n_groups) * BM;
+            const int n_group = (int)(item % p.n_groups);
+            const long long row = m0 + row_in_tile;
+            const bool row_ok = row < p.T;
+            mbar_wait(acc_full(as), aphase);
+            tc_fence_after();
+            const u32 tacc = tmem_base + ((u32)(q * 32) << 16) + (u32)(as * ACC_COLS);
+
+            if (EPI == E_STORE || EPI == E_RELU) {
+                for (int c = 0; c < NCH; c++) {
+                    for (int j = 0; j < BN; j += 32) {
+                        float v[32];
+                        tmem_ld32(tacc + c * BN + j, v);
+                        const int n0 = (n_group * NCH + c) * BN + j;
+                        if (row_ok) {
+                            float *o = p.out + row * p.ldo + n0;
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4) {
+                                if (n0 + e < p.Nout) {
+                                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (p.bias) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + e));
+                                    float4 y = make_float4(v[e] + b4.x, v[e + 1] + b4.y, v[e + 2] + b4.z, v[e + 3] + b4.w);
+                                    if (EPI == E_RELU) {
+                                        y.x = fmaxf(y.x, 0.f);
+                                        y.y = fmaxf(y.y, 0.f);
+                                        y.z = fmaxf(y.z, 0.f);
+                                        y.w = fmaxf(y.w, 0.f);
+                                    }
+                                    *reinterpret_cast<float4 *>(o + e) = y;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if (EPI == E_ADD_MAXPOOL || EPI == E_RELU_MAXPOOL) {
+                // max over the ns consecutive rows of each neighbourhood (ns in {16, 32}: inside one warp)
+                const int ns = p.ns;
+                for (int c = 0; c < NCH; c++) {
+                    for (int j = 0; j < BN; j += 32) {
+                        float v[32];
+                        tmem_ld32(tacc + c * BN + j, v);
+                        const int n0 = (n_group * NCH + c) * BN + j;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias && n0 + e < p.Nout) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + e));
+                            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (EPI == E_ADD_MAXPOOL && row_ok && n0 + e < p.Nout)
+                                r4 = __ldg(reinterpret_cast<const float4 *>(p.R + row * p.ldr + n0 + e));
+                            v[e] = (v[e] + b4.x) + r4.x;
+                            v[e + 1] = (v[e + 1] + b4.y) + r4.y;
+                            v[e + 2] = (v[e + 2] + b4.z) + r4.z;
+                            v[e + 3] = (v[e + 3] + b4.w) + r4.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            float x = v[e];
+                            if (EPI == E_RELU_MAXPOOL) x = fmaxf(x, 0.f);
+                            if (!row_ok) x = -3.4e38f;
+                            for (int off = 1; off < ns; off <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, off));
+                            v[e] = x;
+                        }
+                        if (row_ok && (lane & (ns - 1)) == 0) {
+                            float *o = p.out + (row / ns) * p.ldo + n0;
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4)
+                                if (n0 + e < p.Nout)
+                                    *reinterpret_cast<float4 *>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                        }
+                    }
+                }
+            } else if (EPI == E_ADD_LN) {
+                // out = LayerNorm(acc + bias + R) over the full row of E = NCH * BN columns (n_groups == 1).
+                // Pass 1 parks v = acc + bias + R back in TMEM and sums it; pass 2: centred variance; pass 3: normalise.
+                constexpr int E = NCH * BN;
+                float sum = 0.f;
+                for (int j = 0; j < E; j += 32) {
+                    float v[32];
+                    tmem_ld32(tacc + j, v);
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + j + e))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) r4 = __ldg(reinterpret_cast<const float4 *>(p.R + row * p.ldr + j + e));
+                        v[e] = (v[e] + b4.x) + r4.x;
+                        v[e + 1] = (v[e + 1] + b4.y) + r4.y;
+                        v[e + 2] = (v[e + 2] + b4.z) + r4.z;
+                        v[e + 3] = (v[e + 3] + b4.w) + r4.w;
+                        sum += (v[e] + v[e + 1]) + (v[e + 2] + v[e + 3]);
+                    }
+                    tmem_st32(tacc + j, v);
+                }
+                const float mean = sum * (1.0f / E);
+                float sq = 0.f;
+                for (int j = 0; j < E; j += 32) {
+                    float v[32];
+                    tmem_ld32(tacc + j, v);
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {
+                        const float d = v[e] - mean;
+                        sq = fmaf(d, d, sq);
+                    }
+                }
+                const float rstd = rsqrtf(sq * (1.0f / E) + p.eps);
+                for (int j = 0; j < E; j += 32) {
+                    float v[32];
+                    tmem_ld32(tacc + j, v);
+                    if (row_ok) {
+                        float *o = p.out + row * p.ldo + j;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + j + e));
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + j + e));
+                            *reinterpret_cast<float4 *>(o + e) =
+                                make_float4((v[e] - mean) * rstd * g4.x + b4.x, (v[e + 1] - mean) * rstd * g4.y + b4.y,
+                                            (v[e + 2] - mean) * rstd * g4.z + b4.z, (v[e + 3] - mean) * rstd * g4.w + b4.w);
+                        }
+                    }
+                }
+            }
+
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(as));
+            if (ACC_STAGES == 2) {
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            } else {
+                aphase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
+int launch(const GemmParams &p, cudaStream_t s) {
+    using C = Cfg<NPASS, BN>;
+    auto kern = tc_gemm_kernel<NPASS, BN, NCH, ALOAD, EPI>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const long long grid = p.n_items < pdab::kNumSMs ? p.n_items : pdab::kNumSMs;
+    kern<<<(unsigned)grid, kThreads, C::SMEM_BYTES, s>>>(p);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int NPASS, int ALOAD>
+int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
+    const int chunks = (p.Nout + bn - 1) / bn;
+    auto items = [&](int nch) {
+        p.n_groups = chunks / nch;
+        p.n_items = ((p.T + BM - 1) / BM) * p.n_groups;
+    };
+    if (epi == E_ADD_LN) {
+        if (ALOAD != A_ROWS || bn != 256 || p.Nout % 256 || chunks > 2) return PDAB_EUNSUPPORTED;
+        if (chunks == 1) {
+            items(1);
+            return launch<NPASS, 256, 1, A_ROWS, E_ADD_LN>(p, s);
+        }
+        items(2);
+        return launch<NPASS, 256, 2, A_ROWS, E_ADD_LN>(p, s);
+    }
+    items(1);
+    if (bn == 256) {
+        switch (epi) {
+            case E_STORE: return launch<NPASS, 256, 1, ALOAD, E_STORE>(p, s);
+            case E_RELU: return launch<NPASS, 256, 1, ALOAD, E_RELU>(p, s);
+            case E_ADD_MAXPOOL: return launch<NPASS, 256, 1, ALOAD, E_ADD_MAXPOOL>(p, s);
+            case E_RELU_MAXPOOL: return launch<NPASS, 256, 1, ALOAD, E_RELU_MAXPOOL>(p, s);
+        }
+    } else if (bn == 128) {
+        switch (epi) {
+            case E_STORE: return launch<NPASS, 128, 1, ALOAD, E_STORE>(p, s);
+            case E_RELU: return launch<NPASS, 128, 1, ALOAD, E_RELU>(p, s);
+        }
+    }
+    return PDAB_EUNSUPPORTED;
+}
+
+}  // namespace
+
+// See include/pdab.h for the contract.
+extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilogue, const float *a, int lda,
+                              const float *w_packed, const float *bias, const float *residual, int ldr,
+                              const float *gamma, const float *beta, float eps, int nsample, float *out, int ldo,
+                              pdab_stream_t stream) {
+    if (rows < 0 || k < 1 || nout < 1 || !a || !w_packed || !out) return PDAB_EINVAL;
+    if (rows == 0) return 0;
+    if ((k & 3) || (lda & 3) || (ldo & 3) || (nout & 3) || lda < k) return PDAB_EINVAL;
+    if (npass != 1 && npass != 3) return PDAB_EINVAL;
+    if (bn != 128 && bn != 256) return PDAB_EINVAL;
+    if ((epilogue == E_ADD_LN || epilogue == E_ADD_MAXPOOL) && (!residual || (ldr & 3))) return PDAB_EINVAL;
+    if (epilogue == E_ADD_LN && (!gamma || !beta)) return PDAB_EINVAL;
+    if ((epilogue == E_ADD_MAXPOOL || epilogue == E_RELU_MAXPOOL) && ((nsample != 16 && nsample != 32) || rows % nsample))
+        return PDAB_EUNSUPPORTED;
+    GemmParams p{};
+    p.A = a;
+    p.lda = lda;
+    p.T = rows;
+    p.K = k;
+    p.KA = (k + BK - 1) / BK;
+    p.Wp = w_packed;
+    p.bias = bias;
+    p.Nout = nout;
+    p.out = out;
+    p.ldo = ldo;
+    p.R = residual;
+    p.ldr = ldr;
+    p.gamma = gamma;
+    p.beta = beta;
+    p.eps = eps;
+    p.ns = nsample;
+    cudaStream_t s = pdab::to_stream(stream);
+    return npass == 3 ? dispatch<3, A_ROWS>(p, epilogue, bn, s) : dispatch<1, A_ROWS>(p, epilogue, bn, s);
+}
+
+extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
+                                        const float *features_t, const float *xyz, const float *new_xyz,
+                                        const float *w_packed, const float *bias, float *out, int ldo,
+                                        pdab_stream_t stream) {
+    if (b < 0 || c < 0 || n < 1 || m < 1 || nsample < 1 || nout < 1 || !idx || !xyz || !new_xyz || !w_packed || !out)
+        return PDAB_EINVAL;
+    if (b == 0) return 0;
+    if ((c & 3) || (c > 0 && !features_t) || (ldo & 3) || (nout & 3)) return PDAB_EINVAL;
+    if (npass != 1 && npass != 3) return PDAB_EINVAL;
+    GemmParams p{};
+    p.T = (long long)b * m * nsample;
+    p.K = c + 3;
+    p.KA = (p.K + BK - 1) / BK;
+    p.idx = idx;
+    p.feat_t = features_t;
+    p.xyz = xyz;
+    p.new_xyz = new_xyz;
+    p.C = c;
+    p.Nsrc = n;
+    p.M = m;
+    p.ns = nsample;
+    p.Wp = w_packed;
+    p.bias = bias;
+    p.Nout = nout;
+    p.out = out;
+    p.ldo = ldo;
+    cudaStream_t s = pdab::to_stream(stream);
+    return npass == 3 ? dispatch<3, A_GATHER>(p, E_RELU, 256, s) : dispatch<1, A_GATHER>(p, E_RELU, 256, s);
+}

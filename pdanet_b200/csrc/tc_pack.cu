@@ -1,0 +1,67 @@
+// Weight packing for the tcgen05 kernels (tc_gemm.cu): W (nout, k) row-major -> the exact shared-memory image of
+// every (column chunk, k-atom) tile, so that a pipeline stage's weights are one contiguous cp.async.bulk.
+//
+// Packed layout, in floats:  [chunk = n / bn][atom = k / 32][part: hi, (lo)][row r = n % bn][16-byte slot][4]
+// where the 16-byte slot of logical k-chunk c (c = (k % 32) / 4) in row r is  c ^ (r & 7)  — the canonical K-major
+// SWIZZLE_128B pattern the UMMA shared-memory descriptor expects (rows of 128 B, 8-row groups 1024 B apart).
+// npass = 3: hi = top 19 bits of w (exact in TF32), lo = w - hi (exact in fp32).  npass = 1: cvt.rna.tf32 of w.
+// Runs once per module (weights are static in eval mode); not on the hot path.
+#include "common.cuh"
+
+namespace {
+
+__global__ void pack_kernel(int nout, int k, int npass, int bn, int xyz_last, const float *__restrict__ w,
+                            float *__restrict__ packed, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    // decode the destination index
+    const int parts = npass == 3 ? 2 : 1;
+    const int e = (int)(i & 3);
+    const int slot = (int)((i >> 2) & 7);
+    long long rest = i >> 5;
+    const int r = (int)(rest % bn);
+    rest /= bn;
+    const int part = (int)(rest % parts);
+    rest /= parts;
+    const int atoms = (k + 31) / 32;
+    const int atom = (int)(rest % atoms);
+    const int chunk = (int)(rest / atoms);
+    const int c = slot ^ (r & 7);
+    const int n = chunk * bn + r;
+    const int kk = atom * 32 + c * 4 + e;  // column of the (possibly permuted) A operand
+    float v = 0.f;
+    if (n < nout && kk < k) {
+        // A operand order [features (k - xyz_last), xyz (xyz_last)]  <-  reference order [xyz, features]
+        const int src = xyz_last > 0 ? (kk < k - xyz_last ? kk + xyz_last : kk - (k - xyz_last)) : kk;
+        v = w[(size_t)n * k + src];
+    }
+    float o;
+    if (npass == 3) {
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        o = part == 0 ? hi : v - hi;
+    } else {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+        o = __uint_as_float(t);
+    }
+    packed[i] = o;
+}
+
+}  // namespace
+
+extern "C" size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn) {
+    if (nout < 1 || k < 1 || bn < 1) return 0;
+    const size_t chunks = (size_t)(nout + bn - 1) / bn, atoms = (size_t)(k + 31) / 32;
+    return chunks * atoms * (npass == 3 ? 2 : 1) * (size_t)bn * 32;
+}
+
+extern "C" int pdab_tc_pack_weights(int nout, int k, int npass, int bn, int xyz_last, const float *w, float *packed,
+                                    pdab_stream_t stream) {
+    if (nout < 1 || k < 1 || !w || !packed || xyz_last < 0 || xyz_last > k) return PDAB_EINVAL;
+    if ((npass != 1 && npass != 3) || (bn != 128 && bn != 256)) return PDAB_EINVAL;
+    const long long total = (long long)pdab_tc_packed_floats(nout, k, npass, bn);
+    const long long blocks = (total + 255) / 256;
+    pack_kernel<<<(unsigned)blocks, 256, 0, pdab::to_stream(stream)>>>(nout, k, npass, bn, xyz_last, w, packed, total);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,126 @@
+"""tcgen05 contraction kernels (csrc/tc_gemm.cu) against float64 references of the same op.
+
+Tolerances (relative to the largest |reference| entry of the output):
+  npass = 3 (error-compensated 3xTF32): 5e-6  — fp32-level, what the reference's nn.Linear computes;
+  npass = 1 (TF32 operands)           : 2e-3  — TF32 level, what the reference's cuDNN 1x1 convolutions compute.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {3: 5e-6, 1: 2e-3}
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _rel(out, ref):
+    ref = ref.double()
+    return float((out.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def _mk(rows, k, nout, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, k, generator=g)
+    w = torch.randn(nout, k, generator=g) / k ** 0.5
+    b = torch.randn(nout, generator=g)
+    return x, w, b
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("rows,k,nout", [(128, 32, 128), (1000, 256, 768), (4096, 72, 256), (333, 512, 1536),
+                                         (2048, 128, 64), (5000, 264, 512)])
+def test_linear_store_and_relu(npass, rows, k, nout):
+    from pdanet_b200.tc_linear import PackedLinear, EPI_STORE, EPI_RELU
+    dev = _dev()
+    x, w, b = _mk(rows, k, nout, seed=rows + k)
+    lin = PackedLinear(w.to(dev), b.to(dev), npass=npass)
+    ref = x.double() @ w.double().t() + b.double()
+    out = lin(x.to(dev), EPI_STORE).cpu()
+    assert _rel(out, ref) < TOL[npass]
+    out = lin(x.to(dev), EPI_RELU).cpu()
+    assert _rel(out, ref.clamp_min(0)) < TOL[npass]
+    # no bias, strided input rows
+    lin2 = PackedLinear(w.to(dev), None, npass=npass)
+    xp = torch.zeros(rows, k + 8)
+    xp[:, :k] = x
+    out = lin2(xp.to(dev)[:, :k], EPI_STORE).cpu()
+    assert _rel(out, x.double() @ w.double().t()) < TOL[npass]
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("e", [256, 512])
+def test_linear_add_layernorm(npass, e):
+    from pdanet_b200.tc_linear import PackedLinear, EPI_ADD_LN
+    dev = _dev()
+    rows = 1500
+    x, w, b = _mk(rows, e, e, seed=e)
+    res = torch.randn(rows, e, generator=torch.Generator().manual_seed(5))
+    norm = torch.nn.LayerNorm(e)
+    with torch.no_grad():
+        norm.weight.copy_(torch.rand(e) + 0.5)
+        norm.bias.copy_(torch.randn(e) * 0.1)
+    lin = PackedLinear(w.to(dev), b.to(dev), npass=npass)
+    ref = torch.nn.functional.layer_norm(x.double() @ w.double().t() + b.double() + res.double(), (e,),
+                                         norm.weight.double(), norm.bias.double(), norm.eps)
+    out = lin(x.to(dev), EPI_ADD_LN, residual=res.to(dev), norm=norm.to(dev)).cpu()
+    assert _rel(out, ref) < TOL[npass] * 2
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("ns", [16, 32])
+def test_linear_maxpool_epilogues(npass, ns):
+    from pdanet_b200.tc_linear import PackedLinear, EPI_ADD_MAXPOOL, EPI_RELU_MAXPOOL
+    dev = _dev()
+    groups, k, nout = 100, 128, 512
+    rows = groups * ns
+    x, w, b = _mk(rows, k, nout, seed=ns)
+    res = torch.randn(rows, nout, generator=torch.Generator().manual_seed(6))
+    lin = PackedLinear(w.to(dev), b.to(dev), npass=npass)
+    y = x.double() @ w.double().t() + b.double()
+    ref = (y + res.double()).view(groups, ns, nout).max(dim=1)[0]
+    out = lin(x.to(dev), EPI_ADD_MAXPOOL, residual=res.to(dev), nsample=ns).cpu()
+    assert out.shape == (groups, nout)
+    assert _rel(out, ref) < TOL[npass]
+    ref = y.clamp_min(0).view(groups, ns, nout).max(dim=1)[0]
+    out = lin(x.to(dev), EPI_RELU_MAXPOOL, nsample=ns).cpu()
+    assert _rel(out, ref) < TOL[npass]
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+def test_sa_gather_linear(npass):
+    """Gather prologue == grouping_operation x2 + centre subtraction + cat + first 1x1 conv (reference channel order)."""
+    from pdanet_b200.tc_linear import PackedLinear
+    dev = _dev()
+    B, N, M, ns, C, nout = 3, 512, 200, 16, 64, 256
+    g = torch.Generator().manual_seed(11)
+    xyz = torch.rand(B, N, 3, generator=g) * 10
+    new_xyz = torch.rand(B, M, 3, generator=g) * 10
+    feat = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, M, ns), generator=g, dtype=torch.int32)
+    w = torch.randn(nout, 3 + C, generator=g) / (3 + C) ** 0.5   # reference input order: [xyz(3), features(C)]
+    b = torch.randn(nout, generator=g)
+    lin = PackedLinear(w.to(dev), b.to(dev), npass=npass, bn=256, xyz_last=3)
+    out = lin.sa_gather(idx.to(dev), feat.transpose(1, 2).contiguous().to(dev), xyz.to(dev), new_xyz.to(dev)).cpu()
+    li = idx.long()
+    gx = torch.gather(xyz.unsqueeze(1).expand(B, M, N, 3), 2, li.unsqueeze(-1).expand(B, M, ns, 3)) - new_xyz.unsqueeze(2)
+    gf = torch.gather(feat.transpose(1, 2).unsqueeze(1).expand(B, M, N, C), 2, li.unsqueeze(-1).expand(B, M, ns, C))
+    rows = torch.cat([gx, gf], dim=-1).reshape(B * M * ns, 3 + C).double()
+    ref = (rows @ w.double().t() + b.double()).clamp_min(0)
+    assert _rel(out, ref) < TOL[npass]
+
+
+def test_large_persistent_many_items():
+    """More work items than SMs: the persistent loop, both accumulator stages and the smem ring wrap many times."""
+    from pdanet_b200.tc_linear import PackedLinear, EPI_STORE
+    dev = _dev()
+    rows, k, nout = 70000, 256, 768
+    x, w, b = _mk(rows, k, nout, seed=3)
+    lin = PackedLinear(w.to(dev), b.to(dev), npass=3)
+    out = lin(x.to(dev), EPI_STORE)
+    ref = (x.to(dev).double() @ w.to(dev).double().t() + b.to(dev).double())
+    assert _rel(out.cpu(), ref.cpu()) < TOL[3]
