@@ -15,11 +15,12 @@
 //               in TF32 (top 19 bits), acc += x_hi w_lo + x_lo w_hi + x_hi w_hi.  The dropped x_lo w_lo term is
 //               O(2^-22) relative: fp32-level results (what nn.Linear computes in the reference) at 3 MMAs / k-step.
 //
-// Mapping to the SM.  One CTA per SM, persistent over (row tile, column group) work items; 10 warps:
+// Mapping to the SM.  One CTA per SM, persistent over (row tile, column group) work items; 14 warps:
 //   warp 0      W loader   : one lane issues cp.async.bulk (TMA engine, UBLKCP) of pre-packed weight tiles -> smem
 //   warp 1      MMA issuer : one lane issues tcgen05.mma (M=128, N=BN, K=8 per instruction), tcgen05.commit -> mbarriers
-//   warps 2-5   A producers: global -> registers -> (hi, lo) split -> 128B-swizzled K-major smem tiles
-//   warps 6-9   epilogue   : tcgen05.ld (TMEM -> registers) -> fused epilogue -> global
+//   warps 2-9   A producers: global -> registers -> (hi, lo) split -> 128B-swizzled K-major smem tiles
+//               (4 groups of 2 warps, group g owns every 4th k-atom: 4 k-atoms = 64 KB of loads in flight per SM)
+//   warps 10-13 epilogue   : tcgen05.ld (TMEM -> registers) -> fused epilogue -> global
 // Tiles: 128 rows (= TMEM lanes) x BN columns (fp32 accumulator columns) x 32-float k-atoms (one 128-byte swizzle
 // row).  Smem ring of S stages {A_hi, A_lo, W_hi, W_lo}; TMEM holds two accumulator stages (or one 512-column full
 // row for the LayerNorm epilogue) so the epilogue of item i overlaps the main loop of item i+1.
@@ -35,8 +36,10 @@ using u64 = uint64_t;
 constexpr int BM = 128;            // rows per tile (TMEM lanes)
 constexpr int BK = 32;             // floats per k-atom (128 B swizzle row)
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
-constexpr int kThreads = 320;
+constexpr int kProducerWarps = 8;
+constexpr int kThreads = 32 * (2 + kProducerWarps + 4);
 constexpr int kTmemCols = 512;
+constexpr int kStgPitch = 36;       // floats per row of an epilogue staging tile (32 + 4: 16-byte aligned, conflict-free)
 
 enum ALoad { A_ROWS = 0, A_GATHER = 1 };
 enum Epi { E_STORE = 0, E_RELU = 1, E_ADD_LN = 2, E_ADD_MAXPOOL = 3, E_RELU_MAXPOOL = 4 };
@@ -197,8 +200,13 @@ struct Cfg {
     static constexpr int W_TILE_BYTES = BN * BK * 4;                       // one of {hi, lo}
     static constexpr int STAGE_BYTES = (NPASS == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
     static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGES = STAGES_RAW >= 4 ? 4 : 2;
+    // A-producer groups: group g owns k-atom steps g, g+G, ...  G must divide STAGES so that every smem stage belongs
+    // to ONE group, which then sees every phase of that stage's `empty` barrier (a parity wait can only tell two
+    // consecutive phases apart).
+    static constexpr int GROUPS = STAGES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      4 * 32 * kStgPitch * 4 /*epilogue staging tiles*/;
 };
 
 struct Pipe {
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(full_w(s), 1);
-            mbar_init(full_a(s), 4);
+            mbar_init(full_a(s), kProducerWarps / C::GROUPS);
             mbar_init(empty(s), 1);
         }
         for (int a = 0; a < 2; a++) {
@@ -325,119 +333,165 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                 }
             }
         }
-    } else if (warp < 6) {
-        // ===================================================================== A producers (128 threads)
-        const int pt = threadIdx.x - 64;      // 0..127
-        const int chunk = pt & 7;             // 16-byte chunk inside the 128-byte row
-        const int r0 = pt >> 3;               // rows r0 + 16 i, i = 0..7
-        Pipe pipe;
-        float4 cur[8], nxt[8];
-        int src_row[8];                       // A_GATHER: flat source point row (b*Nsrc + i) per owned row, -1 = padding
+    } else if (warp < 2 + kProducerWarps) {
+        // ===================================================================== A producers (G groups of 8/G warps)
+        // Group g owns k-atom steps g, g+G, g+2G, ... of this CTA's flattened (item, chunk pass, k-atom) sequence and
+        // has exactly ONE batch of loads in flight per thread; the G groups together keep G k-atoms (16 KB each) in
+        // flight per SM, loaded before their smem stage is free.  (A register ring inside one warp
+        // does not work: ptxas folds the ring's loads onto shared scoreboard slots, so waiting for the oldest batch
+        // waits for the newest.)  Thread -> (16-byte chunk of the 128-byte row, R rows RSTEP apart): a warp-wide access
+        // covers 4 rows x 128 B, coalesced in global memory and conflict-free in the swizzled tile.
+        constexpr int G = C::GROUPS;                      // 2 or 4
+        constexpr int WPG = kProducerWarps / G;           // warps per group
+        constexpr int RSTEP = 4 * WPG;                    // rows covered by one group-wide access
+        constexpr int R = BM / RSTEP;                     // rows (float4 loads in flight) per thread
+        const int pw = warp - 2;
+        const int g = pw / WPG, h = pw % WPG;
+        const int chunk = lane & 7;                       // 16-byte chunk inside the 128-byte row
+        const int r0 = h * 4 + (lane >> 3);               // rows r0 + RSTEP i, i = 0..R-1
+        float4 v[R];
+        int src_row[R];                       // A_GATHER: flat source point row (b*Nsrc + i) per owned row, -1 = padding
+        long long meta_item = -1;
 
-        auto load_rows_meta = [&](long long m0) {
-            if (ALOAD == A_GATHER) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const long long t = m0 + r0 + 16 * i;
-                    src_row[i] = -1;
-                    if (t < p.T) {
-                        const long long b = t / ((long long)p.M * p.ns);
-                        src_row[i] = (int)(b * p.Nsrc + __ldg(p.idx + t));
-                    }
-                }
-            }
-        };
-        auto load_atom = [&](long long m0, int ka, float4 (&v)[8]) {
+        const long long my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int steps_per_item = NCH * KA;
+        const long long total = my_items * steps_per_item;
+
+        for (long long step = g; step < total; step += G) {
+            const long long li = step / steps_per_item;
+            const int ka = (int)(step - li * steps_per_item) % KA;
+            const long long item = blockIdx.x + li * gridDim.x;
+            const long long m0 = (item / p.n_groups) * BM;
             const int k = ka * BK + chunk * 4;
             if (ALOAD == A_ROWS) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const long long t = m0 + r0 + 16 * i;
+                for (int i = 0; i < R; i++) {
+                    const long long t = m0 + r0 + RSTEP * i;
                     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (t < p.T && k < p.K) v[i] = __ldg(reinterpret_cast<const float4 *>(p.A + t * p.lda + k));
                 }
             } else {
+                if (item != meta_item) {
+                    meta_item = item;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < R; i++) {
+                        const long long t = m0 + r0 + RSTEP * i;
+                        src_row[i] = -1;
+                        if (t < p.T) {
+                            const long long b = t / ((long long)p.M * p.ns);
+                            src_row[i] = (int)(b * p.Nsrc + __ldg(p.idx + t));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < R; i++) {
                     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (src_row[i] >= 0) {
                         if (k < p.C) {
                             v[i] = __ldg(reinterpret_cast<const float4 *>(p.feat_t + (size_t)src_row[i] * p.C + k));
                         } else if (k == p.C) {  // the three centred coordinates follow the C features
-                            const long long t = m0 + r0 + 16 * i;
-                            const long long g = t / p.ns;  // flat (b, centre)
+                            const long long grp = (m0 + r0 + RSTEP * i) / p.ns;  // flat (b, centre)
                             const float *q = p.xyz + (size_t)src_row[i] * 3;
-                            const float *c = p.new_xyz + g * 3;
+                            const float *c = p.new_xyz + grp * 3;
                             v[i] = make_float4(__ldg(q) - __ldg(c), __ldg(q + 1) - __ldg(c + 1),
                                                __ldg(q + 2) - __ldg(c + 2), 0.f);
                         }
                     }
                 }
             }
-        };
-
-        // flattened (item, chunk pass, k-atom) sequence with a one-step register prefetch
-        long long item = blockIdx.x;
-        int c = 0, ka = 0;
-        bool have = item < n_items;
-        if (have) {
-            load_rows_meta((item / p.n_groups) * BM);
-            load_atom((item / p.n_groups) * BM, 0, cur);
-        }
-        while (have) {
-            // advance to the next step and issue its loads before storing the current one
-            long long nitem = item;
-            int nc = c, nka = ka + 1;
-            if (nka == KA) {
-                nka = 0;
-                if (++nc == NCH) {
-                    nc = 0;
-                    nitem += gridDim.x;
-                }
-            }
-            const bool nhave = nitem < n_items;
-            if (nhave) {
-                if (nitem != item) load_rows_meta((nitem / p.n_groups) * BM);
-                load_atom((nitem / p.n_groups) * BM, nka, nxt);
-            }
-            mbar_wait(empty(pipe.stage), pipe.phase ^ 1);
-            uint8_t *ah = smem + (size_t)pipe.stage * C::STAGE_BYTES;
+            const int stage = (int)(step % S);
+            const u32 phase = (u32)((step / S) & 1);
+            mbar_wait(empty(stage), phase ^ 1);
+            uint8_t *ah = smem + (size_t)stage * C::STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int r = r0 + 16 * i;
+            for (int i = 0; i < R; i++) {
+                const int r = r0 + RSTEP * i;
                 const u32 off = (u32)r * 128u + (u32)((chunk ^ (r & 7)) << 4);
-                const float4 v = cur[i];
+                const float4 x = v[i];
                 if (NPASS == 3) {
-                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    *reinterpret_cast<float4 *>(ah + off) = h;
+                    const float4 hh = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    *reinterpret_cast<float4 *>(ah + off) = hh;
                     *reinterpret_cast<float4 *>(ah + A_TILE_BYTES + off) =
-                        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        make_float4(x.x - hh.x, x.y - hh.y, x.z - hh.z, x.w - hh.w);
                 } else {
                     *reinterpret_cast<float4 *>(ah + off) =
-                        make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                        make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
                 }
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_a(pipe.stage));
-            pipe.advance<S>();
-#pragma unroll
-            for (int i = 0; i < 8; i++) cur[i] = nxt[i];
-            item = nitem;
-            c = nc;
-            ka = nka;
-            have = nhave;
+            if (lane == 0) mbar_arrive(full_a(stage));
         }
     } else {
-        // ===================================================================== epilogue (128 threads, row per thread)
+        // ===================================================================== epilogue (128 threads)
+        // tcgen05.ld hands every thread one ROW (TMEM lane) x 32 consecutive columns.  Global traffic goes through a
+        // per-warp 32x32 staging tile in shared memory so that every load / store instruction covers 4 rows x 128
+        // contiguous bytes (row-per-thread accesses touch 32 different lines per instruction and were 4x slower).
         const int q = warp & 3;                  // TMEM lane quadrant this warp may read
         const int row_in_tile = q * 32 + lane;
+        float *stg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + (warp - (2 + kProducerWarps)) * (32 * kStgPitch);
+        const int srow = lane >> 3, schunk = lane & 7;   // coalesced phase: lane -> (row it*4 + srow, 16-byte chunk)
         int as = 0;
         u32 aphase = 0;
+
+        // v (thread = row) -> global rows [grow0, grow0+32) x columns [n0, n0+32), coalesced
+        auto store_tile = [&](const float (&v)[32], float *base, int ld, long long grow0, long long nrows, int n0) {
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<float4 *>(stg + lane * kStgPitch + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            __syncwarp();
+            const int col = n0 + schunk * 4;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int r = it * 4 + srow;
+                const float4 x = *reinterpret_cast<const float4 *>(stg + r * kStgPitch + schunk * 4);
+                if (grow0 + r < nrows && col < p.Nout)
+                    *reinterpret_cast<float4 *>(base + (grow0 + r) * ld + col) = x;
+            }
+        };
+        // global rows [grow0, grow0+32) x columns [n0, n0+32) -> v (thread = row), coalesced; zeros outside
+        auto load_tile = [&](float (&v)[32], const float *base, int ld, long long grow0, long long nrows, int n0) {
+            __syncwarp();
+            const int col = n0 + schunk * 4;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int r = it * 4 + srow;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow0 + r < nrows && col < p.Nout) x = __ldg(reinterpret_cast<const float4 *>(base + (grow0 + r) * ld + col));
+                *reinterpret_cast<float4 *>(stg + r * kStgPitch + schunk * 4) = x;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                const float4 x = *reinterpret_cast<const float4 *>(stg + lane * kStgPitch + e);
+                v[e] = x.x;
+                v[e + 1] = x.y;
+                v[e + 2] = x.z;
+                v[e + 3] = x.w;
+            }
+        };
+        // 32 consecutive per-column parameters (bias / gamma / beta) starting at n0: lane-distributed load + shuffles
+        // would also do; they are L1-resident broadcasts, so plain __ldg of float4 is used.
+        auto add_bias = [&](float (&v)[32], int n0) {
+            if (!p.bias) return;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                if (n0 + e < p.Nout) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + e));
+                    v[e] += b4.x;
+                    v[e + 1] += b4.y;
+                    v[e + 2] += b4.z;
+                    v[e + 3] += b4.w;
+                }
+            }
+        };
+
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
             const long long m0 = (item / p.n_groups) * BM;
             const int n_group = (int)(item % p.n_groups);
             const long long row = m0 + row_in_tile;
+            const long long wrow0 = m0 + q * 32;     // first row of this warp's 32-row slab
             const bool row_ok = row < p.T;
             mbar_wait(acc_full(as), aphase);
             tc_fence_after();
@@ -446,27 +500,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             if (EPI == E_STORE || EPI == E_RELU) {
                 for (int c = 0; c < NCH; c++) {
                     for (int j = 0; j < BN; j += 32) {
+                        const int n0 = (n_group * NCH + c) * BN + j;
+                        if (n0 >= p.Nout) break;
                         float v[32];
                         tmem_ld32(tacc + c * BN + j, v);
-                        const int n0 = (n_group * NCH + c) * BN + j;
-                        if (row_ok) {
-                            float *o = p.out + row * p.ldo + n0;
+                        add_bias(v, n0);
+                        if (EPI == E_RELU) {
 #pragma unroll
-                            for (int e = 0; e < 32; e += 4) {
-                                if (n0 + e < p.Nout) {
-                                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    if (p.bias) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + e));
-                                    float4 y = make_float4(v[e] + b4.x, v[e + 1] + b4.y, v[e + 2] + b4.z, v[e + 3] + b4.w);
-                                    if (EPI == E_RELU) {
-                                        y.x = fmaxf(y.x, 0.f);
-                                        y.y = fmaxf(y.y, 0.f);
-                                        y.z = fmaxf(y.z, 0.f);
-                                        y.w = fmaxf(y.w, 0.f);
-                                    }
-                                    *reinterpret_cast<float4 *>(o + e) = y;
-                                }
-                            }
+                            for (int e = 0; e < 32; e++) v[e] = fmaxf(v[e], 0.f);
                         }
+                        store_tile(v, p.out, p.ldo, wrow0, p.T, n0);
                     }
                 }
             } else if (EPI == E_ADD_MAXPOOL || EPI == E_RELU_MAXPOOL) {
@@ -474,20 +517,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                 const int ns = p.ns;
                 for (int c = 0; c < NCH; c++) {
                     for (int j = 0; j < BN; j += 32) {
+                        const int n0 = (n_group * NCH + c) * BN + j;
+                        if (n0 >= p.Nout) break;
                         float v[32];
                         tmem_ld32(tacc + c * BN + j, v);
-                        const int n0 = (n_group * NCH + c) * BN + j;
+                        add_bias(v, n0);
+                        if (EPI == E_ADD_MAXPOOL) {
+                            float r[32];
+                            load_tile(r, p.R, p.ldr, wrow0, p.T, n0);
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias && n0 + e < p.Nout) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + e));
-                            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (EPI == E_ADD_MAXPOOL && row_ok && n0 + e < p.Nout)
-                                r4 = __ldg(reinterpret_cast<const float4 *>(p.R + row * p.ldr + n0 + e));
-                            v[e] = (v[e] + b4.x) + r4.x;
-                            v[e + 1] = (v[e + 1] + b4.y) + r4.y;
-                            v[e + 2] = (v[e + 2] + b4.z) + r4.z;
-                            v[e + 3] = (v[e + 3] + b4.w) + r4.w;
+                            for (int e = 0; e < 32; e++) v[e] += r[e];
                         }
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
@@ -512,18 +551,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                 constexpr int E = NCH * BN;
                 float sum = 0.f;
                 for (int j = 0; j < E; j += 32) {
-                    float v[32];
+                    float v[32], r[32];
                     tmem_ld32(tacc + j, v);
+                    add_bias(v, j);
+                    load_tile(r, p.R, p.ldr, wrow0, p.T, j);
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
-                        const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + j + e))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok) r4 = __ldg(reinterpret_cast<const float4 *>(p.R + row * p.ldr + j + e));
-                        v[e] = (v[e] + b4.x) + r4.x;
-                        v[e + 1] = (v[e + 1] + b4.y) + r4.y;
-                        v[e + 2] = (v[e + 2] + b4.z) + r4.z;
-                        v[e + 3] = (v[e + 3] + b4.w) + r4.w;
+                        v[e] += r[e];
+                        v[e + 1] += r[e + 1];
+                        v[e + 2] += r[e + 2];
+                        v[e + 3] += r[e + 3];
                         sum += (v[e] + v[e + 1]) + (v[e + 2] + v[e + 3]);
                     }
                     tmem_st32(tacc + j, v);
@@ -543,17 +580,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                 for (int j = 0; j < E; j += 32) {
                     float v[32];
                     tmem_ld32(tacc + j, v);
-                    if (row_ok) {
-                        float *o = p.out + row * p.ldo + j;
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + j + e));
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + j + e));
-                            *reinterpret_cast<float4 *>(o + e) =
-                                make_float4((v[e] - mean) * rstd * g4.x + b4.x, (v[e + 1] - mean) * rstd * g4.y + b4.y,
-                                            (v[e + 2] - mean) * rstd * g4.z + b4.z, (v[e + 3] - mean) * rstd * g4.w + b4.w);
-                        }
+                    for (int e = 0; e < 32; e += 4) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + j + e));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + j + e));
+                        v[e] = (v[e] - mean) * rstd * g4.x + b4.x;
+                        v[e + 1] = (v[e + 1] - mean) * rstd * g4.y + b4.y;
+                        v[e + 2] = (v[e + 2] - mean) * rstd * g4.z + b4.z;
+                        v[e + 3] = (v[e + 3] - mean) * rstd * g4.w + b4.w;
                     }
+                    store_tile(v, p.out, p.ldo, wrow0, p.T, j);
                 }
             }
 
