@@ -119,7 +119,8 @@ int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, int nsample,
  * replaces: torch.cat / mul / copy / nn.LayerNorm / residual add / ReLU / max-pool launches of the PDA block,
  *           PB/pointnet2_modules.py:893-931, PB/PointFormer.py:28-38. */
 /* row = LayerNorm(cat[pos (c), feat*scale (c), feat (c), glob[row / nsample] (c)]); feat = x[row, 8 : 8+c] with row
- * pitch xpitch (the pdab_pda_group_tokens layout); pos (tokens,c), scale (tokens), glob (tokens/nsample, c). */
+ * pitch xpitch (the pdab_pda_group_tokens layout); pos (tokens,c), scale (tokens), glob (tokens/nsample, c).
+ * lo == NULL: the un-split row is written to `hi` (the tcgen05 GEMMs of pdab_tc_linear split their operand themselves). */
 int pdab_pda_assemble_ln_split(long long tokens, int nsample, int c, int xpitch, const float *pos, const float *x,
                                const float *scale, const float *glob, const float *gamma, const float *beta,
                                float eps, float *hi, float *lo, pdab_stream_t stream);
@@ -131,6 +132,14 @@ int pdab_relu_split(long long n, const float *h, float *hi, float *lo, pdab_stre
 /* out[g, :] = max over the nsample rows of group g of ((a_hi + a_lo) + f);  out (groups, e) */
 int pdab_add_maxpool(long long groups, int nsample, int e, const float *a_hi, const float *a_lo, const float *f,
                      float *out, pdab_stream_t stream);
+
+/* Self-attention inside each neighbourhood, all heads: ctx = softmax(q k^T / sqrt(head_dim)) v per (group, head).
+ * replaces: the attention core of nn.MultiheadAttention in TransformerEncoderLayerPreNorm (q/k/v permutes, 2 bmm,
+ *           softmax, permute back), PB/PointFormer.py:30, PB/pointnet2_modules.py:929.
+ * qkv (groups*nsample, 3*heads*head_dim) = [q | k | v] rows as in_proj leaves them; the nsample rows of a group are
+ * consecutive; ctx (groups*nsample, heads*head_dim).  nsample in {16, 32}, head_dim in {64, 128}. */
+int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, const float *qkv, float *ctx,
+                         pdab_stream_t stream);
 
 /* Fused plain set-abstraction scale: ball query -> group (xyz centred) -> shared MLP
  * (1x1 conv with eval-mode BatchNorm folded in, ReLU) x nlayers -> max over nsample.

@@ -27,6 +27,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ void split_store(float4 v, float4 *hi, float4 *lo) {
+    if (lo == nullptr) {  // un-split output (the tcgen05 GEMMs split their A operand themselves); it is re-read soon
+        *hi = v;
+        return;
+    }
     float4 h;
     h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
     h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -63,7 +67,8 @@ __device__ __forceinline__ void layer_norm_split(float4 (&v)[V4], int lane, cons
         y.y = (v[i].y - mean) * rstd * g.y + b.y;
         y.z = (v[i].z - mean) * rstd * g.z + b.z;
         y.w = (v[i].w - mean) * rstd * g.w + b.w;
-        split_store(y, reinterpret_cast<float4 *>(hi_row + col), reinterpret_cast<float4 *>(lo_row + col));
+        split_store(y, reinterpret_cast<float4 *>(hi_row + col),
+                    lo_row ? reinterpret_cast<float4 *>(lo_row + col) : nullptr);
     }
 }
 
@@ -99,7 +104,7 @@ assemble_ln_split_kernel(long long T, int ns, int C, int xpitch, const float *__
             }
         }
     }
-    layer_norm_split<V4>(v, lane, gamma, beta, eps, hi + row * E, lo + row * E);
+    layer_norm_split<V4>(v, lane, gamma, beta, eps, hi + row * E, lo ? lo + row * E : nullptr);
 }
 
 template <int V4>
@@ -168,7 +173,7 @@ extern "C" int pdab_pda_assemble_ln_split(long long tokens, int nsample, int c, 
                                           const float *x, const float *scale, const float *glob,
                                           const float *gamma, const float *beta, float eps, float *hi, float *lo,
                                           pdab_stream_t stream) {
-    if (tokens < 0 || nsample < 1 || c < 1 || !pos || !x || !scale || !glob || !gamma || !beta || !hi || !lo)
+    if (tokens < 0 || nsample < 1 || c < 1 || !pos || !x || !scale || !glob || !gamma || !beta || !hi)
         return PDAB_EINVAL;
     if (tokens == 0) return 0;
     if ((c & 3) || xpitch < 8 + c || (xpitch & 3) || tokens % nsample) return PDAB_EINVAL;

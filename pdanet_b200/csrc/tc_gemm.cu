@@ -450,25 +450,55 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                     *reinterpret_cast<float4 *>(base + (grow0 + r) * ld + col) = x;
             }
         };
-        // global rows [grow0, grow0+32) x columns [n0, n0+32) -> v (thread = row), coalesced; zeros outside
-        auto load_tile = [&](float (&v)[32], const float *base, int ld, long long grow0, long long nrows, int n0) {
-            __syncwarp();
+        // Residual tiles: global rows [grow0, grow0+32) x columns [n0, n0+32), coalesced float4 loads into registers
+        // (issued one tile ahead of their use so the global latency hides behind the previous tile's work) ...
+        auto issue_tile = [&](float4 (&t)[8], const float *base, int ld, long long grow0, long long nrows, int n0) {
             const int col = n0 + schunk * 4;
 #pragma unroll
             for (int it = 0; it < 8; it++) {
                 const int r = it * 4 + srow;
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (grow0 + r < nrows && col < p.Nout) x = __ldg(reinterpret_cast<const float4 *>(base + (grow0 + r) * ld + col));
-                *reinterpret_cast<float4 *>(stg + r * kStgPitch + schunk * 4) = x;
+                t[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow0 + r < nrows && col < p.Nout)
+                    t[it] = __ldg(reinterpret_cast<const float4 *>(base + (grow0 + r) * ld + col));
             }
+        };
+        // ... then transposed through the staging tile to the thread = row layout and added to v
+        auto add_tile = [&](float (&v)[32], const float4 (&t)[8]) {
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; it++)
+                *reinterpret_cast<float4 *>(stg + (it * 4 + srow) * kStgPitch + schunk * 4) = t[it];
             __syncwarp();
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
                 const float4 x = *reinterpret_cast<const float4 *>(stg + lane * kStgPitch + e);
-                v[e] = x.x;
-                v[e + 1] = x.y;
-                v[e + 2] = x.z;
-                v[e + 3] = x.w;
+                v[e] += x.x;
+                v[e + 1] += x.y;
+                v[e + 2] += x.z;
+                v[e + 3] += x.w;
+            }
+        };
+        // max over the ns (16 or 32) consecutive rows of each neighbourhood: v (thread = row) goes through the staging
+        // tile, then lane = COLUMN reads its 32 rows (bank = 4 r + lane: conflict-free) and writes out[group, n0 + lane].
+        auto pool_store = [&](const float (&v)[32], long long grow0, int n0, int ns) {
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<float4 *>(stg + lane * kStgPitch + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            __syncwarp();
+            float m0 = -3.4e38f, m1 = -3.4e38f;
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                m0 = fmaxf(m0, stg[r * kStgPitch + lane]);
+                m1 = fmaxf(m1, stg[(r + 16) * kStgPitch + lane]);
+            }
+            if (n0 + lane < p.Nout) {
+                if (ns == 32) {
+                    if (grow0 < p.T) p.out[(grow0 / 32) * p.ldo + n0 + lane] = fmaxf(m0, m1);
+                } else {
+                    if (grow0 < p.T) p.out[(grow0 / 16) * p.ldo + n0 + lane] = m0;
+                    if (grow0 + 16 < p.T) p.out[(grow0 / 16 + 1) * p.ldo + n0 + lane] = m1;
+                }
             }
         };
         // 32 consecutive per-column parameters (bias / gamma / beta) starting at n0: lane-distributed load + shuffles
@@ -513,56 +543,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                     }
                 }
             } else if (EPI == E_ADD_MAXPOOL || EPI == E_RELU_MAXPOOL) {
-                // max over the ns consecutive rows of each neighbourhood (ns in {16, 32}: inside one warp)
+                // rows of a tile beyond T cannot occur inside a neighbourhood (T % ns == 0): whole groups are skipped
                 const int ns = p.ns;
-                for (int c = 0; c < NCH; c++) {
-                    for (int j = 0; j < BN; j += 32) {
-                        const int n0 = (n_group * NCH + c) * BN + j;
-                        if (n0 >= p.Nout) break;
-                        float v[32];
-                        tmem_ld32(tacc + c * BN + j, v);
-                        add_bias(v, n0);
-                        if (EPI == E_ADD_MAXPOOL) {
-                            float r[32];
-                            load_tile(r, p.R, p.ldr, wrow0, p.T, n0);
-#pragma unroll
-                            for (int e = 0; e < 32; e++) v[e] += r[e];
-                        }
-#pragma unroll
-                        for (int e = 0; e < 32; e++) {
-                            float x = v[e];
-                            if (EPI == E_RELU_MAXPOOL) x = fmaxf(x, 0.f);
-                            if (!row_ok) x = -3.4e38f;
-                            for (int off = 1; off < ns; off <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, off));
-                            v[e] = x;
-                        }
-                        if (row_ok && (lane & (ns - 1)) == 0) {
-                            float *o = p.out + (row / ns) * p.ldo + n0;
-#pragma unroll
-                            for (int e = 0; e < 32; e += 4)
-                                if (n0 + e < p.Nout)
-                                    *reinterpret_cast<float4 *>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                        }
+                const int nblk = NCH * (BN / 32);
+                auto n0_of = [&](int b) { return (n_group * NCH + b / (BN / 32)) * BN + (b % (BN / 32)) * 32; };
+                float4 rn[8];
+                if (EPI == E_ADD_MAXPOOL) issue_tile(rn, p.R, p.ldr, wrow0, p.T, n0_of(0));
+                for (int b = 0; b < nblk; b++) {
+                    const int n0 = n0_of(b);
+                    if (n0 >= p.Nout) break;
+                    float v[32];
+                    tmem_ld32(tacc + (b / (BN / 32)) * BN + (b % (BN / 32)) * 32, v);
+                    add_bias(v, n0);
+                    if (EPI == E_ADD_MAXPOOL) {
+                        add_tile(v, rn);  // rn is dead once staged: refill it with the next tile right away
+                        if (b + 1 < nblk) issue_tile(rn, p.R, p.ldr, wrow0, p.T, n0_of(b + 1));
                     }
+                    if (EPI == E_RELU_MAXPOOL) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) v[e] = fmaxf(v[e], 0.f);
+                    }
+                    pool_store(v, wrow0, n0, ns);
                 }
             } else if (EPI == E_ADD_LN) {
                 // out = LayerNorm(acc + bias + R) over the full row of E = NCH * BN columns (n_groups == 1).
                 // Pass 1 parks v = acc + bias + R back in TMEM and sums it; pass 2: centred variance; pass 3: normalise.
                 constexpr int E = NCH * BN;
                 float sum = 0.f;
+                float4 rn[8];
+                issue_tile(rn, p.R, p.ldr, wrow0, p.T, 0);
                 for (int j = 0; j < E; j += 32) {
-                    float v[32], r[32];
+                    float v[32];
                     tmem_ld32(tacc + j, v);
                     add_bias(v, j);
-                    load_tile(r, p.R, p.ldr, wrow0, p.T, j);
+                    add_tile(v, rn);  // rn is dead once staged: refill it with the next tile right away
+                    if (j + 32 < E) issue_tile(rn, p.R, p.ldr, wrow0, p.T, j + 32);
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        v[e] += r[e];
-                        v[e + 1] += r[e + 1];
-                        v[e + 2] += r[e + 2];
-                        v[e + 3] += r[e + 3];
-                        sum += (v[e] + v[e + 1]) + (v[e + 2] + v[e + 3]);
-                    }
+                    for (int e = 0; e < 32; e += 4) sum += (v[e] + v[e + 1]) + (v[e + 2] + v[e + 3]);
                     tmem_st32(tacc + j, v);
                 }
                 const float mean = sum * (1.0f / E);
@@ -656,6 +673,8 @@ int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
         switch (epi) {
             case E_STORE: return launch<NPASS, 128, 1, ALOAD, E_STORE>(p, s);
             case E_RELU: return launch<NPASS, 128, 1, ALOAD, E_RELU>(p, s);
+            case E_ADD_MAXPOOL: return launch<NPASS, 128, 1, ALOAD, E_ADD_MAXPOOL>(p, s);
+            case E_RELU_MAXPOOL: return launch<NPASS, 128, 1, ALOAD, E_RELU_MAXPOOL>(p, s);
         }
     }
     return PDAB_EUNSUPPORTED;

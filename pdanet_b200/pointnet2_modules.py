@@ -215,9 +215,12 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         self.pool_method = pool_method
         self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.mlps) > 0)
         self._folded = None  # BN-folded MLP parameters, built lazily in eval mode
+        self._wide = {}      # scale -> packed tensor-core layers (tc_linear.PackedLinear), eval mode
+        self.tc_passes = 3   # 3 = error-compensated 3xTF32 (fp32-level); 1 = plain TF32 (cuDNN's default class)
 
     def train(self, mode: bool = True):
         self._folded = None
+        self._wide = {}
         return super().train(mode)
 
     def _folded_params(self, i):
@@ -229,7 +232,31 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
             self._folded[i] = ([p[0] for p in pairs], [p[1] for p in pairs])
         return self._folded[i]
 
-    def _scale(self, i, xyz, new_xyz, features):
+    def _wide_supported(self, i, features):
+        """Shapes the tensor-core path covers: ball query -> gather-GEMM+ReLU -> GEMM+ReLU -> GEMM+ReLU+max-pool."""
+        seq = self.mlps[i]
+        widths = [seq[3 * k].out_channels for k in range(len(seq) // 3)]
+        return (features is not None and features.shape[1] % 4 == 0 and features.shape[1] >= 32 and len(widths) == 3
+                and all(w % 4 == 0 for w in widths) and self.nsamples[i] in (16, 32)
+                and hasattr(self.ops, "ball_query") and features.is_cuda)
+
+    def _scale_wide(self, i, xyz, new_xyz, features_t):
+        from .tc_linear import EPI_RELU, EPI_RELU_MAXPOOL, PackedLinear
+        if i not in self._wide:
+            w, b = self._folded_params(i)
+            self._wide[i] = [PackedLinear(w[0], b[0], npass=self.tc_passes, bn=256, xyz_last=3),
+                             PackedLinear(w[1], b[1], npass=self.tc_passes),
+                             PackedLinear(w[2], b[2], npass=self.tc_passes)]
+        l1, l2, l3 = self._wide[i]
+        ns = self.nsamples[i]
+        B, M, _ = new_xyz.shape
+        idx = self.ops.ball_query(self.radii[i], ns, xyz, new_xyz)          # (B, M, ns) int32
+        h = l1.sa_gather(idx, features_t, xyz, new_xyz)                     # (B*M*ns, c1): grouped tensor never exists
+        h = l2(h, EPI_RELU)
+        pooled = l3(h, EPI_RELU_MAXPOOL, nsample=ns)                        # (B*M, c3)
+        return pooled.view(B, M, -1).permute(0, 2, 1)
+
+    def _scale(self, i, xyz, new_xyz, features, features_t=None):
         fused_ok = (
             not self.training and not torch.is_grad_enabled() and self.pool_method == "max_pool"
             and not self.dilated_group and self.use_xyz and self.npoint_list is not None
@@ -242,6 +269,8 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
             if self.ops.sa_fused_supported(c0, widths, self.nsamples[i]):
                 w, b = self._folded_params(i)
                 return self.ops.sa_fused(self.radii[i], self.nsamples[i], xyz, new_xyz, features, w, b)
+            if features_t is not None:
+                return self._scale_wide(i, xyz, new_xyz, features_t)
         grouped = self.groupers[i](xyz, new_xyz, features)  # (B, C+3, npoint, nsample)
         y = self.mlps[i](grouped)
         if self.pool_method == "max_pool":
@@ -266,7 +295,15 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
             new_xyz = ctr_xyz
 
         if len(self.groupers) > 0:
-            outs = [self._scale(i, xyz, new_xyz, features) for i in range(len(self.groupers))]
+            features_t = None   # point-major copy of the features, shared by the scales on the tensor-core path
+            if (not self.training and not torch.is_grad_enabled() and self.pool_method == "max_pool"
+                    and not self.dilated_group and self.use_xyz and self.npoint_list is not None
+                    and hasattr(self.ops, "sa_fused")
+                    and any(self._wide_supported(i, features) for i in range(len(self.groupers)))):
+                features_t = features.transpose(1, 2).contiguous()
+            outs = [self._scale(i, xyz, new_xyz, features,
+                                features_t if features_t is not None and self._wide_supported(i, features) else None)
+                    for i in range(len(self.groupers))]
             new_features = torch.cat(outs, dim=1)
             if self.aggregation_layer is not None:
                 new_features = self.aggregation_layer(new_features)

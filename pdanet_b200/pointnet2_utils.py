@@ -237,6 +237,32 @@ def pda_assemble_ln_split(pos, X, scale, glob, nsample, norm):
     return hi, lo
 
 
+def pda_assemble_ln(pos, X, scale, glob, nsample, norm):
+    """LayerNorm(cat[pos, feat*scale, feat, glob]) per token, un-split (T, 4C); see include/pdab.h."""
+    T, C = pos.shape
+    assert pos.is_contiguous() and X.is_contiguous() and scale.is_contiguous() and glob.is_contiguous()
+    y = torch.empty(T, 4 * C, dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        _lib.call("pdab_pda_assemble_ln_split", T, nsample, C, X.shape[-1], pos.data_ptr(), X.data_ptr(),
+                  scale.data_ptr(), glob.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), float(norm.eps),
+                  y.data_ptr(), None, _stream_of(pos))
+    return y
+
+
+def group_attention(qkv, nsample, heads):
+    """softmax(q k^T / sqrt(hd)) v inside each neighbourhood of `nsample` consecutive tokens; qkv (T, 3E) -> (T, E)."""
+    if not qkv.is_cuda:
+        raise RuntimeError("group_attention needs CUDA tensors")
+    T, E3 = qkv.shape
+    E = E3 // 3
+    assert qkv.is_contiguous() and T % nsample == 0 and E % heads == 0
+    ctx = torch.empty(T, E, dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.call("pdab_group_attention", T // nsample, nsample, heads, E // heads, qkv.data_ptr(), ctx.data_ptr(),
+                  _stream_of(qkv))
+    return ctx
+
+
 def add_ln_split(a_hi, a_lo, o, norm):
     T, E = a_hi.shape
     assert a_hi.is_contiguous() and a_lo.is_contiguous() and o.is_contiguous()

@@ -124,3 +124,57 @@ def test_large_persistent_many_items():
     out = lin(x.to(dev), EPI_STORE)
     ref = (x.to(dev).double() @ w.to(dev).double().t() + b.to(dev).double())
     assert _rel(out.cpu(), ref.cpu()) < TOL[3]
+
+
+@pytest.mark.parametrize("ns,hd", [(16, 64), (32, 64), (16, 128), (32, 128)])
+def test_group_attention_vs_torch_mha(ns, hd):
+    """pdab_group_attention == the attention core of nn.MultiheadAttention on (ns, groups, E) sequences."""
+    from pdanet_b200 import pointnet2_utils as ops
+    dev = _dev()
+    heads, groups = 4, 37
+    E = heads * hd
+    g = torch.Generator().manual_seed(ns + hd)
+    qkv = torch.randn(groups * ns, 3 * E, generator=g) * 1.5
+    ctx = ops.group_attention(qkv.to(dev), ns, heads).cpu()
+    q, k, v = [t.double().view(groups, ns, heads, hd).permute(0, 2, 1, 3) for t in qkv.split(E, dim=1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(groups * ns, E)
+    assert _rel(ctx, ref) < 2e-6
+
+
+@pytest.mark.parametrize("tc_passes", [3, 1])
+def test_wide_sa_scale_matches_unfused_module(tc_passes):
+    """Plain SA layer with wide MLPs (the L5 shape): tensor-core path vs the reference statement order
+    (QueryAndGroup -> Conv2d/BN/ReLU x3 -> max_pool2d) of the same module with the same parameters."""
+    from pdanet_b200.pointnet2_modules import PointnetSAModuleMSG_WithSampling
+    dev = _dev()
+    torch.manual_seed(0)
+    mod = PointnetSAModuleMSG_WithSampling(
+        npoint_list=[64], sample_range_list=[-1], sample_type_list=["D-FPS"], radii=[4.8, 6.4], nsamples=[16, 32],
+        mlps=[[64, 64, 64, 128], [64, 64, 128, 256]], aggregation_mlp=[128], confidence_mlp=[], num_class=3).to(dev).eval()
+    with torch.no_grad():
+        for m in mod.modules():  # non-trivial BN statistics so that the folding is exercised
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    mod.tc_passes = tc_passes
+    g = torch.Generator().manual_seed(1)
+    B, N = 2, 512
+    xyz = (torch.rand(B, N, 3, generator=g) * torch.tensor([20.0, 20.0, 2.0])).to(dev)
+    feats = torch.randn(B, 64, N, generator=g).to(dev)
+    ctr = (torch.rand(B, 100, 3, generator=g) * torch.tensor([20.0, 20.0, 2.0])).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            _, fused, _, _ = mod(xyz, feats, None, ctr_xyz=ctr)
+            assert len(mod._wide) == 2, "tensor-core path was not taken"
+            mod.ops = type("NoFused", (), {k: getattr(mod.ops, k) for k in ("ball_query", "grouping_operation",
+                           "gather_operation", "furthest_point_sample", "QueryAndGroup")})
+            _, plain, _, _ = mod(xyz, feats, None, ctr_xyz=ctr)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    err = float((fused - plain).abs().max() / plain.abs().max())
+    assert err < (2e-5 if tc_passes == 3 else 3e-3), err
