@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight per GPU (ScenePipeline slots)")
+    ap.add_argument("--no-graphs", action="store_true", help="do not capture the forward in CUDA graphs")
     ap.add_argument("--matmul", default="ieee", choices=["ieee", "tf32"],
                     help="fp32 matmul mode of the unchanged PyTorch layers (PDA transformer); our kernels are fp32 either way")
     return ap.parse_args()
@@ -53,6 +55,16 @@ def peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def tensor_peak():
+    """TF32 dense peak in TFLOP/s: half the measured bf16 cuBLAS throughput (sustained figure: the kernel is timed inside
+    a long step); kind::tf32 MMAs run at half the bf16 rate on sm_100."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["bf16_tflops_sustained"]) / 2, "measured bf16_tflops_sustained / 2 (MEASURED_PEAKS.json; TF32 = half the bf16 rate)"
+    return 1590.0 / 2, "fallback 1.59 PFLOP/s bf16 / 2 (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -163,15 +175,41 @@ def algorithmic_bytes(key: str, batch: int):
     if name == "pdab_topk_ctr":
         b, n, c, k = a[:4]
         return b * (4 * n * c + 4 * k)
+    if name == "pdab_tc_linear":
+        rows, k, nout, npass, bn, epi = a[:6]
+        out_rows = rows if epi < 3 else rows // 16       # max-pool epilogues write one row per neighbourhood
+        resid = rows * nout * 4 if epi in (2, 3) else 0
+        return rows * k * 4 + out_rows * nout * 4 + resid + nout * k * 4 * (2 if npass == 3 else 1)
+    if name == "pdab_tc_sa_gather_linear":
+        b, c, n, m, ns, nout = a[:6]
+        return b * (4 * c * n + 12 * n + 12 * m + 4 * m * ns) + b * m * ns * nout * 4
+    if name == "pdab_group_attention":
+        groups, ns, heads, hd = a[:4]
+        return groups * ns * heads * hd * 4 * 4          # q, k, v read + ctx written
     if name == "pdab_nms_batched":
         s, stride = a[:2]
         return s * (28 * stride + 8 * stride * ((stride + 63) // 64) + 8 * stride)
     return None
 
 
+def algorithmic_flops(key: str):
+    """(algorithmic flops, tensor-pipe flops issued) of one launch of a tensor-core entry point, else None."""
+    name, _, rest = key.partition("(")
+    a = [int(x) for x in rest.strip(")").split(",") if x.strip()]
+    if name == "pdab_tc_linear":
+        rows, k, nout, npass = a[:4]
+        f = 2.0 * rows * k * nout
+        return f, f * npass
+    if name == "pdab_tc_sa_gather_linear":
+        b, c, n, m, ns, nout, npass = a[:7]
+        f = 2.0 * b * m * ns * (c + 3) * nout
+        return f, f * npass
+    return None
+
+
 def run_gpu_arm(args, cfg, n_points, batch):
     from pdanet_b200 import _lib
-    from pdanet_b200.runner import SceneRunner
+    from pdanet_b200.runner import ScenePipeline, SceneRunner
     from pdanet_b200.synthetic import make_batch
 
     rank = int(os.environ.get("RANK", 0))
@@ -187,10 +225,14 @@ def run_gpu_arm(args, cfg, n_points, batch):
 
     torch.backends.cuda.matmul.allow_tf32 = args.matmul == "tf32"
     runner = SceneRunner(cfg, device=dev, batch_size=batch, num_points=n_points, seed=0)
-    # weak scaling: every rank owns its own `batch` scenes (global scene ids rank*batch ...)
-    host = make_batch(batch, n_points, cfg.POINT_CLOUD_RANGE, first_scene=rank * batch)["points"].pin_memory()
-    dev_points = host.to(dev)
+    # weak scaling: every rank owns its own scenes (global scene ids rank*batch*R ...); the steps rotate over
+    # R distinct synthetic batches so consecutive steps never see the same input
+    R = 4
+    hosts = [make_batch(batch, n_points, cfg.POINT_CLOUD_RANGE, first_scene=(rank * R + r) * batch)["points"].pin_memory()
+             for r in range(R)]
+    devs = [h.to(dev) for h in hosts]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    pipe = ScenePipeline(runner, depth=args.depth, graphs=not args.no_graphs, warm_points=hosts[0])
 
     def barrier():
         torch.cuda.synchronize()
@@ -205,48 +247,61 @@ def run_gpu_arm(args, cfg, n_points, batch):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        runner.infer_device(dev_points)
-        runner.infer(host)
+    for w in range(args.warmup):
+        runner.infer_device(devs[w % R])
+    pipe.run_device([devs[w % R] for w in range(max(args.warmup, args.depth))])
+    pipe.run([hosts[w % R] for w in range(max(args.warmup, args.depth))])
     barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
+    def timed_pipeline(fn, batches):
+        """EXACTLY K steps through the pipelined runner, bracketed by barrier + synchronize; device time between a start
+        event every slot stream waits on and an end event that waits for every slot."""
+        flush.zero_()
+        barrier()
+        s = torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn(batches, start_event=s)
+        e = pipe.join_event()
+        e.synchronize()
+        barrier()
+        return s.elapsed_time(e)
+
     def timed_steps(fn):
-        """K steps, each bracketed by its own CUDA events on the current stream; L2 flushed outside the events."""
+        """K sequential steps, each bracketed by its own CUDA events on the current stream; L2 flushed outside them."""
         ms = []
         barrier()
-        for _ in range(args.steps):
+        for k in range(args.steps):
             flush.zero_()
             torch.cuda.synchronize()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            fn()
+            fn(k)
             e.record()
             e.synchronize()
             ms.append(s.elapsed_time(e))
         barrier()
         return ms
 
-    # ---- leg 1: device-resident inputs ------------------------------------------------------------
-    _lib.launch_counts.clear()
-    step_ms = timed_steps(lambda: runner.infer_device(dev_points))
-    launches = sum(_lib.launch_counts.values())
-    total_ms = max_over_ranks(sum(step_ms))
+    # ---- leg 1: device-resident inputs, K steps pipelined (whole-job throughput)
+    total_ms = max_over_ranks(timed_pipeline(pipe.run_device, [devs[k % R] for k in range(args.steps)]))
     value = world * batch * args.steps / (total_ms / 1e3)
+    launches = pipe.launches_per_step * args.steps
 
-    # ---- leg 1b: the same K steps again with CUDA events around every C-ABI call (per-kernel durations for the
-    # roofline; kept apart so that the extra event records do not perturb `value`)
+    # ---- leg 1b: K sequential, un-pipelined steps (latency of one batch), then the same again with CUDA events around
+    # every C-ABI call (per-kernel durations for the roofline; kept apart so the event records do not perturb anything)
+    seq_ms = timed_steps(lambda k: runner.infer_device(devs[k % R]))
     _lib.enable_timing(True)
-    inst_ms = timed_steps(lambda: runner.infer_device(dev_points))
+    inst_ms = timed_steps(lambda k: runner.infer_device(devs[k % R]))
     kernel_ms = _lib.timings_ms()
     _lib.enable_timing(False)
 
-    # ---- leg 2: end to end through SceneRunner.infer — pinned host input, H2D + D2H inside the timed region
-    e2e_ms = timed_steps(lambda: runner.infer(host))
-    e2e_total = max_over_ranks(sum(e2e_ms))
+    # ---- leg 2: end to end through the public API — pinned host input, H2D + forward + D2H of the predictions inside
+    # the timed region, K steps pipelined
+    e2e_total = max_over_ranks(timed_pipeline(pipe.run, [hosts[k % R] for k in range(args.steps)]))
     e2e_value = world * batch * args.steps / (e2e_total / 1e3)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -255,32 +310,54 @@ def run_gpu_arm(args, cfg, n_points, batch):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel among ours (by time inside the timed steps)
+    # ---- roofline of the dominant kernel among ours (by time inside the sequential instrumented steps).
+    # Launches are grouped by C-ABI entry point (= by kernel): the tensor-core GEMM kernel runs ~25 times per step at
+    # different shapes and is judged as one kernel: sum of algorithmic work / sum of launch durations.
     hbm_peak, peak_src = peaks()
-    per_kernel = []
+    tf32_peak, tf32_src = tensor_peak()
+    per_kernel, groups = [], {}
     for key, ms in kernel_ms.items():
         if not ms:
             continue
         avg = sum(ms) / len(ms)
         nbytes = algorithmic_bytes(key, batch)
+        flops = algorithmic_flops(key)
         per_kernel.append({"kernel": key, "calls_per_step": len(ms) / args.steps, "avg_ms": round(avg, 4),
                            "ms_per_step": round(sum(ms) / args.steps, 4),
-                           "algorithmic_GBps": round(nbytes / avg / 1e6, 2) if nbytes else None})
+                           "algorithmic_GBps": round(nbytes / avg / 1e6, 2) if nbytes else None,
+                           "algorithmic_TFLOPs": round(flops[0] / avg / 1e9, 1) if flops else None})
+        g = groups.setdefault(key.partition("(")[0], {"ms": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0, "mma": 0.0})
+        g["ms"] += sum(ms)
+        g["launches"] += len(ms)
+        g["bytes"] += (nbytes or 0) * len(ms)
+        if flops:
+            g["flops"] += flops[0] * len(ms)
+            g["mma"] += flops[1] * len(ms)
     per_kernel.sort(key=lambda r: -r["ms_per_step"])
-    top = per_kernel[0] if per_kernel else None
     roofline = None
-    if top:
-        achieved = top["algorithmic_GBps"] or 0.0
-        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": top["avg_ms"],
-                    "share_of_step": round(top["ms_per_step"] / (sum(inst_ms) / args.steps), 4)}
-        if top["kernel"].startswith("pdab_fps"):
-            a = [int(x) for x in top["kernel"].partition("(")[2].strip(")").split(",") if x.strip()]
-            b_, n_, m_ = a[:3]
-            roofline["note"] = ("FPS is a serial chain bound by on-chip ALU/shared-memory throughput, not HBM "
-                                "(SURVEY.md §8d); on-chip point-updates/s given beside the HBM figure")
-            roofline["onchip_updates_per_s"] = round(b_ * n_ * (m_ - 1) / (top["avg_ms"] / 1e3), 0)
+    if groups:
+        name, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
+        step_ms = sum(inst_ms) / args.steps
+        common = {"kernel": name, "launches_per_step": g["launches"] / args.steps,
+                  "avg_launch_ms": round(g["ms"] / g["launches"], 4), "share_of_step": round(g["ms"] / args.steps / step_ms, 4),
+                  "traffic": None}
+        if g["flops"] > 0:  # tensor-core kernel: algorithmic flops = 2*rows*k*nout of the fp32 product it computes
+            achieved = g["flops"] / g["ms"] / 1e9
+            roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": round(achieved / tf32_peak, 4), "peak_source": tf32_src,
+                        "mma_issued_TFLOPs": round(g["mma"] / g["ms"] / 1e9, 1),
+                        "mma_issued_frac": round(g["mma"] / g["ms"] / 1e9 / tf32_peak, 4),
+                        "hbm_GBps": round(g["bytes"] / g["ms"] / 1e6, 1),
+                        "note": "fp32-level products on TF32 tensor cores need 3 MMAs per product (error-compensated "
+                                "3xTF32): `achieved` counts the product once (algorithmic), `mma_issued_*` counts "
+                                "the MMAs the tensor pipe executed", **common}
+        else:
+            achieved = g["bytes"] / g["ms"] / 1e6
+            roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(achieved / hbm_peak, 5), "peak_source": peak_src, **common}
+            if name == "pdab_fps":
+                roofline["note"] = ("FPS is a serial chain bound by on-chip ALU/shared-memory latency, not HBM "
+                                    "(SURVEY.md §8d)")
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -296,10 +373,14 @@ def run_gpu_arm(args, cfg, n_points, batch):
         "config": {"workload": f"PDA-SSD {args.config} cfg full inference (backbone+vote+centroid aggregation+head+3D NMS), "
                                f"batch {batch} x {n_points} pts per GPU, random-init weights",
                    "scenes_per_gpu_per_step": batch, "points_per_scene": n_points, "parallelism": f"scene-sharded x{world}",
-                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)",
+                   "pipeline": f"{args.depth} batches in flight per GPU (one stream + one CUDA graph each)"
+                               if not args.no_graphs else f"{args.depth} batches in flight per GPU (streams, eager launches)",
+                   "l2": "256 MiB flush before the timed region; inside it every step streams ~2.5 GB of intermediates "
+                         "(>> 126 MB L2) and the steps rotate over 4 distinct input batches",
+                   "sequential_ms_per_step": round(sum(seq_ms) / len(seq_ms), 3),
                    "torch_layers": f"fp32 matmul mode {args.matmul}; cuDNN 1x1 convs TF32-allowed (torch default, as the reference)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
-                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_total / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_total / args.steps},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "kernels": per_kernel[:12],
     }

@@ -180,6 +180,11 @@ int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilo
                    const float *w_packed, const float *bias, const float *residual, int ldr, const float *gamma,
                    const float *beta, float eps, int nsample, float *out, int ldo, pdab_stream_t stream);
 
+/* Grid size of the persistent tensor-core kernels (default 148 = one CTA per SM).  A caller that pipelines batches on
+ * several streams lowers it (e.g. 148 - scenes per batch) so the persistent grid never queues behind the one-CTA-per-
+ * scene FPS kernels of another batch.  Process-wide; 1 <= n <= 148. */
+int pdab_set_persistent_ctas(int n);
+
 /* Number of floats pdab_tc_pack_weights writes for a (nout, k) weight matrix. */
 size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn);
 /* Packs W (nout, k) row-major (device) into the shared-memory image the tensor-core kernels stream:

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "pdab_group_attention": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
+    "pdab_set_persistent_ctas": (_i, [_i]),
     "pdab_tc_packed_floats": (_sz, [_i, _i, _i, _i]),
     "pdab_tc_pack_weights": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_tc_sa_gather_linear": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -129,6 +130,6 @@ def call(fn: str, *args) -> int:
     start.record(stream)
     rc = f(*args)
     end.record(stream)
-    key = fn + str(tuple(a for a in args[:6] if isinstance(a, int) and 0 <= a < (1 << 24)))  # fn + leading sizes
+    key = fn + str(tuple(a for a in args[:7] if isinstance(a, int) and 0 <= a < (1 << 24)))  # fn + leading sizes
     _timing.setdefault(key, []).append((start, end))
     return check(fn, rc)

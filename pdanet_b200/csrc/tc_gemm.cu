@@ -630,6 +630,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
     }
 }
 
+// CTAs of the persistent grid.  148 = every SM; a pipelined caller that overlaps this kernel with SM-filling latency
+// chains of another batch (FPS: one 192 KB-smem CTA per scene) lowers it so that no CTA of the grid waits for an SM.
+int g_persistent_ctas = pdab::kNumSMs;
+
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
 int launch(const GemmParams &p, cudaStream_t s) {
     using C = Cfg<NPASS, BN>;
@@ -639,7 +643,7 @@ int launch(const GemmParams &p, cudaStream_t s) {
         PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    const long long grid = p.n_items < pdab::kNumSMs ? p.n_items : pdab::kNumSMs;
+    const long long grid = p.n_items < g_persistent_ctas ? p.n_items : g_persistent_ctas;
     kern<<<(unsigned)grid, kThreads, C::SMEM_BYTES, s>>>(p);
     PDAB_LAUNCH_CHECK();
     return 0;
@@ -681,6 +685,12 @@ int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
 }
 
 }  // namespace
+
+extern "C" int pdab_set_persistent_ctas(int n) {
+    if (n < 1 || n > pdab::kNumSMs) return PDAB_EINVAL;
+    g_persistent_ctas = n;
+    return 0;
+}
 
 // See include/pdab.h for the contract.
 extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilogue, const float *a, int lda,

@@ -32,12 +32,15 @@ class IASSD(nn.Module):
         self.module_list = [self.backbone_3d, self.point_head]
         self.nms_utils = nms_utils if nms_utils is not None else _cuda_nms
         self.batched_post_processing = batched_post_processing and hasattr(self.nms_utils, "nms_batched")
+        self.output_padded = False  # True: forward returns post_processing_padded's fixed-shape device tensors
 
     def forward(self, batch_dict):
         for module in self.module_list:
             batch_dict = module(batch_dict)
         if self.training:
             raise NotImplementedError("training losses are outside the built hot path")
+        if self.output_padded:
+            return self.post_processing_padded(batch_dict)
         if self.batched_post_processing:
             return self.post_processing_batched(batch_dict)
         return self.post_processing(batch_dict)
@@ -93,6 +96,48 @@ class IASSD(nn.Module):
                                "pred_scores": (raw_max if raw_max is not None else scores)[s].index_select(0, sel),
                                "pred_labels": labels[s].index_select(0, sel)})
         return pred_dicts, {}
+
+
+    # ------------------------------------------------------------------ fixed shapes, no host sync
+    def post_processing_padded(self, batch_dict):
+        """Same selection as `post_processing_batched`, returned as fixed-shape device tensors with NO host sync, so the
+        whole forward can be captured in a CUDA graph and pipelined across streams:
+        pred_boxes (B,P,C), pred_scores (B,P), pred_labels (B,P) int64, num (B) int32; rows >= num[s] are zero.
+        `unpack_padded` turns the host copy into the reference's list of pred_dicts."""
+        cfg = self.model_cfg.POST_PROCESSING
+        nms_cfg = cfg.NMS_CONFIG
+        B = batch_dict["batch_size"]
+        boxes = batch_dict["batch_box_preds"]
+        M = boxes.shape[0] // B
+        boxes = boxes.view(B, M, boxes.shape[-1])
+        src_cls = batch_dict["batch_cls_preds"].view(B, M, -1)
+        probs = src_cls if batch_dict["cls_preds_normalized"] else torch.sigmoid(src_cls)
+        scores, labels = probs.max(dim=-1)
+        labels = labels + 1
+        valid = scores >= cfg.SCORE_THRESH
+        key = torch.where(valid, scores, torch.full_like(scores, float("-inf")))
+        _, order = key.sort(dim=1, descending=True, stable=True)      # (score desc, index asc)
+        counts = valid.sum(dim=1).clamp(max=nms_cfg.NMS_PRE_MAXSIZE).int()
+        sorted_boxes = torch.gather(boxes[..., :7], 1, order.unsqueeze(-1).expand(-1, -1, 7)).contiguous()
+        keep, num = self.nms_utils.nms_batched(sorted_boxes, counts, nms_cfg.NMS_THRESH)
+        P = min(M, nms_cfg.NMS_POST_MAXSIZE)
+        num = num.clamp(max=P)
+        live = torch.arange(P, device=boxes.device).unsqueeze(0) < num.unsqueeze(1)            # (B, P)
+        sel = torch.gather(order, 1, torch.where(live, keep[:, :P], torch.zeros_like(keep[:, :P])))
+        out_scores = src_cls.max(dim=-1)[0] if cfg.OUTPUT_RAW_SCORE else scores
+        return {
+            "pred_boxes": torch.gather(boxes, 1, sel.unsqueeze(-1).expand(-1, -1, boxes.shape[-1])) * live.unsqueeze(-1),
+            "pred_scores": torch.gather(out_scores, 1, sel) * live,
+            "pred_labels": torch.gather(labels, 1, sel) * live,
+            "num": num,
+        }
+
+    @staticmethod
+    def unpack_padded(padded_host):
+        """Host copy of `post_processing_padded`'s tensors -> list of pred_dicts (views, no copies)."""
+        nums = padded_host["num"].tolist()
+        return [{"pred_boxes": padded_host["pred_boxes"][s, :n], "pred_scores": padded_host["pred_scores"][s, :n],
+                 "pred_labels": padded_host["pred_labels"][s, :n]} for s, n in enumerate(nums)]
 
 
 def build_model(cfg, ops=None, nms_utils=None, batched_post_processing=True) -> IASSD:

@@ -459,7 +459,9 @@ class Vote_layer(nn.Module):
         feat_offsets = offsets[..., 3:]                       # empty: ctr_reg has 3 outputs
         ctr_offsets = offsets[..., :3]
         if self.max_offset_limit is not None:
-            lim = self.max_offset_limit.to(xyz.device).view(1, 1, 3)
+            if self.max_offset_limit.device != xyz.device:  # moved once (not a registered buffer in the reference,
+                self.max_offset_limit = self.max_offset_limit.to(xyz.device)  # :1708-1710: state_dict keys unchanged)
+            lim = self.max_offset_limit.view(1, 1, 3)
             limited = torch.minimum(torch.maximum(ctr_offsets, -lim), lim)
             vote_xyz = xyz + limited
         else:

@@ -64,3 +64,122 @@ class SceneRunner:
             torch.cuda.current_stream().synchronize()
         self.d2h_bytes = nbytes
         return out
+
+
+class ScenePipeline:
+    """`depth` batches in flight on one GPU, one CUDA stream per slot, the whole forward of a slot captured ONCE in a
+    CUDA graph (fixed shapes: batch_size x num_points), replayed per batch.
+
+    Why: distance-FPS is a serial latency chain that occupies one SM per scene for milliseconds (hard
+    part 1); run back to back it idles ~130 SMs.  With two batches in flight the FPS of batch k+1 runs on its 16 SMs
+    while the tensor-core / gather kernels of batch k use the others; the graph removes the host launch cost of the
+    ~350 kernels of a step.  The persistent tensor-core kernels are told to leave one SM per in-flight scene free
+    (`pdab_set_persistent_ctas`) so their grid never queues behind an FPS CTA.
+
+    Results are identical to `SceneRunner.infer` (same kernels, same order per batch); tests check it.
+    """
+
+    def __init__(self, runner: SceneRunner, depth: int = 2, graphs: bool = True, warm_points: torch.Tensor = None):
+        from types import SimpleNamespace
+        from . import _lib
+        from .synthetic import make_batch
+        self.runner, self.depth, self.graphs = runner, depth, graphs
+        dev, B, N = runner.device, runner.batch_size, runner.num_points
+        self.model = runner.model
+        self.launches_per_step = 0
+        if depth > 1 and B < 100:
+            _lib.check("pdab_set_persistent_ctas", _lib.lib().pdab_set_persistent_ctas(148 - B))
+        if warm_points is None:
+            warm_points = make_batch(B, N, runner.cfg.POINT_CLOUD_RANGE)["points"]
+        self.slots = []
+        with torch.cuda.device(dev), torch.no_grad():
+            for _ in range(depth):
+                s = SimpleNamespace(stream=torch.cuda.Stream(dev), inp=torch.empty(B * N, 5, device=dev),
+                                    pinned_in=torch.empty(B * N, 5).pin_memory(), graph=None, out=None,
+                                    pinned_out=None, done=torch.cuda.Event(), busy=False, tag=None)
+                s.inp.copy_(warm_points.to(dev))
+                torch.cuda.synchronize(dev)
+                with torch.cuda.stream(s.stream):
+                    for _ in range(2):  # builds the packed weights / folded parameters, primes cuBLAS and cuDNN
+                        s.out = self._forward(s.inp)
+                s.stream.synchronize()
+                if graphs:
+                    before = sum(_lib.launch_counts.values())
+                    s.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(s.graph, stream=s.stream):
+                        s.out = self._forward(s.inp)
+                    self.launches_per_step = sum(_lib.launch_counts.values()) - before
+                s.pinned_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in s.out.items()}
+                self.slots.append(s)
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.slots[0].pinned_out.values())
+        self.h2d_bytes = B * N * 5 * 4
+
+    def _forward(self, points_dev):
+        prev = self.model.output_padded
+        self.model.output_padded = True
+        try:
+            return self.model({"batch_size": self.runner.batch_size, "points": points_dev})
+        finally:
+            self.model.output_padded = prev
+
+    def _launch(self, s, src, to_host):
+        from . import _lib
+        with torch.cuda.stream(s.stream):
+            s.inp.copy_(src, non_blocking=True)
+            if self.graphs:
+                s.graph.replay()
+            else:
+                s.out = self._forward(s.inp)
+            if to_host:
+                for k, v in s.out.items():
+                    s.pinned_out[k].copy_(v, non_blocking=True)
+            s.done.record(s.stream)
+        s.busy = True
+
+    def _collect(self, s, to_host):
+        s.done.synchronize()
+        s.busy = False
+        if not to_host:
+            return None
+        return self.model.unpack_padded({k: v.clone() for k, v in s.pinned_out.items()})
+
+    @torch.no_grad()
+    def run(self, host_batches, start_event: torch.cuda.Event = None) -> List[List[dict]]:
+        """Host (B*N,5) batches -> per-batch lists of host pred_dicts; H2D, forward and D2H of different batches overlap.
+        `start_event` (recorded by the caller) is waited on by every slot stream before its first work."""
+        return self._run(host_batches, True, start_event)
+
+    @torch.no_grad()
+    def run_device(self, dev_batches, start_event: torch.cuda.Event = None):
+        """Batches already resident in HBM; predictions stay on the device (overwritten per slot) — throughput leg."""
+        return self._run(dev_batches, False, start_event)
+
+    def _run(self, batches, to_host, start_event):
+        results = [None] * len(batches)
+        with torch.cuda.device(self.runner.device):
+            if start_event is not None:
+                for s in self.slots:
+                    s.stream.wait_event(start_event)
+            for k, b in enumerate(batches):
+                s = self.slots[k % self.depth]
+                if s.busy:
+                    results[s.tag] = self._collect(s, to_host)
+                src = b
+                if to_host and not b.is_pinned():
+                    s.pinned_in.copy_(b)
+                    src = s.pinned_in
+                s.tag = k
+                self._launch(s, src, to_host)
+            for s in self.slots:
+                if s.busy:
+                    results[s.tag] = self._collect(s, to_host)
+        return results
+
+    def join_event(self) -> torch.cuda.Event:
+        """An event on the current stream that fires after everything enqueued on the slot streams."""
+        cur = torch.cuda.current_stream(self.runner.device)
+        for s in self.slots:
+            cur.wait_event(s.done)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(cur)
+        return e

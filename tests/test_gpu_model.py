@@ -183,3 +183,33 @@ def test_pda_group_tokens_matches_channel_major_grouper():
         assert torch.equal(tok[..., 0:7], ref[..., 0:7])
         assert torch.equal(tok[..., 8:], ref[..., 7:])
         assert (tok[..., 7] == 0).all()
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_pipelined_runner_equals_sequential_runner(graphs):
+    """ScenePipeline (2 batches in flight, CUDA graphs, padded sync-free post-processing) returns exactly what
+    SceneRunner.infer returns batch by batch — pipelining is scheduling, not arithmetic."""
+    from pdanet_b200 import _lib
+    from pdanet_b200.runner import ScenePipeline, SceneRunner
+    cfg = load_config("kitti")
+    B, N = 2, 16384
+    runner = SceneRunner(cfg, device="cuda:0", batch_size=B, num_points=N, seed=0)
+    batches = [make_batch(B, N, cfg.POINT_CLOUD_RANGE, first_scene=10 * k)["points"] for k in range(5)]
+    want = [runner.infer(b) for b in batches]
+    try:
+        pipe = ScenePipeline(runner, depth=2, graphs=graphs, warm_points=batches[0])
+        got = pipe.run(batches)
+        got2 = pipe.run(batches[::-1])[::-1]       # slots reused in another order: no state leaks between replays
+    finally:
+        _lib.lib().pdab_set_persistent_ctas(148)
+    if graphs:
+        assert pipe.launches_per_step > 20
+    for res in (got, got2):
+        assert len(res) == len(want)
+        for w_b, g_b in zip(want, res):
+            assert len(w_b) == len(g_b) == B
+            for w, g in zip(w_b, g_b):
+                assert w["pred_boxes"].shape == g["pred_boxes"].shape
+                assert torch.equal(w["pred_labels"], g["pred_labels"])
+                assert torch.allclose(w["pred_boxes"], g["pred_boxes"], rtol=1e-5, atol=1e-5)
+                assert torch.allclose(w["pred_scores"], g["pred_scores"], rtol=1e-5, atol=1e-6)
