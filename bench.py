@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight per GPU (ScenePipeline slots)")
     ap.add_argument("--no-graphs", action="store_true", help="do not capture the forward in CUDA graphs")
+    ap.add_argument("--tc-passes", type=int, default=None, choices=[1, 2, 3],
+                    help="tensor-core product mode of our GEMM kernels: 3 = 3xTF32 (fp32-level), 2 = split-bf16 (2^-16), "
+                         "1 = TF32; default = the modules' default")
     ap.add_argument("--matmul", default="ieee", choices=["ieee", "tf32"],
                     help="fp32 matmul mode of the unchanged PyTorch layers (PDA transformer); our kernels are fp32 either way")
     return ap.parse_args()
@@ -224,7 +227,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
     _lib.lib()  # fail loudly if the extension is missing
 
     torch.backends.cuda.matmul.allow_tf32 = args.matmul == "tf32"
-    runner = SceneRunner(cfg, device=dev, batch_size=batch, num_points=n_points, seed=0)
+    runner = SceneRunner(cfg, device=dev, batch_size=batch, num_points=n_points, seed=0, tc_passes=args.tc_passes)
     # weak scaling: every rank owns its own scenes (global scene ids rank*batch*R ...); the steps rotate over
     # R distinct synthetic batches so consecutive steps never see the same input
     R = 4
@@ -378,6 +381,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
                    "l2": "256 MiB flush before the timed region; inside it every step streams ~2.5 GB of intermediates "
                          "(>> 126 MB L2) and the steps rotate over 4 distinct input batches",
                    "sequential_ms_per_step": round(sum(seq_ms) / len(seq_ms), 3),
+                   "tc_passes": next((m.tc_passes for m in runner.model.modules() if hasattr(m, "tc_passes")), None),
                    "torch_layers": f"fp32 matmul mode {args.matmul}; cuDNN 1x1 convs TF32-allowed (torch default, as the reference)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_total / args.steps},

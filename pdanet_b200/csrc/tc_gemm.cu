@@ -34,8 +34,9 @@ using u32 = uint32_t;
 using u64 = uint64_t;
 
 constexpr int BM = 128;            // rows per tile (TMEM lanes)
-constexpr int BK = 32;             // floats per k-atom (128 B swizzle row)
-constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+constexpr int BK = 32;             // fp32 / tf32 elements per k-atom (128 B swizzle row); bf16 mode: 64 elements
+constexpr int A_TILE_BYTES = BM * 128;     // 16 KB: 128 rows x one 128-byte swizzle row
+__host__ __device__ constexpr int bk_of(int npass) { return npass == 2 ? 64 : 32; }
 constexpr int kProducerWarps = 8;
 constexpr int kThreads = 32 * (2 + kProducerWarps + 4);
 constexpr int kTmemCols = 512;
@@ -134,6 +135,15 @@ __device__ __forceinline__ void umma_tf32(u32 d_tmem, u64 adesc, u64 bdesc, u32 
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with bf16 operands (kind::f16): K = 16 per instruction, twice the tf32 rate.
+__device__ __forceinline__ void umma_bf16(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(u32 bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -181,9 +191,25 @@ __device__ __forceinline__ u64 umma_desc(u32 smem_addr) {
     return (u64)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // Instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128.
-template <int BN>
+// FMT: 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16).
+template <int BN, int FMT>
 __device__ __forceinline__ constexpr u32 umma_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+    return (1u << 4) | ((u32)FMT << 7) | ((u32)FMT << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+}
+// 8 fp32 -> 8 bf16 (round to nearest even) packed in a uint4, and the bf16 of the remainders
+__device__ __forceinline__ void bf16_split8(const float4 &a, const float4 &b, uint4 &hi, uint4 &lo) {
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // cvt.rn.bf16x2.f32 d, hi_half_src, lo_half_src
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+        const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);
+        const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
@@ -197,8 +223,8 @@ __device__ __forceinline__ float tf32_rna(float v) {
 
 template <int NPASS, int BN>
 struct Cfg {
-    static constexpr int W_TILE_BYTES = BN * BK * 4;                       // one of {hi, lo}
-    static constexpr int STAGE_BYTES = (NPASS == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
+    static constexpr int W_TILE_BYTES = BN * 128;                          // one of {hi, lo}
+    static constexpr int STAGE_BYTES = (NPASS >= 2 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
     static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW >= 4 ? 4 : 2;
     // A-producer groups: group g owns k-atom steps g, g+G, ...  G must divide STAGES so that every smem stage belongs
@@ -206,7 +232,8 @@ struct Cfg {
     // consecutive phases apart).
     static constexpr int GROUPS = STAGES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      4 * 32 * kStgPitch * 4 /*epilogue staging tiles*/;
+                                      4 * 32 * kStgPitch * 4 /*epilogue staging tiles*/ +
+                                      4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/;
 };
 
 struct Pipe {
@@ -242,8 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
     volatile u32 *tmem_slot_ptr = reinterpret_cast<volatile u32 *>(smem + S * C::STAGE_BYTES + 8 * (3 * S + 4));
 
     auto a_hi = [&](int s) { return smem_base + (u32)s * C::STAGE_BYTES; };
-    auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };                       // NPASS == 3 only
-    auto w_hi = [&](int s) { return a_hi(s) + (NPASS == 3 ? 2 : 1) * A_TILE_BYTES; };
+    auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };                       // NPASS >= 2 only
+    auto w_hi = [&](int s) { return a_hi(s) + (NPASS >= 2 ? 2 : 1) * A_TILE_BYTES; };
     auto w_lo = [&](int s) { return w_hi(s) + C::W_TILE_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +288,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (EPI == E_ADD_LN) {  // LayerNorm scale / shift -> smem once (Nout = NCH * BN <= 512 columns)
+        float *sg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + 4 * 512;
+        for (int i = threadIdx.x; i < NCH * BN; i += kThreads) {
+            sg[i] = __ldg(p.gamma + i);
+            sg[512 + i] = __ldg(p.beta + i);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -273,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
         // ===================================================================== W loader
         if (lane == 0) {
             Pipe pipe;
-            constexpr u32 BYTES = (NPASS == 3 ? 2 : 1) * C::W_TILE_BYTES;
+            constexpr u32 BYTES = (NPASS >= 2 ? 2 : 1) * C::W_TILE_BYTES;
             for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int n_group = (int)(item % p.n_groups);
                 for (int c = 0; c < NCH; c++) {
@@ -282,7 +316,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                     for (int ka = 0; ka < KA; ka++) {
                         mbar_wait(empty(pipe.stage), pipe.phase ^ 1);
                         mbar_arrive_expect_tx(full_w(pipe.stage), BYTES);
-                        bulk_g2s(w_hi(pipe.stage), src + (size_t)ka * BYTES, BYTES, full_w(pipe.stage));
+                        // several smaller bulk copies: more requests in flight per SM than one 64 KB copy
+                        constexpr u32 PIECE = 8192;
+#pragma unroll
+                        for (u32 o = 0; o < BYTES; o += PIECE)
+                            bulk_g2s(w_hi(pipe.stage) + o, src + (size_t)ka * BYTES + o, PIECE, full_w(pipe.stage));
                         pipe.advance<S>();
                     }
                 }
@@ -294,7 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             Pipe pipe;
             int as = 0;
             u32 aphase = 0;
-            constexpr u32 idesc = umma_idesc<BN>();
+            constexpr u32 idesc = umma_idesc<BN, NPASS == 2 ? 1 : 2>();
+            constexpr int BKE = bk_of(NPASS), KSTEP = NPASS == 2 ? 16 : 8;   // elements per k-atom / per MMA
             for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
                 mbar_wait(acc_empty(as), aphase ^ 1);  // epilogue has drained this accumulator stage
                 tc_fence_after();
@@ -305,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                         mbar_wait(full_a(pipe.stage), pipe.phase);
                         tc_fence_after();
                         // k-steps of 8 inside the atom; the last atom may be partially filled (zero padded)
-                        const int ksteps = (ka == KA - 1) ? ((p.K - ka * BK + 7) >> 3) : (BK / 8);
+                        const int ksteps = (ka == KA - 1) ? ((p.K - ka * BKE + KSTEP - 1) / KSTEP) : (BKE / KSTEP);
                         for (int kk = 0; kk < ksteps; kk++) {
                             const u32 acc = (ka | kk) ? 1u : 0u;
                             const u64 ah = umma_desc(a_hi(pipe.stage) + kk * 32);
@@ -316,6 +355,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                                 umma_tf32(d, ah, wl, idesc, acc);   // small terms first
                                 umma_tf32(d, al, wh, idesc, 1u);
                                 umma_tf32(d, ah, wh, idesc, 1u);
+                            } else if (NPASS == 2) {
+                                const u64 al = umma_desc(a_lo(pipe.stage) + kk * 32);
+                                const u64 wl = umma_desc(w_lo(pipe.stage) + kk * 32);
+                                umma_bf16(d, ah, wl, idesc, acc);
+                                umma_bf16(d, al, wh, idesc, 1u);
+                                umma_bf16(d, ah, wh, idesc, 1u);
                             } else {
                                 umma_tf32(d, ah, wh, idesc, acc);
                             }
@@ -344,12 +389,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
         constexpr int G = C::GROUPS;                      // 2 or 4
         constexpr int WPG = kProducerWarps / G;           // warps per group
         constexpr int RSTEP = 4 * WPG;                    // rows covered by one group-wide access
-        constexpr int R = BM / RSTEP;                     // rows (float4 loads in flight) per thread
+        constexpr int R = BM / RSTEP;                     // rows per thread
+        constexpr int V = NPASS == 2 ? 2 : 1;             // float4 loads per row: bf16 mode packs 8 fp32 -> one 16 B chunk
+        constexpr int BKE = bk_of(NPASS);                 // elements per k-atom
         const int pw = warp - 2;
         const int g = pw / WPG, h = pw % WPG;
-        const int chunk = lane & 7;                       // 16-byte chunk inside the 128-byte row
+        const int chunk = lane & 7;                       // 16-byte chunk inside the 128-byte smem row
         const int r0 = h * 4 + (lane >> 3);               // rows r0 + RSTEP i, i = 0..R-1
-        float4 v[R];
+        float4 v[R][V];
         int src_row[R];                       // A_GATHER: flat source point row (b*Nsrc + i) per owned row, -1 = padding
         long long meta_item = -1;
 
@@ -362,13 +409,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             const int ka = (int)(step - li * steps_per_item) % KA;
             const long long item = blockIdx.x + li * gridDim.x;
             const long long m0 = (item / p.n_groups) * BM;
-            const int k = ka * BK + chunk * 4;
+            const int k = ka * BKE + chunk * 4 * V;       // first fp32 column this thread converts
             if (ALOAD == A_ROWS) {
 #pragma unroll
                 for (int i = 0; i < R; i++) {
                     const long long t = m0 + r0 + RSTEP * i;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t < p.T && k < p.K) v[i] = __ldg(reinterpret_cast<const float4 *>(p.A + t * p.lda + k));
+#pragma unroll
+                    for (int u = 0; u < V; u++) {
+                        v[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t < p.T && k + 4 * u < p.K)
+                            v[i][u] = __ldg(reinterpret_cast<const float4 *>(p.A + t * p.lda + k + 4 * u));
+                    }
                 }
             } else {
                 if (item != meta_item) {
@@ -385,16 +436,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                 }
 #pragma unroll
                 for (int i = 0; i < R; i++) {
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (src_row[i] >= 0) {
-                        if (k < p.C) {
-                            v[i] = __ldg(reinterpret_cast<const float4 *>(p.feat_t + (size_t)src_row[i] * p.C + k));
-                        } else if (k == p.C) {  // the three centred coordinates follow the C features
-                            const long long grp = (m0 + r0 + RSTEP * i) / p.ns;  // flat (b, centre)
-                            const float *q = p.xyz + (size_t)src_row[i] * 3;
-                            const float *c = p.new_xyz + grp * 3;
-                            v[i] = make_float4(__ldg(q) - __ldg(c), __ldg(q + 1) - __ldg(c + 1),
-                                               __ldg(q + 2) - __ldg(c + 2), 0.f);
+#pragma unroll
+                    for (int u = 0; u < V; u++) {
+                        const int kc = k + 4 * u;
+                        v[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (src_row[i] >= 0) {
+                            if (kc < p.C) {
+                                v[i][u] = __ldg(reinterpret_cast<const float4 *>(p.feat_t + (size_t)src_row[i] * p.C + kc));
+                            } else if (kc == p.C) {  // the three centred coordinates follow the C features
+                                const long long grp = (m0 + r0 + RSTEP * i) / p.ns;  // flat (b, centre)
+                                const float *q = p.xyz + (size_t)src_row[i] * 3;
+                                const float *c = p.new_xyz + grp * 3;
+                                v[i][u] = make_float4(__ldg(q) - __ldg(c), __ldg(q + 1) - __ldg(c + 1),
+                                                      __ldg(q + 2) - __ldg(c + 2), 0.f);
+                            }
                         }
                     }
                 }
@@ -407,13 +462,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             for (int i = 0; i < R; i++) {
                 const int r = r0 + RSTEP * i;
                 const u32 off = (u32)r * 128u + (u32)((chunk ^ (r & 7)) << 4);
-                const float4 x = v[i];
                 if (NPASS == 3) {
+                    const float4 x = v[i][0];
                     const float4 hh = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     *reinterpret_cast<float4 *>(ah + off) = hh;
                     *reinterpret_cast<float4 *>(ah + A_TILE_BYTES + off) =
                         make_float4(x.x - hh.x, x.y - hh.y, x.z - hh.z, x.w - hh.w);
+                } else if (NPASS == 2) {
+                    uint4 hi, lo;
+                    bf16_split8(v[i][0], v[i][V - 1], hi, lo);
+                    *reinterpret_cast<uint4 *>(ah + off) = hi;
+                    *reinterpret_cast<uint4 *>(ah + A_TILE_BYTES + off) = lo;
                 } else {
+                    const float4 x = v[i][0];
                     *reinterpret_cast<float4 *>(ah + off) =
                         make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
                 }
@@ -429,7 +490,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
         // contiguous bytes (row-per-thread accesses touch 32 different lines per instruction and were 4x slower).
         const int q = warp & 3;                  // TMEM lane quadrant this warp may read
         const int row_in_tile = q * 32 + lane;
-        float *stg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + (warp - (2 + kProducerWarps)) * (32 * kStgPitch);
+        const int ew = warp - (2 + kProducerWarps);   // 0..3
+        float *stg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + ew * (32 * kStgPitch);
+        // Per-column parameters live in shared memory: with ~216 KB of it carved out the L1 is ~12 KB and thrashed by
+        // the A stream, so an __ldg of bias / gamma / beta inside the block loop was an L2 round trip on the critical path.
+        float *sbias = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + ew * 512;
+        const float *sgamma = reinterpret_cast<const float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + 4 * 512;
+        const float *sbeta = sgamma + 512;
         const int srow = lane >> 3, schunk = lane & 7;   // coalesced phase: lane -> (row it*4 + srow, 16-byte chunk)
         int as = 0;
         u32 aphase = 0;
@@ -501,19 +568,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                 }
             }
         };
-        // 32 consecutive per-column parameters (bias / gamma / beta) starting at n0: lane-distributed load + shuffles
-        // would also do; they are L1-resident broadcasts, so plain __ldg of float4 is used.
-        auto add_bias = [&](float (&v)[32], int n0) {
-            if (!p.bias) return;
+        // bias of columns [c0, c0+32) of this item (c0 relative to the item's first column), staged per item below
+        auto add_bias = [&](float (&v)[32], int c0) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
-                if (n0 + e < p.Nout) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + e));
-                    v[e] += b4.x;
-                    v[e + 1] += b4.y;
-                    v[e + 2] += b4.z;
-                    v[e + 3] += b4.w;
-                }
+                const float4 b4 = *reinterpret_cast<const float4 *>(sbias + c0 + e);
+                v[e] += b4.x;
+                v[e + 1] += b4.y;
+                v[e + 2] += b4.z;
+                v[e + 3] += b4.w;
             }
         };
 
@@ -523,6 +586,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             const long long row = m0 + row_in_tile;
             const long long wrow0 = m0 + q * 32;     // first row of this warp's 32-row slab
             const bool row_ok = row < p.T;
+            __syncwarp();
+            for (int i = lane; i < NCH * BN; i += 32) {   // this item's bias -> smem while the MMAs still run
+                const int n = n_group * NCH * BN + i;
+                sbias[i] = (p.bias && n < p.Nout) ? __ldg(p.bias + n) : 0.f;
+            }
+            __syncwarp();
             mbar_wait(acc_full(as), aphase);
             tc_fence_after();
             const u32 tacc = tmem_base + ((u32)(q * 32) << 16) + (u32)(as * ACC_COLS);
@@ -534,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                         if (n0 >= p.Nout) break;
                         float v[32];
                         tmem_ld32(tacc + c * BN + j, v);
-                        add_bias(v, n0);
+                        add_bias(v, c * BN + j);
                         if (EPI == E_RELU) {
 #pragma unroll
                             for (int e = 0; e < 32; e++) v[e] = fmaxf(v[e], 0.f);
@@ -554,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                     if (n0 >= p.Nout) break;
                     float v[32];
                     tmem_ld32(tacc + (b / (BN / 32)) * BN + (b % (BN / 32)) * 32, v);
-                    add_bias(v, n0);
+                    add_bias(v, b * 32);
                     if (EPI == E_ADD_MAXPOOL) {
                         add_tile(v, rn);  // rn is dead once staged: refill it with the next tile right away
                         if (b + 1 < nblk) issue_tile(rn, p.R, p.ldr, wrow0, p.T, n0_of(b + 1));
@@ -599,8 +668,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                     tmem_ld32(tacc + j, v);
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
-                        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + j + e));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + j + e));
+                        const float4 g4 = *reinterpret_cast<const float4 *>(sgamma + j + e);
+                        const float4 b4 = *reinterpret_cast<const float4 *>(sbeta + j + e);
                         v[e] = (v[e] - mean) * rstd * g4.x + b4.x;
                         v[e + 1] = (v[e + 1] - mean) * rstd * g4.y + b4.y;
                         v[e + 2] = (v[e + 2] - mean) * rstd * g4.z + b4.z;
@@ -700,7 +769,8 @@ extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn
     if (rows < 0 || k < 1 || nout < 1 || !a || !w_packed || !out) return PDAB_EINVAL;
     if (rows == 0) return 0;
     if ((k & 3) || (lda & 3) || (ldo & 3) || (nout & 3) || lda < k) return PDAB_EINVAL;
-    if (npass != 1 && npass != 3) return PDAB_EINVAL;
+    if (npass < 1 || npass > 3) return PDAB_EINVAL;
+    if (npass == 2 && (k & 7)) return PDAB_EINVAL;
     if (bn != 128 && bn != 256) return PDAB_EINVAL;
     if ((epilogue == E_ADD_LN || epilogue == E_ADD_MAXPOOL) && (!residual || (ldr & 3))) return PDAB_EINVAL;
     if (epilogue == E_ADD_LN && (!gamma || !beta)) return PDAB_EINVAL;
@@ -711,7 +781,7 @@ extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn
     p.lda = lda;
     p.T = rows;
     p.K = k;
-    p.KA = (k + BK - 1) / BK;
+    p.KA = (k + bk_of(npass) - 1) / bk_of(npass);
     p.Wp = w_packed;
     p.bias = bias;
     p.Nout = nout;
@@ -724,7 +794,8 @@ extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn
     p.eps = eps;
     p.ns = nsample;
     cudaStream_t s = pdab::to_stream(stream);
-    return npass == 3 ? dispatch<3, A_ROWS>(p, epilogue, bn, s) : dispatch<1, A_ROWS>(p, epilogue, bn, s);
+    return npass == 3 ? dispatch<3, A_ROWS>(p, epilogue, bn, s)
+           : npass == 2 ? dispatch<2, A_ROWS>(p, epilogue, bn, s) : dispatch<1, A_ROWS>(p, epilogue, bn, s);
 }
 
 extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
@@ -735,11 +806,11 @@ extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample,
         return PDAB_EINVAL;
     if (b == 0) return 0;
     if ((c & 3) || (c > 0 && !features_t) || (ldo & 3) || (nout & 3)) return PDAB_EINVAL;
-    if (npass != 1 && npass != 3) return PDAB_EINVAL;
+    if (npass < 1 || npass > 3 || (npass == 2 && (c & 7))) return PDAB_EINVAL;
     GemmParams p{};
     p.T = (long long)b * m * nsample;
     p.K = c + 3;
-    p.KA = (p.K + BK - 1) / BK;
+    p.KA = (p.K + bk_of(npass) - 1) / bk_of(npass);
     p.idx = idx;
     p.feat_t = features_t;
     p.xyz = xyz;
@@ -754,5 +825,6 @@ extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample,
     p.out = out;
     p.ldo = ldo;
     cudaStream_t s = pdab::to_stream(stream);
-    return npass == 3 ? dispatch<3, A_GATHER>(p, E_RELU, 256, s) : dispatch<1, A_GATHER>(p, E_RELU, 256, s);
+    return npass == 3 ? dispatch<3, A_GATHER>(p, E_RELU, 256, s)
+           : npass == 2 ? dispatch<2, A_GATHER>(p, E_RELU, 256, s) : dispatch<1, A_GATHER>(p, E_RELU, 256, s);
 }

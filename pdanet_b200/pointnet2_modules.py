@@ -361,6 +361,7 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
         self.pool_method = pool_method
         self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.fin_conv) > 0)
         self.fast_eval = True   # token-major eval path (pda_block.py); False = the reference's statement order
+        self.tc_passes = 3      # tensor-core product mode of the fast path: 3 = 3xTF32, 2 = split-bf16, 1 = TF32
         self._plans = {}
 
     def train(self, mode: bool = True):
@@ -375,7 +376,7 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
     def _scale_fast(self, i, xyz, new_xyz, features_t, centre_feature_t):
         from .pda_block import PDAScalePlan
         if i not in self._plans:
-            self._plans[i] = PDAScalePlan(self, i)
+            self._plans[i] = PDAScalePlan(self, i, npass=self.tc_passes)
         return self._plans[i](self.ops, xyz, new_xyz, features_t, centre_feature_t)
 
     def _scale(self, i, xyz, new_xyz, features, global_feature):

@@ -24,7 +24,8 @@ def shard_scenes(num_scenes: int, world_size: int, rank: int) -> range:
 
 
 class SceneRunner:
-    def __init__(self, cfg="kitti", device="cuda:0", batch_size=16, num_points=None, seed=0, model=None):
+    def __init__(self, cfg="kitti", device="cuda:0", batch_size=16, num_points=None, seed=0, model=None,
+                 tc_passes=None):
         self.cfg = load_config(cfg) if isinstance(cfg, str) else cfg
         self.device = torch.device(device)
         self.batch_size = batch_size
@@ -33,6 +34,10 @@ class SceneRunner:
             torch.manual_seed(seed)
             model = build_model(self.cfg)
         self.model = model.to(self.device).eval()
+        if tc_passes is not None:  # tensor-core product mode of every module that has one (see tc_linear.PackedLinear)
+            for m in self.model.modules():
+                if hasattr(m, "tc_passes"):
+                    m.tc_passes = tc_passes
         rows = self.batch_size * self.num_points
         self._pinned = torch.empty(rows, 5, dtype=torch.float32).pin_memory()
         self._dev = torch.empty(rows, 5, dtype=torch.float32, device=self.device)

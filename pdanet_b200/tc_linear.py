@@ -20,7 +20,9 @@ def _stream(t: torch.Tensor):
 
 
 class PackedLinear:
-    """y = epilogue(x W^T + b).  npass = 3: error-compensated 3xTF32 (fp32-level); npass = 1: plain TF32."""
+    """y = epilogue(x W^T + b).  npass = 3: error-compensated 3xTF32 (fp32-level products); npass = 2: split-bf16
+    "bf16x3" (hi/lo bf16 operands, 3 MMAs at twice the TF32 rate, ~2^-16 relative product error, fp32 range);
+    npass = 1: plain TF32 (2^-11)."""
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], npass: int = 3, bn: Optional[int] = None,
                  xyz_last: int = 0):
@@ -28,6 +30,8 @@ class PackedLinear:
             raise RuntimeError("PackedLinear needs CUDA weights (pdanet_b200 has no CPU path)")
         w = weight.detach().float().contiguous()
         self.nout, self.k = int(w.shape[0]), int(w.shape[1])
+        if npass == 2 and self.k % 8:
+            npass = 3   # split-bf16 packs 8 inputs per 16-byte chunk; odd widths (K = 12 position MLP) use 3xTF32
         self.npass = npass
         self.bn = bn if bn is not None else (256 if self.nout > 128 else 128)
         self.xyz_last = xyz_last

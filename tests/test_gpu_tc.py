@@ -2,6 +2,7 @@
 
 Tolerances (relative to the largest |reference| entry of the output):
   npass = 3 (error-compensated 3xTF32): 5e-6  — fp32-level, what the reference's nn.Linear computes;
+  npass = 2 (split-bf16, "bf16x3")    : 4e-5  — 16-bit-mantissa products (hi/lo bf16 operands, 3 MMAs at the bf16 rate);
   npass = 1 (TF32 operands)           : 2e-3  — TF32 level, what the reference's cuDNN 1x1 convolutions compute.
 """
 import pytest
@@ -9,7 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL = {3: 5e-6, 1: 2e-3}
+TOL = {3: 5e-6, 2: 4e-5, 1: 2e-3}
 
 
 def _dev():
@@ -31,7 +32,7 @@ def _mk(rows, k, nout, seed=0):
     return x, w, b
 
 
-@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("npass", [3, 2, 1])
 @pytest.mark.parametrize("rows,k,nout", [(128, 32, 128), (1000, 256, 768), (4096, 72, 256), (333, 512, 1536),
                                          (2048, 128, 64), (5000, 264, 512)])
 def test_linear_store_and_relu(npass, rows, k, nout):
@@ -52,7 +53,7 @@ def test_linear_store_and_relu(npass, rows, k, nout):
     assert _rel(out, x.double() @ w.double().t()) < TOL[npass]
 
 
-@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("npass", [3, 2, 1])
 @pytest.mark.parametrize("e", [256, 512])
 def test_linear_add_layernorm(npass, e):
     from pdanet_b200.tc_linear import PackedLinear, EPI_ADD_LN
@@ -71,7 +72,7 @@ def test_linear_add_layernorm(npass, e):
     assert _rel(out, ref) < TOL[npass] * 2
 
 
-@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("npass", [3, 2, 1])
 @pytest.mark.parametrize("ns", [16, 32])
 def test_linear_maxpool_epilogues(npass, ns):
     from pdanet_b200.tc_linear import PackedLinear, EPI_ADD_MAXPOOL, EPI_RELU_MAXPOOL
@@ -91,7 +92,7 @@ def test_linear_maxpool_epilogues(npass, ns):
     assert _rel(out, ref) < TOL[npass]
 
 
-@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("npass", [3, 2, 1])
 def test_sa_gather_linear(npass):
     """Gather prologue == grouping_operation x2 + centre subtraction + cat + first 1x1 conv (reference channel order)."""
     from pdanet_b200.tc_linear import PackedLinear

@@ -48,7 +48,7 @@ def main():
         out = torch.empty(rows, nout, device=dev)
         flops = 2.0 * rows * k * nout
         res = {"shape": name, "rows": rows, "k": k, "nout": nout}
-        for npass in (3, 1):
+        for npass in (3, 2, 1):
             lin = PackedLinear(w, b, npass=npass)
             ms = timeit(lambda: lin(x, EPI_STORE, out=out), args.iters)
             res[f"tc{npass}_ms"] = round(ms, 4)

@@ -40,5 +40,19 @@ elif op == "sa_fused":
     bs = [torch.randn(dims[i + 1], device="cuda") * 0.1 for i in range(3)]
     for _ in range(3):
         ops.sa_fused(r, ns, xyz, xyz[:, :M].contiguous(), feats, ws, bs)
+elif op == "tc_linear":   # rows k nout npass epilogue  (epilogue: 0 store 1 relu 2 add+LN 3 add+maxpool 4 relu+maxpool)
+    from pdanet_b200.tc_linear import PackedLinear
+    rows, k, nout, npass, epi = a
+    x = torch.randn(rows, k, device="cuda")
+    lin = PackedLinear(torch.randn(nout, k, device="cuda") / k ** 0.5, torch.randn(nout, device="cuda"), npass=npass)
+    res = torch.randn(rows, nout, device="cuda") if epi in (2, 3) else None
+    norm = torch.nn.LayerNorm(nout).cuda() if epi == 2 else None
+    for _ in range(3):
+        lin(x, epi, residual=res, norm=norm, nsample=32)
+elif op == "attention":   # groups ns heads hd
+    G, ns, H, hd = a
+    qkv = torch.randn(G * ns, 3 * H * hd, device="cuda")
+    for _ in range(3):
+        ops.group_attention(qkv, ns, H)
 torch.cuda.synchronize()
 print("done")
