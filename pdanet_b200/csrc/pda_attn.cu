@@ -9,16 +9,18 @@
 // never crosses neighbourhoods (sequence length NS = nsample, batch = centres).  ctx (T, E): row t = concatenated heads,
 // i.e. exactly the operand of out_proj.
 //
-// One CTA (128 threads) per (neighbourhood, head): Q, K, V tiles (NS x HD each) staged in shared memory (row pitch
-// HD+4 floats: 16-byte aligned, conflict-free for the access patterns below), scores in registers.
-//   S = (Q / sqrt(hd)) K^T : thread (i, jb) owns query row i and KPT = NS/TPR keys; float4 steps along hd, the TPR threads
-//                            of a row read the same q (broadcast), 8 rows per warp hit 8 different bank groups.
-//   softmax               : max / sum over the TPR lanes of a row by shuffles; exp in full precision (expf) so the
-//                            result tracks torch.softmax to ~1e-7.
-//   O = P V               : P goes through shared memory once; thread (i, db) owns HD/TPR output columns, interleaved
-//                            in float4 units so a row's TPR lanes write 16*TPR contiguous bytes per instruction.
-// IEEE fp32 on the CUDA cores throughout (north_star: the distribution-aware encoding stays on CUDA cores; the
-// contractions here are 16x16 / 32x32 — far below a tcgen05 tile).  FLOPs 4*NS*NS*HD per CTA; FMA:LDS ~ 3.5:1.
+// One CTA (4 warps) per (neighbourhood, head).  Q, K, V tiles (NS x HD) are staged in shared memory with coalesced
+// float4 loads; the two contractions are NS x NS x HD — far below a tcgen05 tile (M = 128) — so they run on the
+// warp-level tensor-core path, mma.sync m16n8k8 TF32, with the same error compensation as the big GEMMs:
+//   x = x_hi + x_lo (hi = top 19 bits, exact in TF32),  acc += x_hi y_lo + x_lo y_hi + x_hi y_hi     (3 MMAs)
+// i.e. fp32-level scores and outputs (|err| ~ 1e-6 relative).  A first version on the FMA pipe was bound by shared
+// memory bandwidth (97.8 % l1tex: 9.2 k wavefronts per CTA, profiles/r01_ncu_group_attention_*); fragments cut that ~6x.
+//   S = (Q / sqrt(hd)) K^T : warp w owns m-tile (w % MT) and NS/8/NW n-tiles; A / B fragments by conflict-free LDS.32
+//                            (row pitch HD+4: bank = 4 g + t).
+//   softmax               : S goes through shared memory once; thread (row, lane block) as before, max / sum by
+//                            shuffles over the TPR lanes of a row, full-precision expf (tracks torch.softmax to ~1e-7).
+//   O = P V               : A fragments from P (pitch NS+4), B fragments from V (pitch HD+8: bank = 8 t + g);
+//                            each warp owns HD/8/NW output n-tiles and writes 32-byte row segments.
 #include "common.cuh"
 
 namespace {
@@ -27,107 +29,164 @@ constexpr int kThreads = 128;
 
 template <int NS, int HD>
 struct AttnSmem {
-    static constexpr int PITCH = HD + 4;
-    static constexpr int PP = NS + 1;
-    static constexpr int FLOATS = 3 * NS * PITCH + NS * PP;
+    static constexpr int QP = HD + 4;   // Q, K row pitch (floats)
+    static constexpr int VP = HD + 8;   // V row pitch
+    static constexpr int PP = NS + 4;   // S / P row pitch
+    static constexpr int FLOATS = 2 * NS * QP + NS * VP + NS * PP;
     static constexpr int BYTES = FLOATS * 4;
 };
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// D (16x8, fp32) += A (16x8, row) . B (8x8, col), TF32 operands
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_tf32(d, ah, bl);  // small terms first
+    mma_tf32(d, al, bh);
+    mma_tf32(d, ah, bh);
+}
 
 template <int NS, int HD>
 __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long groups, int heads, const float *__restrict__ qkv,
                                                                    float *__restrict__ ctx) {
     using SM = AttnSmem<NS, HD>;
-    constexpr int PITCH = SM::PITCH, PP = SM::PP;
-    constexpr int TPR = kThreads / NS;      // threads per query row: 4 (NS=32) or 8 (NS=16)
-    constexpr int KPT = NS / TPR;           // keys per thread: 8 or 2
-    constexpr int DPT4 = HD / 4 / TPR;      // float4 output columns per thread
+    constexpr int QP = SM::QP, VP = SM::VP, PP = SM::PP;
+    constexpr int MT = NS / 16;             // m-tiles (16 query rows each): 1 or 2
+    constexpr int NW = 4 / MT;              // warps along n
+    constexpr int S_NT = (NS / 8 + NW - 1) / NW;   // score n-tiles per warp (NS=16: warps 2,3 idle in this phase)
+    constexpr int O_NT = HD / 8 / NW;       // output n-tiles per warp
+    constexpr int TPR = kThreads / NS;      // softmax: threads per query row
+    constexpr int KPT = NS / TPR;           // softmax: keys per thread
     extern __shared__ __align__(16) float sm[];
-    float *sQ = sm, *sK = sQ + NS * PITCH, *sV = sK + NS * PITCH, *sP = sV + NS * PITCH;
+    float *sQ = sm, *sK = sQ + NS * QP, *sV = sK + NS * QP, *sP = sV + NS * VP;
 
     const long long gh = blockIdx.x;
-    const long long g = gh / heads;
-    const int h = (int)(gh - g * heads);
+    const long long grp = gh / heads;
+    const int h = (int)(gh - grp * heads);
     const int E = heads * HD;
-    const float *base = qkv + g * NS * 3LL * E + h * HD;
-    const int tid = threadIdx.x;
+    const float *base = qkv + grp * NS * 3LL * E + h * HD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;  // mma fragment coordinates
 
-    // stage Q (pre-scaled), K, V: rows of HD contiguous floats, float4 coalesced
-    constexpr float scaling = HD == 64 ? 0.125f : 0.08838834764831845f;   // head_dim ** -0.5 (PyTorch scales q)
-    constexpr int F4_PER_ROW = HD / 4;
-    for (int i = tid; i < 3 * NS * F4_PER_ROW; i += kThreads) {
-        const int part = i / (NS * F4_PER_ROW);
-        const int rem = i - part * (NS * F4_PER_ROW);
-        const int r = rem / F4_PER_ROW, c4 = rem - r * F4_PER_ROW;
-        float4 v = __ldg(reinterpret_cast<const float4 *>(base + (long long)r * 3 * E + part * E) + c4);
-        if (part == 0) {
-            v.x *= scaling;
-            v.y *= scaling;
-            v.z *= scaling;
-            v.w *= scaling;
+    // ---- stage Q, K, V (rows of HD contiguous floats) with cp.async: 16-byte copies straight into shared memory, all
+    // of a thread's copies in flight at once (no register staging), so the stage-in costs one memory latency.  The
+    // head_dim ** -0.5 scaling PyTorch applies to q is applied to the scores instead (same product, one rounding later).
+    constexpr float scaling = HD == 64 ? 0.125f : 0.08838834764831845f;
+    constexpr int F4 = HD / 4;
+#pragma unroll 4
+    for (int i = tid; i < 3 * NS * F4; i += kThreads) {
+        const int part = i / (NS * F4);
+        const int rem = i - part * (NS * F4);
+        const int r = rem / F4, c4 = rem - r * F4;
+        const float *src = base + (long long)r * 3 * E + part * E + c4 * 4;
+        float *dst = part == 0 ? sQ + r * QP + c4 * 4 : part == 1 ? sK + r * QP + c4 * 4 : sV + r * VP + c4 * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int mt = warp % MT, nw = warp / MT;
+    const int m0 = mt * 16;
+
+    // ---- S = Q K^T on the tensor cores (3xTF32)
+    if (nw * S_NT * 8 < NS) {
+        float acc[S_NT][4];
+#pragma unroll
+        for (int n = 0; n < S_NT; n++) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll 4
+        for (int k0 = 0; k0 < HD; k0 += 8) {
+            uint32_t ah[4], al[4];
+            split_tf32(sQ[(m0 + g) * QP + k0 + t], ah[0], al[0]);
+            split_tf32(sQ[(m0 + g + 8) * QP + k0 + t], ah[1], al[1]);
+            split_tf32(sQ[(m0 + g) * QP + k0 + t + 4], ah[2], al[2]);
+            split_tf32(sQ[(m0 + g + 8) * QP + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < S_NT; n++) {
+                const int n0 = (nw * S_NT + n) * 8;
+                uint32_t bh[2], bl[2];
+                split_tf32(sK[(n0 + g) * QP + k0 + t], bh[0], bl[0]);
+                split_tf32(sK[(n0 + g) * QP + k0 + t + 4], bh[1], bl[1]);
+                mma_3x(acc[n], ah, al, bh, bl);
+            }
         }
-        *reinterpret_cast<float4 *>(sm + part * NS * PITCH + r * PITCH + c4 * 4) = v;
+#pragma unroll
+        for (int n = 0; n < S_NT; n++) {
+            const int n0 = (nw * S_NT + n) * 8;
+            *reinterpret_cast<float2 *>(sP + (m0 + g) * PP + n0 + 2 * t) =
+                make_float2(acc[n][0] * scaling, acc[n][1] * scaling);
+            *reinterpret_cast<float2 *>(sP + (m0 + g + 8) * PP + n0 + 2 * t) =
+                make_float2(acc[n][2] * scaling, acc[n][3] * scaling);
+        }
     }
     __syncthreads();
 
-    const int i = tid / TPR;     // query row
-    const int jb = tid % TPR;    // key block / output column block
-
-    // ---- scores
-    float s[KPT];
-#pragma unroll
-    for (int jj = 0; jj < KPT; jj++) s[jj] = 0.f;
-    const float *qrow = sQ + i * PITCH;
-#pragma unroll 4
-    for (int d = 0; d < HD; d += 4) {
-        const float4 q4 = *reinterpret_cast<const float4 *>(qrow + d);
+    // ---- softmax over the NS keys of each row (the TPR lanes of a row are adjacent lanes of one warp)
+    {
+        const int i = tid / TPR, jb = tid % TPR;
+        float s[KPT];
+        float mx = -3.4e38f;
 #pragma unroll
         for (int jj = 0; jj < KPT; jj++) {
-            const float4 k4 = *reinterpret_cast<const float4 *>(sK + (jb + jj * TPR) * PITCH + d);
-            s[jj] = fmaf(q4.x, k4.x, s[jj]);
-            s[jj] = fmaf(q4.y, k4.y, s[jj]);
-            s[jj] = fmaf(q4.z, k4.z, s[jj]);
-            s[jj] = fmaf(q4.w, k4.w, s[jj]);
+            s[jj] = sP[i * PP + jb + jj * TPR];
+            mx = fmaxf(mx, s[jj]);
         }
+#pragma unroll
+        for (int off = 1; off < TPR; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < KPT; jj++) {
+            s[jj] = expf(s[jj] - mx);
+            sum += s[jj];
+        }
+#pragma unroll
+        for (int off = 1; off < TPR; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int jj = 0; jj < KPT; jj++) sP[i * PP + jb + jj * TPR] = s[jj] * inv;
     }
-    // ---- softmax over the NS keys of row i (the TPR lanes of a row are adjacent lanes of one warp)
-    float mx = s[0];
-#pragma unroll
-    for (int jj = 1; jj < KPT; jj++) mx = fmaxf(mx, s[jj]);
-#pragma unroll
-    for (int off = 1; off < TPR; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < KPT; jj++) {
-        s[jj] = expf(s[jj] - mx);
-        sum += s[jj];
-    }
-#pragma unroll
-    for (int off = 1; off < TPR; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int jj = 0; jj < KPT; jj++) sP[i * PP + jb + jj * TPR] = s[jj] * inv;
     __syncthreads();
 
-    // ---- O = P V
-    float4 o[DPT4];
+    // ---- O = P V on the tensor cores (3xTF32)
+    {
+        float acc[O_NT][4];
 #pragma unroll
-    for (int e = 0; e < DPT4; e++) o[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int j = 0; j < NS; j++) {
-        const float pj = sP[i * PP + j];
-        const float *vrow = sV + j * PITCH;
+        for (int n = 0; n < O_NT; n++) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
 #pragma unroll
-        for (int e = 0; e < DPT4; e++) {
-            const float4 v4 = *reinterpret_cast<const float4 *>(vrow + (e * TPR + jb) * 4);
-            o[e].x = fmaf(pj, v4.x, o[e].x);
-            o[e].y = fmaf(pj, v4.y, o[e].y);
-            o[e].z = fmaf(pj, v4.z, o[e].z);
-            o[e].w = fmaf(pj, v4.w, o[e].w);
+        for (int k0 = 0; k0 < NS; k0 += 8) {
+            uint32_t ah[4], al[4];
+            split_tf32(sP[(m0 + g) * PP + k0 + t], ah[0], al[0]);
+            split_tf32(sP[(m0 + g + 8) * PP + k0 + t], ah[1], al[1]);
+            split_tf32(sP[(m0 + g) * PP + k0 + t + 4], ah[2], al[2]);
+            split_tf32(sP[(m0 + g + 8) * PP + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < O_NT; n++) {
+                const int n0 = (nw * O_NT + n) * 8;
+                uint32_t bh[2], bl[2];
+                split_tf32(sV[(k0 + t) * VP + n0 + g], bh[0], bl[0]);
+                split_tf32(sV[(k0 + t + 4) * VP + n0 + g], bh[1], bl[1]);
+                mma_3x(acc[n], ah, al, bh, bl);
+            }
+        }
+        float *orow0 = ctx + (grp * NS + m0 + g) * (long long)E + h * HD;
+        float *orow1 = orow0 + 8LL * E;
+#pragma unroll
+        for (int n = 0; n < O_NT; n++) {
+            const int n0 = (nw * O_NT + n) * 8;
+            *reinterpret_cast<float2 *>(orow0 + n0 + 2 * t) = make_float2(acc[n][0], acc[n][1]);
+            *reinterpret_cast<float2 *>(orow1 + n0 + 2 * t) = make_float2(acc[n][2], acc[n][3]);
         }
     }
-    float *orow = ctx + (g * NS + i) * (long long)E + h * HD;
-#pragma unroll
-    for (int e = 0; e < DPT4; e++) *reinterpret_cast<float4 *>(orow + (e * TPR + jb) * 4) = o[e];
 }
 
 template <int NS, int HD>

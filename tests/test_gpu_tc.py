@@ -140,7 +140,7 @@ def test_group_attention_vs_torch_mha(ns, hd):
     q, k, v = [t.double().view(groups, ns, heads, hd).permute(0, 2, 1, 3) for t in qkv.split(E, dim=1)]
     att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(groups * ns, E)
-    assert _rel(ctx, ref) < 2e-6
+    assert _rel(ctx, ref) < 5e-6
 
 
 @pytest.mark.parametrize("tc_passes", [3, 1])
