@@ -155,6 +155,16 @@ int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsample, const f
                   const float *features, int nlayers, const int *dims_host, const float *const *weights_host,
                   const float *const *biases_host, float *out, pdab_stream_t stream);
 
+/* Two scales of one plain SA layer (same centres, same cloud) in ONE kernel: a single scan of the cloud serves both radii,
+ * then both MLP + max-pool phases run; out (B, cout_a + cout_b, M) is the channel-concatenation of the two scales
+ * (PB/pointnet2_modules.py:1655-1674).  weights_host / biases_host: HOST arrays of 6 device pointers, scale a's three
+ * layers then scale b's.  Shapes covered: dims[0] <= 8, a = (16,16,32), b = (32,32,64), nsample <= 32; else
+ * PDAB_EUNSUPPORTED (the caller runs pdab_sa_fused per scale). */
+int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
+                       const float *xyz, const float *new_xyz, const float *features, const int *dims_a_host,
+                       const int *dims_b_host, const float *const *weights_host, const float *const *biases_host,
+                       float *out, pdab_stream_t stream);
+
 /* ---- tensor-core (tcgen05 / TMEM) contractions ---------------------------------- */
 
 /* Epilogues of pdab_tc_linear. */

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_group_attention": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_sa_fused_pair": (_i, [_i, _i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
     "pdab_set_persistent_ctas": (_i, [_i]),
     "pdab_tc_packed_floats": (_sz, [_i, _i, _i, _i]),

@@ -54,4 +54,69 @@ __device__ __forceinline__ void ball_scan_to_smem(int n, const float *__restrict
     __syncthreads();
 }
 
+// Two radii in ONE pass over the cloud (the two scales of an SA layer share centres and points), eight independent
+// distance tests in flight per thread and a single branch for the rare hit.  Same results as two calls of
+// ball_scan_to_smem: hits are taken in index order, each list stops at its own nsample.
+//   tile : shared float4[kScanTile + 8]; sidx_a / sidx_b : shared int[nsample_x * STRIDE]
+template <int THREADS, int STRIDE>
+__device__ __forceinline__ void ball_scan2_to_smem(int n, const float *__restrict__ xyz, bool active, float cx, float cy,
+                                                   float cz, float r2a, int ns_a, float r2b, int ns_b, float4 *tile,
+                                                   int *__restrict__ sidx_a, int *__restrict__ sidx_b) {
+    const int t = threadIdx.x;
+    const int nthreads = blockDim.x;
+    active = active && t < THREADS;
+    int ca = active ? 0 : ns_a, cb = active ? 0 : ns_b;
+    const float r2max = fmaxf(r2a, r2b);
+    for (int base = 0; base < n; base += kScanTile) {
+        const int len = min(kScanTile, n - base);
+        const int len8 = (len + 7) & ~7;
+        __syncthreads();
+        for (int i = t; i < len8; i += nthreads) {
+            if (i < len) {
+                const float *p = xyz + (size_t)(base + i) * 3;
+                tile[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+            } else {
+                tile[i] = make_float4(1e30f, 1e30f, 1e30f, 0.f);  // padding: squared distance overflows to +inf, never a hit
+            }
+        }
+        __syncthreads();
+        if (!__all_sync(0xffffffffu, ca >= ns_a && cb >= ns_b)) {
+            for (int i = 0; i < len8; i += 8) {
+                float d2[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float4 p = tile[i + u];
+                    d2[u] = sqdist3(cx, cy, cz, p.x, p.y, p.z);
+                }
+                const float mn = fminf(fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])),
+                                       fminf(fminf(d2[4], d2[5]), fminf(d2[6], d2[7])));
+                if (mn < r2max && (ca < ns_a || cb < ns_b)) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (d2[u] < r2a && ca < ns_a) {
+                            sidx_a[ca * STRIDE + t] = base + i + u;
+                            ca++;
+                        }
+                        if (d2[u] < r2b && cb < ns_b) {
+                            sidx_b[cb * STRIDE + t] = base + i + u;
+                            cb++;
+                        }
+                    }
+                }
+            }
+        }
+        if (__syncthreads_and(ca >= ns_a && cb >= ns_b)) break;
+    }
+    if (active) {
+        const int fa = ca > 0 ? sidx_a[t] : 0;  // empty ball: the pre-zeroed row groups point 0
+        for (int l = ca; l < ns_a; l++) sidx_a[l * STRIDE + t] = fa;
+        const int fb = cb > 0 ? sidx_b[t] : 0;
+        for (int l = cb; l < ns_b; l++) sidx_b[l * STRIDE + t] = fb;
+    } else if (t < THREADS) {
+        for (int l = 0; l < ns_a; l++) sidx_a[l * STRIDE + t] = 0;
+        for (int l = 0; l < ns_b; l++) sidx_b[l * STRIDE + t] = 0;
+    }
+    __syncthreads();
+}
+
 }  // namespace pdab

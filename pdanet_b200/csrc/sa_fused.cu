@@ -47,6 +47,53 @@ __device__ __forceinline__ void dense(const float *__restrict__ W, const float *
 
 constexpr int kMlpThreads = 256;  // 128 scan threads + 128 helpers; all 8 warps run the MLP phase
 
+// Phase 2 of the fused kernels: one LANE per (centre, neighbour): a warp takes one centre (nsample = 32) or two
+// (nsample = 16) at a time, every lane pushes its neighbour through the three layers with the weights broadcast from
+// shared memory, and the channel maximum over the neighbourhood is a shuffle butterfly; results go to sout[C3][kStride].
+template <int C0P, int C1, int C2, int C3>
+__device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, const float *__restrict__ xyz,
+                                          const float *__restrict__ features, const float *sW1, const float *sb1,
+                                          const float *sW2, const float *sb2, const float *sW3, const float *sb3,
+                                          const float *sctr, const int *sidx, float *sout) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // lanes per centre: 32 (nsample 17..32: idle lanes repeat sample 0, harmless for a max), 16, 8, ...
+    const int lpc = nsample > 16 ? 32 : (nsample > 8 ? 16 : 8);
+    const int cpw = 32 / lpc;                       // centres per warp pass
+    const int sub = lane / lpc, sl = lane % lpc;    // which centre of the pass, which sample lane
+    for (int base = warp * cpw; base < nctr; base += (kMlpThreads / 32) * cpw) {
+        const int jl = min(base + sub, nctr - 1);   // tail: duplicate the last centre (its store is idempotent)
+        const int s = min(sl, nsample - 1);         // nsample <= lpc <= 32: one neighbour per lane
+        const int k = sidx[s * kStride + jl];
+        float in[C0P];
+        in[0] = __ldg(xyz + (size_t)k * 3 + 0) - sctr[jl * 3 + 0];  // grouped_xyz -= new_xyz (PB/pointnet2_utils.py:692)
+        in[1] = __ldg(xyz + (size_t)k * 3 + 1) - sctr[jl * 3 + 1];
+        in[2] = __ldg(xyz + (size_t)k * 3 + 2) - sctr[jl * 3 + 2];
+#pragma unroll
+        for (int q = 3; q < C0P; q++) in[q] = (q - 3 < c) ? __ldg(features + (size_t)(q - 3) * n + k) : 0.f;
+        float h1[C1], h2[C2];
+        dense<C0P, C1, true>(sW1, sb1, in, h1);
+        dense<C1, C2, true>(sW2, sb2, h1, h2);
+        // last layer: each output channel is reduced over the neighbourhood as soon as it is computed
+#pragma unroll 4
+        for (int r = 0; r < C3; r++) {
+            float acc = sb3[r];
+            const float4 *w4 = reinterpret_cast<const float4 *>(sW3 + r * C2);
+#pragma unroll
+            for (int q = 0; q < C2 / 4; q++) {
+                const float4 w = w4[q];
+                acc = fmaf(w.x, h2[4 * q + 0], acc);
+                acc = fmaf(w.y, h2[4 * q + 1], acc);
+                acc = fmaf(w.z, h2[4 * q + 2], acc);
+                acc = fmaf(w.w, h2[4 * q + 3], acc);
+            }
+            float v = fmaxf(acc, 0.f);
+            for (int off = lpc >> 1; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+            if (sl == (r % lpc)) sout[r * kStride + jl] = v;
+        }
+    }
+}
+
+
 // C0P: input width padded to a multiple of 4 (3 + C real channels, rest zero weights/inputs)
 //
 // Phase 1: threads 0..127 each scan the cloud for one centre (hit lists in shared memory).
@@ -108,41 +155,7 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     pdab::ball_scan_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2, nsample, tile, sidx);
 
     const int nctr = min(kThreads, m - j0);
-    // lanes per centre: 32 (nsample 17..32: idle lanes repeat sample 0, harmless for a max), 16, 8, ...
-    const int lpc = nsample > 16 ? 32 : (nsample > 8 ? 16 : 8);
-    const int cpw = 32 / lpc;                       // centres per warp pass
-    const int sub = lane / lpc, sl = lane % lpc;    // which centre of the pass, which sample lane
-    for (int base = warp * cpw; base < nctr; base += (kMlpThreads / 32) * cpw) {
-        const int jl = min(base + sub, nctr - 1);   // tail: duplicate the last centre (its store is idempotent)
-        const int s = min(sl, nsample - 1);         // nsample <= lpc <= 32: one neighbour per lane
-        const int k = sidx[s * kStride + jl];
-        float in[C0P];
-        in[0] = __ldg(xyz + (size_t)k * 3 + 0) - sctr[jl * 3 + 0];  // grouped_xyz -= new_xyz (PB/pointnet2_utils.py:692)
-        in[1] = __ldg(xyz + (size_t)k * 3 + 1) - sctr[jl * 3 + 1];
-        in[2] = __ldg(xyz + (size_t)k * 3 + 2) - sctr[jl * 3 + 2];
-#pragma unroll
-        for (int q = 3; q < C0P; q++) in[q] = (q - 3 < c) ? __ldg(features + (size_t)(q - 3) * n + k) : 0.f;
-        float h1[C1], h2[C2];
-        dense<C0P, C1, true>(sW1, sb1, in, h1);
-        dense<C1, C2, true>(sW2, sb2, h1, h2);
-        // last layer: each output channel is reduced over the neighbourhood as soon as it is computed
-#pragma unroll 4
-        for (int r = 0; r < C3; r++) {
-            float acc = sb3[r];
-            const float4 *w4 = reinterpret_cast<const float4 *>(sW3 + r * C2);
-#pragma unroll
-            for (int q = 0; q < C2 / 4; q++) {
-                const float4 w = w4[q];
-                acc = fmaf(w.x, h2[4 * q + 0], acc);
-                acc = fmaf(w.y, h2[4 * q + 1], acc);
-                acc = fmaf(w.z, h2[4 * q + 2], acc);
-                acc = fmaf(w.w, h2[4 * q + 3], acc);
-            }
-            float v = fmaxf(acc, 0.f);
-            for (int off = lpc >> 1; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-            if (sl == (r % lpc)) sout[r * kStride + jl] = v;
-        }
-    }
+    mlp_phase<C0P, C1, C2, C3>(c, n, nsample, nctr, xyz, features, sW1, sb1, sW2, sb2, sW3, sb3, sctr, sidx, sout);
     __syncthreads();
     for (int i = t; i < C3 * nctr; i += kMlpThreads) {
         const int r = i / nctr, jl = i - r * nctr;
@@ -162,6 +175,94 @@ int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const f
     dim3 grid(pdab::div_up(m, kThreads), b);
     kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, radius * radius, nsample, xyz, new_xyz, features, W[0], B[0], W[1],
                                            B[1], W[2], B[2], out);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Both scales of an SA layer in one kernel: ONE scan of the cloud fills the two hit lists (ball_scan2_to_smem), then the
+// two MLP + max-pool phases run back to back; the outputs land in one (B, A3 + B3, M) tensor, i.e. already concatenated
+// along the channel axis as PB/pointnet2_modules.py:1674 (torch.cat of the scales) wants it.
+template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3>
+__global__ void __launch_bounds__(kMlpThreads, 2)
+sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns_b, const float *__restrict__ xyz,
+                     const float *__restrict__ new_xyz, const float *__restrict__ features,
+                     const float *__restrict__ Wa1, const float *__restrict__ ba1, const float *__restrict__ Wa2,
+                     const float *__restrict__ ba2, const float *__restrict__ Wa3, const float *__restrict__ ba3,
+                     const float *__restrict__ Wb1, const float *__restrict__ bb1, const float *__restrict__ Wb2,
+                     const float *__restrict__ bb2, const float *__restrict__ Wb3, const float *__restrict__ bb3,
+                     float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);
+    float *sWa1 = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);
+    float *sWa2 = sWa1 + A1 * C0P, *sWa3 = sWa2 + A2 * A1;
+    float *sWb1 = sWa3 + A3 * A2, *sWb2 = sWb1 + B1 * C0P, *sWb3 = sWb2 + B2 * B1;
+    float *sba1 = sWb3 + B3 * B2, *sba2 = sba1 + A1, *sba3 = sba2 + A2;
+    float *sbb1 = sba3 + A3, *sbb2 = sbb1 + B1, *sbb3 = sbb2 + B2;
+    float *sctr = sbb3 + B3;                                          // 3 x kThreads
+    float *sout = sctr + 3 * kThreads;                                // (A3 + B3) x kStride
+    int *sidx_a = reinterpret_cast<int *>(sout + (A3 + B3) * kStride);  // ns_a x kStride
+    int *sidx_b = sidx_a + ns_a * kStride;                              // ns_b x kStride
+
+    const int scene = blockIdx.y;
+    const int t = threadIdx.x;
+    const int j0 = blockIdx.x * kThreads;
+    const int j = j0 + t;
+    const bool active = t < kThreads && j < m;
+    const int c0 = 3 + c;
+    xyz += (size_t)scene * n * 3;
+    if (c > 0) features += (size_t)scene * c * n;
+
+    for (int i = t; i < A1 * C0P; i += kMlpThreads) sWa1[i] = (i % C0P) < c0 ? Wa1[(i / C0P) * c0 + i % C0P] : 0.f;
+    for (int i = t; i < B1 * C0P; i += kMlpThreads) sWb1[i] = (i % C0P) < c0 ? Wb1[(i / C0P) * c0 + i % C0P] : 0.f;
+    for (int i = t; i < A2 * A1; i += kMlpThreads) sWa2[i] = Wa2[i];
+    for (int i = t; i < A3 * A2; i += kMlpThreads) sWa3[i] = Wa3[i];
+    for (int i = t; i < B2 * B1; i += kMlpThreads) sWb2[i] = Wb2[i];
+    for (int i = t; i < B3 * B2; i += kMlpThreads) sWb3[i] = Wb3[i];
+    for (int i = t; i < A1; i += kMlpThreads) sba1[i] = ba1[i];
+    for (int i = t; i < A2; i += kMlpThreads) sba2[i] = ba2[i];
+    for (int i = t; i < A3; i += kMlpThreads) sba3[i] = ba3[i];
+    for (int i = t; i < B1; i += kMlpThreads) sbb1[i] = bb1[i];
+    for (int i = t; i < B2; i += kMlpThreads) sbb2[i] = bb2[i];
+    for (int i = t; i < B3; i += kMlpThreads) sbb3[i] = bb3[i];
+
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (active) {
+        const float *ctr = new_xyz + ((size_t)scene * m + j) * 3;
+        cx = ctr[0];
+        cy = ctr[1];
+        cz = ctr[2];
+    }
+    if (t < kThreads) {
+        sctr[t * 3 + 0] = cx;
+        sctr[t * 3 + 1] = cy;
+        sctr[t * 3 + 2] = cz;
+    }
+    pdab::ball_scan2_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2a, ns_a, r2b, ns_b, tile, sidx_a, sidx_b);
+
+    const int nctr = min(kThreads, m - j0);
+    mlp_phase<C0P, A1, A2, A3>(c, n, ns_a, nctr, xyz, features, sWa1, sba1, sWa2, sba2, sWa3, sba3, sctr, sidx_a, sout);
+    mlp_phase<C0P, B1, B2, B3>(c, n, ns_b, nctr, xyz, features, sWb1, sbb1, sWb2, sbb2, sWb3, sbb3, sctr, sidx_b,
+                               sout + A3 * kStride);
+    __syncthreads();
+    for (int i = t; i < (A3 + B3) * nctr; i += kMlpThreads) {
+        const int r = i / nctr, jl = i - r * nctr;
+        __stcs(out + ((size_t)scene * (A3 + B3) + r) * m + j0 + jl, sout[r * kStride + jl]);
+    }
+}
+
+template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3>
+int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns_b, const float *xyz,
+                const float *new_xyz, const float *features, const float *const *W, const float *const *B, float *out,
+                cudaStream_t stream) {
+    const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
+                        sizeof(float) * (A1 * C0P + A2 * A1 + A3 * A2 + B1 * C0P + B2 * B1 + B3 * B2 + A1 + A2 + A3 + B1 +
+                                         B2 + B3 + 3 * kThreads + (A3 + B3) * kStride) +
+                        sizeof(int) * (size_t)(ns_a + ns_b) * kStride;
+    auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3>;
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(pdab::div_up(m, kThreads), b);
+    kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, ra * ra, ns_a, rb * rb, ns_b, xyz, new_xyz, features, W[0], B[0],
+                                              W[1], B[1], W[2], B[2], W[3], B[3], W[4], B[4], W[5], B[5], out);
     PDAB_LAUNCH_CHECK();
     return 0;
 }
@@ -191,5 +292,30 @@ extern "C" int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsamp
     PDAB_NARROW(8, 16, 16, 32)
     PDAB_NARROW(8, 32, 32, 64)
 #undef PDAB_NARROW
+    return PDAB_EUNSUPPORTED;
+}
+
+extern "C" int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b,
+                                  int nsample_b, const float *xyz, const float *new_xyz, const float *features,
+                                  const int *dims_a_host, const int *dims_b_host, const float *const *weights_host,
+                                  const float *const *biases_host, float *out, pdab_stream_t stream) {
+    if (b < 0 || c < 0 || n < 1 || m < 0 || nsample_a < 1 || nsample_b < 1 || !xyz || !new_xyz || !out || !dims_a_host ||
+        !dims_b_host || !weights_host || !biases_host || (c > 0 && !features))
+        return PDAB_EINVAL;
+    if (b == 0 || m == 0) return 0;
+    if (dims_a_host[0] != 3 + c || dims_b_host[0] != 3 + c) return PDAB_EINVAL;
+    if (nsample_a > 32 || nsample_b > 32 || b > 65535) return PDAB_EUNSUPPORTED;
+    for (int l = 0; l < 6; l++)
+        if (!weights_host[l] || !biases_host[l]) return PDAB_EINVAL;
+    cudaStream_t s = pdab::to_stream(stream);
+    const int d0 = dims_a_host[0];
+    const bool a_small = dims_a_host[1] == 16 && dims_a_host[2] == 16 && dims_a_host[3] == 32;
+    const bool b_large = dims_b_host[1] == 32 && dims_b_host[2] == 32 && dims_b_host[3] == 64;
+    if (a_small && b_large && d0 <= 4)
+        return launch_pair<4, 16, 16, 32, 32, 32, 64>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
+                                                      features, weights_host, biases_host, out, s);
+    if (a_small && b_large && d0 <= 8)
+        return launch_pair<8, 16, 16, 32, 32, 32, 64>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
+                                                      features, weights_host, biases_host, out, s);
     return PDAB_EUNSUPPORTED;
 }

@@ -256,6 +256,20 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         pooled = l3(h, EPI_RELU_MAXPOOL, nsample=ns)                        # (B*M, c3)
         return pooled.view(B, M, -1).permute(0, 2, 1)
 
+    def _pair(self, xyz, new_xyz, features):
+        """Both narrow scales in ONE kernel (one scan of the cloud for the two radii), already concatenated; None if the
+        layer is not a two-scale narrow layer in eval mode."""
+        if (self.training or torch.is_grad_enabled() or self.pool_method != "max_pool" or self.dilated_group
+                or not self.use_xyz or self.npoint_list is None or len(self.groupers) != 2
+                or not hasattr(self.ops, "sa_fused_pair")):
+            return None
+        dims = [[seq[3 * k].out_channels for k in range(len(seq) // 3)] for seq in self.mlps]
+        if not self.ops.sa_fused_pair_supported(self.mlps[0][0].in_channels, dims[0], self.nsamples[0], dims[1],
+                                                self.nsamples[1]):
+            return None
+        (wa, ba), (wb, bb) = self._folded_params(0), self._folded_params(1)
+        return self.ops.sa_fused_pair(self.radii, self.nsamples, xyz, new_xyz, features, wa + wb, ba + bb)
+
     def _scale(self, i, xyz, new_xyz, features, features_t=None):
         fused_ok = (
             not self.training and not torch.is_grad_enabled() and self.pool_method == "max_pool"
@@ -301,10 +315,12 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
                     and hasattr(self.ops, "sa_fused")
                     and any(self._wide_supported(i, features) for i in range(len(self.groupers)))):
                 features_t = features.transpose(1, 2).contiguous()
-            outs = [self._scale(i, xyz, new_xyz, features,
-                                features_t if features_t is not None and self._wide_supported(i, features) else None)
-                    for i in range(len(self.groupers))]
-            new_features = torch.cat(outs, dim=1)
+            new_features = self._pair(xyz, new_xyz, features)
+            if new_features is None:
+                outs = [self._scale(i, xyz, new_xyz, features,
+                                    features_t if features_t is not None and self._wide_supported(i, features) else None)
+                        for i in range(len(self.groupers))]
+                new_features = torch.cat(outs, dim=1)
             if self.aggregation_layer is not None:
                 new_features = self.aggregation_layer(new_features)
         else:

@@ -322,6 +322,37 @@ def sa_fused(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tens
     return out
 
 
+def sa_fused_pair_supported(c0: int, dims_a: Sequence[int], ns_a: int, dims_b: Sequence[int], ns_b: int) -> bool:
+    """Two-scale shapes the pair kernel covers (csrc/sa_fused.cu: one scan of the cloud for both radii)."""
+    return (c0 <= 8 and tuple(dims_a) == (16, 16, 32) and tuple(dims_b) == (32, 32, 64) and ns_a <= 32 and ns_b <= 32)
+
+
+def sa_fused_pair(radii, nsamples, xyz, new_xyz, features, weights, biases) -> torch.Tensor:
+    """Both scales of a plain SA layer in one kernel (forward only).  radii / nsamples: 2 entries; weights / biases:
+    6 BN-folded tensors (scale a's three layers, then scale b's).  Returns (B, cout_a + cout_b, M), the scales
+    concatenated along the channel axis."""
+    assert xyz.is_cuda and xyz.is_contiguous() and new_xyz.is_contiguous()
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = 0 if features is None else features.shape[1]
+    if features is not None:
+        assert features.is_contiguous()
+    dims_a = [3 + C] + [int(w.shape[0]) for w in weights[:3]]
+    dims_b = [3 + C] + [int(w.shape[0]) for w in weights[3:]]
+    for w, bvec in zip(weights, biases):
+        assert w.is_cuda and w.is_contiguous() and w.dtype == torch.float32
+        assert bvec.is_cuda and bvec.is_contiguous() and bvec.dtype == torch.float32
+    out = torch.empty(B, dims_a[-1] + dims_b[-1], M, dtype=torch.float32, device=xyz.device)
+    da, db = (ctypes.c_int * 4)(*dims_a), (ctypes.c_int * 4)(*dims_b)
+    w_a = (ctypes.c_void_p * 6)(*[w.data_ptr() for w in weights])
+    b_a = (ctypes.c_void_p * 6)(*[x.data_ptr() for x in biases])
+    with torch.cuda.device(xyz.device):
+        _lib.call("pdab_sa_fused_pair", B, C, N, M, float(radii[0]), int(nsamples[0]), float(radii[1]), int(nsamples[1]),
+                  xyz.data_ptr(), new_xyz.data_ptr(), features.data_ptr() if features is not None else None, da, db,
+                  w_a, b_a, out.data_ptr(), torch.cuda.current_stream(xyz.device).cuda_stream)
+    return out
+
+
 # --------------------------------------------------------------------------- grouper modules
 
 class QueryAndGroup(nn.Module):

@@ -370,3 +370,30 @@ def test_nms_equals_committed_reference_golden(nms_utils):
         assert got.cpu().tolist() == z[f"keep_{tag}"].tolist(), tag
         iou = nms_utils.boxes_iou_bev(boxes, boxes).cpu()
         assert torch.equal(iou, torch.from_numpy(z[f"iou_{tag}"])), tag
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(16384, 4096), (1000, 300), (2048, 129)])
+def test_sa_fused_pair_equals_two_single_scale_kernels(n, m):
+    """One scan for both radii (pdab_sa_fused_pair) == two pdab_sa_fused launches concatenated, bit for bit:
+    same hit lists (index order, per-radius nsample cut, first-hit fill, empty ball -> point 0), same MLP arithmetic."""
+    import math
+    from pdanet_b200 import pointnet2_utils as ops
+    from util import scene_xyz
+    dev = torch.device("cuda:0")
+    B = 2
+    xyz = scene_xyz(7, B, n, duplicate_frac=0.05).to(dev)
+    ctr = xyz[:, :m].contiguous() + 0.01
+    ctr[:, 0] = 1000.0          # a centre with two empty balls
+    feats = torch.rand(B, 1, n, device=dev)
+    g = torch.Generator().manual_seed(3)
+    ws, bs = [], []
+    for dims in ([4, 16, 16, 32], [4, 32, 32, 64]):
+        for i in range(3):
+            ws.append((torch.randn(dims[i + 1], dims[i], generator=g) / math.sqrt(dims[i])).to(dev))
+            bs.append((torch.randn(dims[i + 1], generator=g) * 0.1).to(dev))
+    for radii, ns in (((0.2, 0.8), (16, 32)), ((2.5, 1.0), (5, 32))):
+        pair = ops.sa_fused_pair(radii, ns, xyz, ctr, feats, ws, bs)
+        a = ops.sa_fused(radii[0], ns[0], xyz, ctr, feats, ws[:3], bs[:3])
+        b = ops.sa_fused(radii[1], ns[1], xyz, ctr, feats, ws[3:], bs[3:])
+        assert torch.equal(pair, torch.cat([a, b], dim=1))
