@@ -147,7 +147,7 @@ def run_reference_arm(args, cfg, n_points, batch):
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -388,12 +388,25 @@ def run_gpu_arm(args, cfg, n_points, batch):
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "kernels": per_kernel[:12],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to fd 1 (NCCL prints its
+    version banner there) has been redirected to stderr by main()."""
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
+_OUT = sys.stdout
+
+
 def main():
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     from pdanet_b200.config import load_config
     cfg = load_config(args.config)
