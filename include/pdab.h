@@ -87,6 +87,32 @@ int pdab_group_points(int b, int c, int n, int npoints, int nsample, const float
 int pdab_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
                            float *grad_points, pdab_stream_t stream);
 
+/* Three nearest neighbours of every `unknown` point among the `known` points of its scene.
+ * replaces: three_nn_wrapper, PB/src/pointnet2_api.cpp:27, PB/src/interpolate_gpu.cu:16-78.
+ * unknown (B,N,3), known (B,M,3) -> dist2 (B,N,3) squared distances ascending, idx (B,N,3); ties keep the lowest index;
+ * with fewer than three candidates the missing entries are (+inf, 0) as in the reference. */
+int pdab_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                  pdab_stream_t stream);
+/* out[b,c,i] = sum_k weight[b,i,k] * points[b,c,idx[b,i,k]].
+ * replaces: three_interpolate_wrapper, PB/src/pointnet2_api.cpp:28, PB/src/interpolate_gpu.cu:84-120.
+ * points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N). */
+int pdab_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                           float *out, pdab_stream_t stream);
+/* grad_points[b,c,idx[b,i,k]] += grad_out[b,c,i] * weight[b,i,k]   (grad_points pre-zeroed by the caller).
+ * replaces: three_interpolate_grad_wrapper, PB/src/pointnet2_api.cpp:29, PB/src/interpolate_gpu.cu:127-166. */
+int pdab_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                                float *grad_points, pdab_stream_t stream);
+
+/* ---- roiaware_pool3d_cuda (training-side target assignment of PDA-SSD) ----------- */
+
+/* box_idx_of_points[b,i] = lowest k with point i of scene b inside box k (rotated box, 1e-5 margin in x/y), untouched
+ * otherwise (the caller pre-fills -1, pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py:38).
+ * replaces: points_in_boxes_gpu, pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp (pybind name),
+ *           kernel roiaware_pool3d_kernel.cu:313-359.
+ * boxes (B,T,7) [x,y,z,dx,dy,dz,heading], pts (B,M,3). */
+int pdab_points_in_boxes(int batch_size, int boxes_num, int pts_num, const float *boxes, const float *pts,
+                         int *box_idx_of_points, pdab_stream_t stream);
+
 /* ---- fused ops (additive; no reference native unit, they replace Python glue) ---- */
 
 /* Class-aware ("ctr_aware") sampling: idx[b,:] = indices of the npoint largest

@@ -138,6 +138,44 @@ def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans):
     return 1
 
 
+def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
+    lib().orc_three_nn(C.c_int(b), C.c_int(n), C.c_int(m), _f(unknown), _f(known), _f(dist2), _i(idx))
+
+
+def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):
+    lib().orc_three_interpolate(C.c_int(b), C.c_int(c), C.c_int(m), C.c_int(n), _f(points), _i(idx), _f(weight), _f(out))
+
+
+def three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_points):
+    lib().orc_three_interpolate_grad(C.c_int(b), C.c_int(c), C.c_int(n), C.c_int(m), _f(grad_out), _i(idx), _f(weight),
+                                     _f(grad_points))
+
+
+def points_in_boxes(points: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+    """points (B,M,3), boxes (B,T,7) -> (B,M) int32, -1 = background (roiaware_pool3d_utils.py:28-41)."""
+    B, M, _ = points.shape
+    out = torch.full((B, M), -1, dtype=torch.int32)
+    lib().orc_points_in_boxes(C.c_int(B), C.c_int(boxes.shape[1]), C.c_int(M), _f(boxes.contiguous()),
+                              _f(points.contiguous()), _i(out))
+    return out
+
+
+def three_nn(unknown: torch.Tensor, known: torch.Tensor):
+    B, N, _ = unknown.shape
+    dist2 = torch.zeros(B, N, 3, dtype=torch.float32)
+    idx = torch.zeros(B, N, 3, dtype=torch.int32)
+    three_nn_wrapper(B, N, known.shape[1], unknown.contiguous(), known.contiguous(), dist2, idx)
+    return dist2, idx
+
+
+def three_interpolate(features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    B, c, m = features.shape
+    n = idx.shape[1]
+    out = torch.zeros(B, c, n, dtype=torch.float32)
+    three_interpolate_wrapper(B, c, m, n, features.contiguous(), idx.contiguous(), weight.contiguous(), out)
+    return out
+
+
 # ---------------------------------------------------------------- convenience (allocating) forms
 
 def fps(xyz: torch.Tensor, npoint: int) -> torch.Tensor:

@@ -4,7 +4,8 @@ Compiles, from the sources where they lie under /root/reference (never copied
 into this repo), for sm_100a:
 
   oracle/_ref/libpdanet_ref_pointnet2.so
-      PB/src/{sampling_gpu,ball_query_gpu,group_points_gpu}.cu verbatim
+      PB/src/{sampling_gpu,ball_query_gpu,group_points_gpu,interpolate_gpu}.cu and
+      pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu verbatim
       + oracle/ref_binding.cu (our C-ABI over the reference launchers; the
       reference's own .cpp wrappers need <THC/THC.h>, absent from torch 2.11).
   oracle/_ref/iou3d_nms_cuda.so
@@ -35,6 +36,7 @@ OUT = HERE / "_ref"
 REF = Path(os.environ.get("PDANET_REFERENCE", "/root/reference"))
 PB = REF / "pcdet/ops/pointnet2/pointnet2_batch/src"
 IOU = REF / "pcdet/ops/iou3d_nms/src"
+ROI = REF / "pcdet/ops/roiaware_pool3d/src"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -83,8 +85,9 @@ def build(force: bool = False) -> bool:
            "-DTORCH_EXTENSION_NAME=iou3d_nms_cuda", *incs, "-I/usr/local/cuda/include"]
 
     jobs = []
-    for name in ("sampling_gpu", "ball_query_gpu", "group_points_gpu"):
+    for name in ("sampling_gpu", "ball_query_gpu", "group_points_gpu", "interpolate_gpu"):
         jobs.append([*nv, f"-I{PB}", "-c", PB / f"{name}.cu", "-o", obj / f"pb_{name}.o"])
+    jobs.append([*nv, "-c", ROI / "roiaware_pool3d_kernel.cu", "-o", obj / "roi_kernel.o"])
     jobs.append([*nv, "-c", HERE / "ref_binding.cu", "-o", obj / "ref_binding.o"])
     jobs.append([*nv, "-DTORCH_EXTENSION_NAME=iou3d_nms_cuda", f"-I{IOU}", "-c",
                  IOU / "iou3d_nms_kernel.cu", "-o", obj / "iou_kernel.o"])
@@ -95,7 +98,7 @@ def build(force: bool = False) -> bool:
 
     _run([NVCC, *ARCH, "-shared", "-o", lib_pn,
           obj / "pb_sampling_gpu.o", obj / "pb_ball_query_gpu.o", obj / "pb_group_points_gpu.o",
-          obj / "ref_binding.o", "-lcudart"])
+          obj / "pb_interpolate_gpu.o", obj / "roi_kernel.o", obj / "ref_binding.o", "-lcudart"])
     ldirs = [f"-L{p}" for p in libdirs]
     rpaths = [f"-Wl,-rpath,{p}" for p in libdirs]
     _run(["g++", "-shared", "-o", lib_iou,

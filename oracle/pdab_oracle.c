@@ -473,3 +473,97 @@ void orc_sa_mlp_maxpool(int b, int c, int n, int m, int ns, const float *xyz, co
     free(a0);
     free(a1);
 }
+
+/* -------------------------------------------------------------- feature propagation */
+
+/* PB/src/interpolate_gpu.cu:16-59.  Three nearest `known` points of every `unknown` point: scan k ascending, strict '<'
+ * insertion (lowest index wins ties); the reference keeps the bests as doubles starting at 1e40 and compares the fp32
+ * distance against them, so an infinite / NaN distance never enters and missing entries read (float)1e40 = +inf, idx 0.
+ * Distance in the compiled op order (SASS of the rebuilt reference): rn(dy*dy), fma(dx,dx,.), fma(dz,dz,.). */
+void orc_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx) {
+    for (int bi = 0; bi < b; bi++)
+        for (int i = 0; i < n; i++) {
+            const float *u = unknown + ((size_t)bi * n + i) * 3;
+            const float *K = known + (size_t)bi * m * 3;
+            double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+            int i1 = 0, i2 = 0, i3 = 0;
+            for (int k = 0; k < m; k++) {
+                const float d = sqdist3(u[0], u[1], u[2], K[k * 3], K[k * 3 + 1], K[k * 3 + 2]);
+                if (d < best1) {
+                    best3 = best2; i3 = i2;
+                    best2 = best1; i2 = i1;
+                    best1 = d; i1 = k;
+                } else if (d < best2) {
+                    best3 = best2; i3 = i2;
+                    best2 = d; i2 = k;
+                } else if (d < best3) {
+                    best3 = d; i3 = k;
+                }
+            }
+            float *o = dist2 + ((size_t)bi * n + i) * 3;
+            int *oi = idx + ((size_t)bi * n + i) * 3;
+            o[0] = (float)best1; o[1] = (float)best2; o[2] = (float)best3;
+            oi[0] = i1; oi[1] = i2; oi[2] = i3;
+        }
+}
+
+/* PB/src/interpolate_gpu.cu:84-101: out = w0*p0 + w1*p1 + w2*p2, contracted by nvcc as
+ * fma(w2, p2, fma(w0, p0, rn(w1*p1))) (SASS of the rebuilt reference). */
+void orc_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                           float *out) {
+    for (int bi = 0; bi < b; bi++)
+        for (int ci = 0; ci < c; ci++) {
+            const float *p = points + ((size_t)bi * c + ci) * m;
+            for (int i = 0; i < n; i++) {
+                const int *id = idx + ((size_t)bi * n + i) * 3;
+                const float *w = weight + ((size_t)bi * n + i) * 3;
+                float t = w[1] * p[id[1]];
+                t = fmaf(w[0], p[id[0]], t);
+                t = fmaf(w[2], p[id[2]], t);
+                out[((size_t)bi * c + ci) * n + i] = t;
+            }
+        }
+}
+
+/* PB/src/interpolate_gpu.cu:127-147 (the reference scatters with float atomics; summed here in index order). */
+void orc_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                                float *grad_points) {
+    for (int bi = 0; bi < b; bi++)
+        for (int ci = 0; ci < c; ci++) {
+            float *gp = grad_points + ((size_t)bi * c + ci) * m;
+            for (int i = 0; i < n; i++) {
+                const int *id = idx + ((size_t)bi * n + i) * 3;
+                const float *w = weight + ((size_t)bi * n + i) * 3;
+                const float g = grad_out[((size_t)bi * c + ci) * n + i];
+                for (int k = 0; k < 3; k++) gp[id[k]] += g * w[k];
+            }
+        }
+}
+
+/* -------------------------------------------------------------- points in boxes */
+
+/* pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:16-38,313-338.  First box (lowest k) containing the point;
+ * out must be pre-filled with -1 by the caller (roiaware_pool3d_utils.py:38).  Arithmetic as compiled for sm_100a:
+ * local_x = fma(sx, cosa, -rn(sy*sina)), local_y = fma(sy, cosa, rn(sx*sina)) with cosa = cosf(-rz), sina = sinf(-rz);
+ * the three extent tests run in double.  (libm cosf/sinf may differ from libdevice in the last ulp: a point within
+ * ~1e-7 of a face can flip; the GPU kernel is pinned against the reference kernel itself in tests/test_gpu_ops.py.) */
+void orc_points_in_boxes(int batch, int nboxes, int npts, const float *boxes, const float *pts, int *out) {
+    for (int bi = 0; bi < batch; bi++)
+        for (int i = 0; i < npts; i++) {
+            const float *p = pts + ((size_t)bi * npts + i) * 3;
+            for (int k = 0; k < nboxes; k++) {
+                const float *bx = boxes + ((size_t)bi * nboxes + k) * 7;
+                if ((double)fabsf(p[2] - bx[2]) > (double)bx[5] / 2.0) continue;
+                const float sx = p[0] - bx[0], sy = p[1] - bx[1];
+                const float cosa = cosf(-bx[6]), sina = sinf(-bx[6]);
+                const float lx = fmaf(sx, cosa, -(sy * sina));
+                const float ly = fmaf(sy, cosa, sx * sina);
+                const float margin = 1e-5f;
+                if ((double)fabsf(lx) < (double)bx[3] / 2.0 + (double)margin &&
+                    (double)fabsf(ly) < (double)bx[4] / 2.0 + (double)margin) {
+                    out[(size_t)bi * npts + i] = k;
+                    break;
+                }
+            }
+        }
+}

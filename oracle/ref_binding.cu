@@ -28,6 +28,12 @@ void ball_query_dilated_kernel_launcher_fast(int b, int n, int m, float max_radi
 void group_points_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out);
 void group_points_grad_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx, float *grad_points);
 
+// PB/src/interpolate_gpu.h:17-27, pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:341 (no header in the reference)
+void three_nn_kernel_launcher_fast(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx);
+void three_interpolate_kernel_launcher_fast(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out);
+void three_interpolate_grad_kernel_launcher_fast(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points);
+void points_in_boxes_launcher(int batch_size, int boxes_num, int pts_num, const float *boxes, const float *pts, int *box_idx_of_points);
+
 static int done() {
     cudaError_t e = cudaDeviceSynchronize();
     return e == cudaSuccess ? 0 : (int)e;
@@ -74,6 +80,28 @@ int ref_group(int b, int c, int n, int np, int ns, const float *points, const in
 int ref_group_grad(int b, int c, int n, int np, int ns, const float *grad_out, const int *idx, float *grad_points) {
     cudaDeviceSynchronize();
     group_points_grad_kernel_launcher_fast(b, c, n, np, ns, grad_out, idx, grad_points);
+    return done();
+}
+
+int ref_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx) {
+    cudaDeviceSynchronize();
+    three_nn_kernel_launcher_fast(b, n, m, unknown, known, dist2, idx);
+    return done();
+}
+int ref_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out) {
+    cudaDeviceSynchronize();
+    three_interpolate_kernel_launcher_fast(b, c, m, n, points, idx, weight, out);
+    return done();
+}
+int ref_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                               float *grad_points) {
+    cudaDeviceSynchronize();
+    three_interpolate_grad_kernel_launcher_fast(b, c, n, m, grad_out, idx, weight, grad_points);
+    return done();
+}
+int ref_points_in_boxes(int batch, int nboxes, int npts, const float *boxes, const float *pts, int *out) {
+    cudaDeviceSynchronize();
+    points_in_boxes_launcher(batch, nboxes, npts, boxes, pts, out);
     return done();
 }
 

@@ -28,6 +28,10 @@ _SIGNATURES = {
     "pdab_ball_query_dilated": (_i, [_i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "pdab_group_points": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pdab_group_points_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_three_nn": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_three_interpolate": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_three_interpolate_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_points_in_boxes": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "pdab_topk_ctr": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_pda_group": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_pda_group_tokens": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -10,9 +10,8 @@ torch CUDA stream.  Differences from the reference, all deliberate:
     fprintf + exit(-1) (PB/src/ball_query.cpp:17-29);
   * launches go to torch's current stream with a device guard, not to the
     legacy default stream of whatever device happens to be current.
-Functions of the reference module that PDA-SSD never reaches (three_nn,
-three_interpolate, ellipsoid_query, chamfer) are not provided and raise
-NotImplementedError naming SURVEY.md section 8(f).
+Functions of the reference module that PDA-SSD never reaches (ellipsoid_query,
+chamfer) are not provided and raise NotImplementedError naming SURVEY.md section 8(f).
 """
 from __future__ import annotations
 
@@ -136,9 +135,36 @@ def _out_of_scope(name):
     return fn
 
 
-three_nn_wrapper = _out_of_scope("three_nn_wrapper")
-three_interpolate_wrapper = _out_of_scope("three_interpolate_wrapper")
-three_interpolate_grad_wrapper = _out_of_scope("three_interpolate_grad_wrapper")
+def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
+    """PB/src/interpolate.cpp:21-33."""
+    pu = _chk(unknown_tensor, "unknown", torch.float32, (b, n, 3))
+    pk = _chk(known_tensor, "known", torch.float32, (b, m, 3))
+    pd = _chk(dist2_tensor, "dist2", torch.float32, (b, n, 3))
+    pi = _chk(idx_tensor, "idx", torch.int32, (b, n, 3))
+    with _same_device(unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
+        _lib.call("pdab_three_nn", b, n, m, pu, pk, pd, pi, _stream(unknown_tensor))
+
+
+def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tensor, out_tensor):
+    """PB/src/interpolate.cpp:36-47."""
+    pp = _chk(points_tensor, "points", torch.float32, (b, c, m))
+    pi = _chk(idx_tensor, "idx", torch.int32, (b, n, 3))
+    pw = _chk(weight_tensor, "weight", torch.float32, (b, n, 3))
+    po = _chk(out_tensor, "out", torch.float32, (b, c, n))
+    with _same_device(points_tensor, idx_tensor, weight_tensor, out_tensor):
+        _lib.call("pdab_three_interpolate", b, c, m, n, pp, pi, pw, po, _stream(points_tensor))
+
+
+def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
+    """PB/src/interpolate.cpp:50-61."""
+    pg = _chk(grad_out_tensor, "grad_out", torch.float32, (b, c, n))
+    pi = _chk(idx_tensor, "idx", torch.int32, (b, n, 3))
+    pw = _chk(weight_tensor, "weight", torch.float32, (b, n, 3))
+    po = _chk(grad_points_tensor, "grad_points", torch.float32, (b, c, m))
+    with _same_device(grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
+        _lib.call("pdab_three_interpolate_grad", b, c, n, m, pg, pi, pw, po, _stream(grad_out_tensor))
+
+
 ellipsoid_query = _out_of_scope("ellipsoid_query")
 chamfer_forward = _out_of_scope("chamfer_forward")
 chamfer_backward = _out_of_scope("chamfer_backward")

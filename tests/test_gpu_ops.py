@@ -397,3 +397,86 @@ def test_sa_fused_pair_equals_two_single_scale_kernels(n, m):
         a = ops.sa_fused(radii[0], ns[0], xyz, ctr, feats, ws[:3], bs[:3])
         b = ops.sa_fused(radii[1], ns[1], xyz, ctr, feats, ws[3:], bs[3:])
         assert torch.equal(pair, torch.cat([a, b], dim=1))
+
+
+# ------------------------------------------------------------------ feature propagation, points in boxes
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,M", [(2, 4096, 1024), (1, 1000, 257), (2, 300, 2), (1, 64, 1)])
+def test_three_nn_and_interpolate_bit_exact(B, N, M, request):
+    """three_nn / three_interpolate (+grad) against the CPU oracle, and against the reference's own kernels when
+    oracle/_ref is present: indices, squared distances and interpolated features bit for bit (duplicates -> ties)."""
+    from conftest import load_ref_pointnet2
+    from pdanet_b200 import pointnet2_batch_cuda as shim, pointnet2_utils as ops
+    g = torch.Generator().manual_seed(B * 1000 + N + M)
+    known = scene_xyz(5, B, max(M, 3), duplicate_frac=0.1)[:, :M].contiguous()
+    unknown = scene_xyz(6, B, N, quantize=0.5)
+    want_d2, want_idx = oracle.three_nn(unknown, known)
+    d2 = torch.zeros(B, N, 3, device="cuda")
+    idx = torch.zeros(B, N, 3, dtype=torch.int32, device="cuda")
+    shim.three_nn_wrapper(B, N, M, dev(unknown), dev(known), d2, idx)
+    assert torch.equal(idx.cpu(), want_idx)
+    assert torch.equal(d2.cpu(), want_d2)
+    C_ = 19
+    feats = torch.randn(B, C_, M, generator=g)
+    w = torch.rand(B, N, 3, generator=g)
+    w = w / w.sum(dim=2, keepdim=True)
+    want = oracle.three_interpolate(feats, want_idx, w)
+    f = dev(feats).requires_grad_(True)
+    got = ops.three_interpolate(f, idx, dev(w))
+    assert torch.equal(got.detach().cpu(), want)
+    # gradient: scatter-add of grad_out * weight (float atomics: order differs -> tolerance)
+    go = torch.randn(B, C_, N, generator=g)
+    got.backward(dev(go))
+    ref_grad = torch.zeros(B, C_, M, dtype=torch.float64)
+    for k in range(3):
+        ref_grad.scatter_add_(2, want_idx[:, :, k].long().unsqueeze(1).expand(B, C_, N), (go * w[:, :, k].unsqueeze(1)).double())
+    assert torch.allclose(f.grad.cpu().double(), ref_grad, rtol=1e-4, atol=1e-4)
+    ref = load_ref_pointnet2()
+    if ref is not None:
+        rd2 = torch.zeros(B, N, 3, device="cuda")
+        ridx = torch.zeros(B, N, 3, dtype=torch.int32, device="cuda")
+        u, k = dev(unknown), dev(known)
+        assert ref.ref_three_nn(B, N, M, _vp(u), _vp(k), _vp(rd2), _vp(ridx)) == 0
+        assert torch.equal(ridx, idx) and torch.equal(rd2, d2)
+        rout = torch.zeros(B, C_, N, device="cuda")
+        fw, ww = dev(feats), dev(w)
+        assert ref.ref_three_interpolate(B, C_, M, N, _vp(fw), _vp(ridx), _vp(ww), _vp(rout)) == 0
+        assert torch.equal(rout, got.detach())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,M", [(2, 37, 20000), (1, 600, 5000), (3, 1, 100)])
+def test_points_in_boxes_bit_exact(B, T, M):
+    """points_in_boxes_gpu against the reference kernel (when built) and the CPU oracle: first containing box, -1 outside;
+    points are drawn inside / on the faces / outside of the boxes."""
+    from conftest import load_ref_pointnet2
+    from pdanet_b200.roiaware_pool3d_utils import points_in_boxes_gpu
+    g = torch.Generator().manual_seed(T + M)
+    boxes = torch.stack([random_boxes(100 + b, T, extent=(30.0, 30.0, 2.0)) for b in range(B)])
+    pts = torch.rand(B, M, 3, generator=g) * torch.tensor([30.0, 30.0, 2.0])
+    # a third of the points: box-local coordinates in [-0.55, 0.55] x extents (inside, near faces, just outside)
+    k = torch.randint(0, T, (B, M // 3), generator=g)
+    bsel = torch.gather(boxes, 1, k.unsqueeze(-1).expand(B, M // 3, 7))
+    loc = (torch.rand(B, M // 3, 3, generator=g) - 0.5) * 1.1 * bsel[..., 3:6]
+    loc[:, ::7] = torch.sign(loc[:, ::7]) * 0.5 * bsel[:, ::7, 3:6]           # exactly on a face (before rotation)
+    ca, sa = torch.cos(bsel[..., 6]), torch.sin(bsel[..., 6])
+    pts[:, :M // 3, 0] = bsel[..., 0] + loc[..., 0] * ca - loc[..., 1] * sa
+    pts[:, :M // 3, 1] = bsel[..., 1] + loc[..., 0] * sa + loc[..., 1] * ca
+    pts[:, :M // 3, 2] = bsel[..., 2] + loc[..., 2]
+    got = points_in_boxes_gpu(dev(pts), dev(boxes)).cpu()
+    assert got.dtype == torch.int32 and got.shape == (B, M)
+    assert (got >= 0).float().mean() > 0.1 and (got < 0).float().mean() > 0.1
+    ref = load_ref_pointnet2()
+    if ref is not None:
+        want = torch.full((B, M), -1, dtype=torch.int32, device="cuda")
+        bb, pp = dev(boxes), dev(pts)
+        assert ref.ref_points_in_boxes(B, T, M, _vp(bb), _vp(pp), _vp(want)) == 0
+        assert torch.equal(got, want.cpu())
+    cpu = oracle.points_in_boxes(pts, boxes)
+    # libm vs libdevice cosf/sinf may differ in the last ulp: points within ~1e-6 of a face may flip
+    assert (got != cpu).float().mean() < 1e-3

@@ -236,3 +236,26 @@ def test_oracle_nms_vs_reference_cuda_nms_golden():
             keep = torch.zeros(boxes.shape[0], dtype=torch.int64)
             num = oracle.nms_gpu(boxes, keep, thresh)
             assert keep[:num].tolist() == z[f"keep_{tag}"].tolist(), tag
+
+
+def test_three_nn_interpolate_and_points_in_boxes_oracle():
+    """Oracle restatements of the §8f-3/4 ops against straightforward float64 numpy/torch statements."""
+    g = torch.Generator().manual_seed(0)
+    unknown, known = torch.rand(2, 200, 3, generator=g) * 10, torch.rand(2, 50, 3, generator=g) * 10
+    d2, idx = oracle.three_nn(unknown, known)
+    full = torch.cdist(unknown.double(), known.double()) ** 2
+    want_d, want_i = full.topk(3, dim=2, largest=False)
+    assert torch.equal(idx.long(), want_i)                       # random clouds: no ties
+    assert torch.allclose(d2.double(), want_d, rtol=1e-5, atol=1e-6)
+    feats = torch.randn(2, 7, 50, generator=g)
+    w = torch.rand(2, 200, 3, generator=g)
+    out = oracle.three_interpolate(feats, idx, w)
+    gathered = torch.stack([torch.gather(feats, 2, idx[:, :, k].long().unsqueeze(1).expand(2, 7, 200)) for k in range(3)], -1)
+    assert torch.allclose(out.double(), (gathered.double() * w.unsqueeze(1).double()).sum(-1), rtol=1e-5, atol=1e-6)
+    # fewer than three candidates -> (+inf, 0) padding, as (float)1e40 in the reference
+    d2, idx = oracle.three_nn(unknown[:, :5], known[:, :2])
+    assert torch.isinf(d2[..., 2]).all() and (idx[..., 2] == 0).all()
+    # points in boxes: axis-aligned and rotated box, first match wins
+    boxes = torch.tensor([[[0.0, 0.0, 0.0, 4.0, 2.0, 2.0, 0.0], [0.0, 0.0, 0.0, 4.0, 2.0, 2.0, 1.5707964]]])
+    pts = torch.tensor([[[1.9, 0.9, 0.9], [0.5, 1.9, 0.0], [3.0, 0.0, 0.0], [0.0, 0.0, 1.1]]])
+    assert oracle.points_in_boxes(pts, boxes)[0].tolist() == [0, 1, -1, -1]
