@@ -41,31 +41,48 @@ ball_query_kernel(int n, int m, float r2_hi, float r2_lo, int nsample, const flo
     for (int base = 0; base < n; base += kTile) {
         const int len = min(kTile, n - base);
         __syncthreads();  // previous tile fully consumed
-        for (int i = threadIdx.x; i < len; i += kThreads) {
-            const float *p = xyz + (size_t)(base + i) * 3;
-            tile[i] = make_float4(p[0], p[1], p[2], 0.f);
+        const int len8 = (len + 7) & ~7;
+        for (int i = threadIdx.x; i < len8; i += kThreads) {
+            if (i < len) {
+                const float *p = xyz + (size_t)(base + i) * 3;
+                tile[i] = make_float4(p[0], p[1], p[2], 0.f);
+            } else {
+                tile[i] = make_float4(1e30f, 1e30f, 1e30f, 0.f);  // padding: distance overflows to +inf, never a hit
+            }
         }
         __syncthreads();
         if (!__all_sync(0xffffffffu, cnt >= nsample)) {
-#pragma unroll 4
-            for (int i = 0; i < len; i++) {
-                const float4 p = tile[i];
-                const float d2 = pdab::sqdist3(cx, cy, cz, p.x, p.y, p.z);
-                if (DILATED) {
-                    // PB/src/ball_query_gpu.cu:92-111: two independent tests; a point
-                    // can be emitted by both.
-                    if (d2 == 0.f && cnt < nsample) {
-                        if (cnt == 0) first = base + i;
-                        row[cnt++] = base + i;
-                    }
-                    if (d2 >= r2_lo && d2 < r2_hi && cnt < nsample) {
-                        if (cnt == 0) first = base + i;
-                        row[cnt++] = base + i;
-                    }
-                } else {
-                    if (d2 < r2_hi && cnt < nsample) {
-                        if (cnt == 0) first = base + i;
-                        row[cnt++] = base + i;
+            // eight independent distance tests in flight, one branch for the (rare) hit
+            for (int i0 = 0; i0 < len8; i0 += 8) {
+                float d2v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float4 p = tile[i0 + u];
+                    d2v[u] = pdab::sqdist3(cx, cy, cz, p.x, p.y, p.z);
+                }
+                const float mn = fminf(fminf(fminf(d2v[0], d2v[1]), fminf(d2v[2], d2v[3])),
+                                       fminf(fminf(d2v[4], d2v[5]), fminf(d2v[6], d2v[7])));
+                if ((DILATED ? !(mn <= r2_hi) : !(mn < r2_hi)) || cnt >= nsample) continue;  // dilated also emits d2 == 0
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float d2 = d2v[u];
+                    const int i = i0 + u;
+                    if (DILATED) {
+                        // PB/src/ball_query_gpu.cu:92-111: two independent tests; a point
+                        // can be emitted by both.
+                        if (d2 == 0.f && cnt < nsample) {
+                            if (cnt == 0) first = base + i;
+                            row[cnt++] = base + i;
+                        }
+                        if (d2 >= r2_lo && d2 < r2_hi && cnt < nsample) {
+                            if (cnt == 0) first = base + i;
+                            row[cnt++] = base + i;
+                        }
+                    } else {
+                        if (d2 < r2_hi && cnt < nsample) {
+                            if (cnt == 0) first = base + i;
+                            row[cnt++] = base + i;
+                        }
                     }
                 }
             }

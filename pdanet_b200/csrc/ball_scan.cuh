@@ -7,7 +7,7 @@
 
 namespace pdab {
 
-constexpr int kScanTile = 1024;  // points per staging tile (float4, 16 KB)
+constexpr int kScanTile = 1024;  // points per staging tile (float4, 16 KB); callers allocate kScanTile + 8 (padding to 8)
 
 // All threads of the CTA must call this (it contains CTA barriers).
 //   THREADS : number of centres scanned by the CTA (threads 0..THREADS-1 own one each);
@@ -26,20 +26,36 @@ __device__ __forceinline__ void ball_scan_to_smem(int n, const float *__restrict
     int cnt = active ? 0 : nsample;
     for (int base = 0; base < n; base += kScanTile) {
         const int len = min(kScanTile, n - base);
+        const int len8 = (len + 7) & ~7;
         __syncthreads();
-        for (int i = t; i < len; i += nthreads) {
-            const float *p = xyz + (size_t)(base + i) * 3;
-            tile[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        for (int i = t; i < len8; i += nthreads) {
+            if (i < len) {
+                const float *p = xyz + (size_t)(base + i) * 3;
+                tile[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+            } else {
+                tile[i] = make_float4(1e30f, 1e30f, 1e30f, 0.f);  // padding: squared distance overflows to +inf, never a hit
+            }
         }
         __syncthreads();
         if (!__all_sync(0xffffffffu, cnt >= nsample)) {
-#pragma unroll 4
-            for (int i = 0; i < len; i++) {
-                const float4 p = tile[i];
-                const float d2 = sqdist3(cx, cy, cz, p.x, p.y, p.z);
-                if (d2 < r2 && cnt < nsample) {
-                    sidx[cnt * STRIDE + t] = base + i;
-                    cnt++;
+            // eight independent distance tests in flight, one branch for the (rare) hit
+            for (int i = 0; i < len8; i += 8) {
+                float d2[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float4 p = tile[i + u];
+                    d2[u] = sqdist3(cx, cy, cz, p.x, p.y, p.z);
+                }
+                const float mn = fminf(fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])),
+                                       fminf(fminf(d2[4], d2[5]), fminf(d2[6], d2[7])));
+                if (mn < r2 && cnt < nsample) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (d2[u] < r2 && cnt < nsample) {
+                            sidx[cnt * STRIDE + t] = base + i + u;
+                            cnt++;
+                        }
+                    }
                 }
             }
         }

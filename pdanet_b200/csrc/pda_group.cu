@@ -25,7 +25,7 @@ pda_group_kernel(int c, int n, int m, float radius, float r2, float two_r2, floa
                  const float *__restrict__ features, float *__restrict__ out, int *__restrict__ idx_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
-    float *sctr = reinterpret_cast<float *>(tile + pdab::kScanTile);  // 3 * kThreads
+    float *sctr = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);  // 3 * kThreads
     int *sidx = reinterpret_cast<int *>(sctr + 3 * kThreads);          // nsample * kStride
 
     const int scene = blockIdx.y;
@@ -114,7 +114,7 @@ pda_group_tokens_kernel(int c, int n, int m, int pitch, float radius, float r2, 
                         const float *__restrict__ features_t, float *__restrict__ out, int *__restrict__ idx_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
-    float *sctr = reinterpret_cast<float *>(tile + pdab::kScanTile);
+    float *sctr = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);
     int *sidx = reinterpret_cast<int *>(sctr + 3 * kThreads);
 
     const int scene = blockIdx.y;
@@ -197,7 +197,7 @@ extern "C" int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, i
     if (pitch < 8 + c || (pitch & 3) || (c & 3)) return PDAB_EINVAL;
     if (b == 0 || m == 0) return 0;
     if (nsample > 128 || b > 65535) return PDAB_EUNSUPPORTED;
-    const size_t smem = sizeof(float4) * pdab::kScanTile + sizeof(float) * 3 * kThreads +
+    const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) + sizeof(float) * 3 * kThreads +
                         sizeof(int) * (size_t)nsample * kStride;
     PDAB_CUDA(cudaFuncSetAttribute(pda_group_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const float two_r2 = (float)(2.0 * (double)radius * (double)radius);
@@ -216,7 +216,7 @@ extern "C" int pdab_pda_group(int b, int c, int n, int m, float radius, int nsam
         return PDAB_EINVAL;
     if (b == 0 || m == 0) return 0;
     if (nsample > 128 || b > 65535) return PDAB_EUNSUPPORTED;
-    const size_t smem = sizeof(float4) * pdab::kScanTile + sizeof(float) * 3 * kThreads +
+    const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) + sizeof(float) * 3 * kThreads +
                         sizeof(int) * (size_t)nsample * kStride;
     static int configured_smem = 0;
     if ((int)smem > configured_smem) {

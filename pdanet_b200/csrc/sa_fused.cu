@@ -111,7 +111,7 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
                        float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
-    float *sW1 = reinterpret_cast<float *>(tile + pdab::kScanTile);  // C1 x C0P
+    float *sW1 = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);  // C1 x C0P
     float *sW2 = sW1 + C1 * C0P;                                      // C2 x C1
     float *sW3 = sW2 + C2 * C1;                                       // C3 x C2
     float *sb1 = sW3 + C3 * C2;
@@ -167,7 +167,7 @@ template <int C0P, int C1, int C2, int C3>
 int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
                   const float *features, const float *const *W, const float *const *B, float *out,
                   cudaStream_t stream) {
-    const size_t smem = sizeof(float4) * pdab::kScanTile +
+    const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
                         sizeof(float) * (C1 * C0P + C2 * C1 + C3 * C2 + C1 + C2 + C3 + 3 * kThreads + C3 * kStride) +
                         sizeof(int) * (size_t)nsample * kStride;
     auto kern = sa_fused_narrow_kernel<C0P, C1, C2, C3>;
