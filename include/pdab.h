@@ -221,6 +221,10 @@ int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilo
  * scene FPS kernels of another batch.  Process-wide; 1 <= n <= 148. */
 int pdab_set_persistent_ctas(int n);
 
+/* 1 (default): the tensor-core kernels run as cta_group::2 CTA pairs (thread-block clusters of 2, M = 256) when the problem
+ * is large enough; 0: single CTAs only.  Same results either way (the pairing is a schedule, not arithmetic). */
+int pdab_set_cta_pairs(int on);
+
 /* Number of floats pdab_tc_pack_weights writes for a (nout, k) weight matrix. */
 size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn);
 /* Packs W (nout, k) row-major (device) into the shared-memory image the tensor-core kernels stream:

@@ -15,7 +15,13 @@
 //               in TF32 (top 19 bits), acc += x_hi w_lo + x_lo w_hi + x_hi w_hi.  The dropped x_lo w_lo term is
 //               O(2^-22) relative: fp32-level results (what nn.Linear computes in the reference) at 3 MMAs / k-step.
 //
-// Mapping to the SM.  One CTA per SM, persistent over (row tile, column group) work items; 14 warps:
+// Mapping to the SM.  One CTA per SM, persistent over (row tile, column group) work items.  Large problems run as
+// CTA PAIRS (cta_group::2, thread-block clusters of 2): one tcgen05.mma covers M = 256 rows across the two SMs, each SM
+// stages its own 128 rows of A and HALF of the weight tile, so per SM the tensor core reads 8 KB instead of 12 KB of
+// shared memory per MMA and half the weight bytes arrive from L2 — the kernel is shared-memory-bandwidth bound
+// (profiles/r01_ncu_tc_gemm_*).  The leader CTA issues the MMAs and multicasts its commits to both CTAs' barriers; the
+// peer's producers / epilogue arrive on the leader's barriers remotely (mapa + mbarrier.arrive.release.cluster).
+// Warps (single CTA: 14, pair: 12 per CTA):
 //   warp 0      W loader   : one lane issues cp.async.bulk (TMA engine, UBLKCP) of pre-packed weight tiles -> smem
 //   warp 1      MMA issuer : one lane issues tcgen05.mma (M=128, N=BN, K=8 per instruction), tcgen05.commit -> mbarriers
 //   warps 2-9   A producers: global -> registers -> (hi, lo) split -> 128B-swizzled K-major smem tiles
@@ -37,8 +43,6 @@ constexpr int BM = 128;            // rows per tile (TMEM lanes)
 constexpr int BK = 32;             // fp32 / tf32 elements per k-atom (128 B swizzle row); bf16 mode: 64 elements
 constexpr int A_TILE_BYTES = BM * 128;     // 16 KB: 128 rows x one 128-byte swizzle row
 __host__ __device__ constexpr int bk_of(int npass) { return npass == 2 ? 64 : 32; }
-constexpr int kProducerWarps = 8;
-constexpr int kThreads = 32 * (2 + kProducerWarps + 4);
 constexpr int kTmemCols = 512;
 constexpr int kStgPitch = 36;       // floats per row of an epilogue staging tile (32 + 4: 16-byte aligned, conflict-free)
 
@@ -106,6 +110,39 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz; a healthy wait is microseconds
     }
 }
+// acquire at cluster scope: for barriers that CTAs of the pair arrive on remotely
+__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        u32 ok;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(u32 bar, u32 cta) {
+    asm volatile(
+        "{\n.reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ u32 cluster_ctarank() {
+    u32 r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -117,36 +154,74 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u3
                  : "memory");
 }
 
+// CG = 1: one SM; CG = 2: CTA pair (both CTAs' allocating warps execute the instruction, same smem slot offset)
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(u32 dst_smem, u32 ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(u32 taddr, u32 ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if (CG == 2)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, issued by ONE thread.
+template <int CG>
 __device__ __forceinline__ void umma_tf32(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (CG == 2)
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 // Same with bf16 operands (kind::f16): K = 16 per instruction, twice the tf32 rate.
+template <int CG>
 __device__ __forceinline__ void umma_bf16(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (CG == 2)
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 // Arrive on an mbarrier when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync).
+// CG = 2: the arrival is multicast to the barrier at this offset in BOTH CTAs of the pair.
+template <int CG>
 __device__ __forceinline__ void umma_commit(u32 bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (CG == 2)
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+            "h"((unsigned short)3)
+            : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread `lane` of the warp gets columns [c, c+32) of TMEM lane (warp%4)*32+lane.
@@ -192,9 +267,9 @@ __device__ __forceinline__ u64 umma_desc(u32 smem_addr) {
 }
 // Instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128.
 // FMT: 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16).
-template <int BN, int FMT>
+template <int BN, int FMT, int CG>
 __device__ __forceinline__ constexpr u32 umma_idesc() {
-    return (1u << 4) | ((u32)FMT << 7) | ((u32)FMT << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+    return (1u << 4) | ((u32)FMT << 7) | ((u32)FMT << 10) | ((u32)(BN >> 3) << 17) | ((u32)((BM * CG) >> 4) << 24);
 }
 // 8 fp32 -> 8 bf16 (round to nearest even) packed in a uint4, and the bf16 of the remainders
 __device__ __forceinline__ void bf16_split8(const float4 &a, const float4 &b, uint4 &hi, uint4 &lo) {
@@ -221,16 +296,21 @@ __device__ __forceinline__ float tf32_rna(float v) {
 
 // ------------------------------------------------------------------------------------------- kernel
 
-template <int NPASS, int BN>
+// CG = 1: one CTA per SM, M = 128.  CG = 2: CTA pair (cta_group::2), M = 256: each CTA produces its own 128 rows of A and
+// holds HALF of the W tile (rows [rank * BN/2, +BN/2) of the chunk); the tensor cores of the pair read both halves, so
+// per SM the MMA reads 8 KB of shared memory instead of 12 KB and receives half the weight bytes from L2.
+template <int NPASS, int BN, int CG>
 struct Cfg {
-    static constexpr int W_TILE_BYTES = BN * 128;                          // one of {hi, lo}
+    static constexpr int W_TILE_BYTES = BN * 128 / CG;                     // one of {hi, lo}, per CTA
     static constexpr int STAGE_BYTES = (NPASS >= 2 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
     static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW >= 4 ? 4 : 2;
     // A-producer groups: group g owns k-atom steps g, g+G, ...  G must divide STAGES so that every smem stage belongs
     // to ONE group, which then sees every phase of that stage's `empty` barrier (a parity wait can only tell two
     // consecutive phases apart).
-    static constexpr int GROUPS = STAGES;
+    static constexpr int STAGES = CG == 2 ? (STAGES_RAW >= 6 ? 6 : 3) : (STAGES_RAW >= 4 ? 4 : 2);
+    static constexpr int GROUPS = CG == 2 ? 3 : STAGES;
+    static constexpr int PRODUCER_WARPS = CG == 2 ? 6 : 8;
+    static constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + 4);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                       4 * 32 * kStgPitch * 4 /*epilogue staging tiles*/ +
                                       4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/;
@@ -248,10 +328,17 @@ struct Pipe {
     }
 };
 
-template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p) {
-    using C = Cfg<NPASS, BN>;
+template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
+__global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel(const GemmParams p) {
+    using C = Cfg<NPASS, BN, CG>;
     constexpr int S = C::STAGES;
+    constexpr int kThreads = C::THREADS, kProducerWarps = C::PRODUCER_WARPS;
+    // CTA pair: rank 0 (leader) issues the MMAs for both SMs; work items are 256-row tiles, 128 rows per CTA
+    const u32 rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const long long item0 = CG == 2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const long long item_step = CG == 2 ? (gridDim.x >> 1) : gridDim.x;
+    auto row0_of = [&](long long item) { return (item / p.n_groups) * (long long)(BM * CG) + (long long)rank * BM; };
     constexpr int ACC_STAGES = (NCH * BN * 2 <= kTmemCols) ? 2 : 1;
     constexpr int ACC_COLS = kTmemCols / ACC_STAGES;  // column stride between accumulator stages
 
@@ -259,14 +346,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
     const u32 smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const u32 bar_base = smem_base + S * C::STAGE_BYTES;
-    // barriers (8 B each): full_w[S], full_a[S], empty[S], acc_full[2], acc_empty[2]; then the TMEM base address
+    // barriers (8 B each): full_w[S], full_a[S], empty[S], acc_full[2], acc_empty[2], peer_w[S]; then the TMEM base address.
+    // CTA pair: full_a / acc_empty / peer_w of the LEADER also receive the peer's arrivals (remote mbarrier.arrive);
+    // empty / acc_full are signalled in both CTAs by the leader's multicast tcgen05.commit.
     auto full_w = [&](int s) { return bar_base + 8u * s; };
     auto full_a = [&](int s) { return bar_base + 8u * (S + s); };
     auto empty = [&](int s) { return bar_base + 8u * (2 * S + s); };
     auto acc_full = [&](int a) { return bar_base + 8u * (3 * S + a); };
     auto acc_empty = [&](int a) { return bar_base + 8u * (3 * S + 2 + a); };
-    const u32 tmem_slot = bar_base + 8u * (3 * S + 4);
-    volatile u32 *tmem_slot_ptr = reinterpret_cast<volatile u32 *>(smem + S * C::STAGE_BYTES + 8 * (3 * S + 4));
+    auto peer_w = [&](int s) { return bar_base + 8u * (3 * S + 4 + s); };
+    const u32 tmem_slot = bar_base + 8u * (4 * S + 4);
+    volatile u32 *tmem_slot_ptr = reinterpret_cast<volatile u32 *>(smem + S * C::STAGE_BYTES + 8 * (4 * S + 4));
 
     auto a_hi = [&](int s) { return smem_base + (u32)s * C::STAGE_BYTES; };
     auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };                       // NPASS >= 2 only
@@ -278,16 +368,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(full_w(s), 1);
-            mbar_init(full_a(s), kProducerWarps / C::GROUPS);
+            mbar_init(full_a(s), CG * (kProducerWarps / C::GROUPS));
             mbar_init(empty(s), 1);
+            mbar_init(peer_w(s), 1);
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), 4);
+            mbar_init(acc_empty(a), 4 * CG);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (CG == 2) cluster_sync_all();  // both CTAs of the pair resident, barriers initialised before any remote arrive
+    if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
     if (EPI == E_ADD_LN) {  // LayerNorm scale / shift -> smem once (Nout = NCH * BN <= 512 columns)
         float *sg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + 4 * 512;
         for (int i = threadIdx.x; i < NCH * BN; i += kThreads) {
@@ -307,41 +399,66 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
         // ===================================================================== W loader
         if (lane == 0) {
             Pipe pipe;
-            constexpr u32 BYTES = (NPASS >= 2 ? 2 : 1) * C::W_TILE_BYTES;
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            constexpr int PARTS = NPASS >= 2 ? 2 : 1;
+            constexpr u32 BYTES = PARTS * C::W_TILE_BYTES;          // bytes this CTA receives per stage
+            constexpr size_t TILE = (size_t)PARTS * BN * 128;        // packed bytes of one (chunk, k-atom) tile
+            constexpr u32 PIECE = C::W_TILE_BYTES < 8192 ? C::W_TILE_BYTES : 8192;
+            for (long long item = item0; item < n_items; item += item_step) {
                 const int n_group = (int)(item % p.n_groups);
                 for (int c = 0; c < NCH; c++) {
                     const int chunk = n_group * NCH + c;
-                    const uint8_t *src = reinterpret_cast<const uint8_t *>(p.Wp) + (size_t)chunk * KA * BYTES;
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(p.Wp) + (size_t)chunk * KA * TILE;
                     for (int ka = 0; ka < KA; ka++) {
                         mbar_wait(empty(pipe.stage), pipe.phase ^ 1);
                         mbar_arrive_expect_tx(full_w(pipe.stage), BYTES);
-                        // several smaller bulk copies: more requests in flight per SM than one 64 KB copy
-                        constexpr u32 PIECE = 8192;
+                        // several smaller bulk copies: more requests in flight per SM than one big copy.  CTA pair:
+                        // this CTA takes rows [rank * BN/2, +BN/2) of the hi and of the lo image.
 #pragma unroll
-                        for (u32 o = 0; o < BYTES; o += PIECE)
-                            bulk_g2s(w_hi(pipe.stage) + o, src + (size_t)ka * BYTES + o, PIECE, full_w(pipe.stage));
+                        for (int part = 0; part < PARTS; part++) {
+                            const uint8_t *ps = src + (size_t)ka * TILE + (size_t)part * BN * 128 + (size_t)rank * C::W_TILE_BYTES;
+#pragma unroll
+                            for (u32 o = 0; o < C::W_TILE_BYTES; o += PIECE)
+                                bulk_g2s(w_hi(pipe.stage) + part * C::W_TILE_BYTES + o, ps + o, PIECE, full_w(pipe.stage));
+                        }
                         pipe.advance<S>();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================================== MMA issuer (leader) / W relay (peer)
+        if (CG == 2 && !leader) {
+            // the peer's weight half lands on the peer's own full_w barrier (a bulk copy signals a barrier of the CTA
+            // it writes to); one thread forwards each completion to the leader, in stage order
+            if (lane == 0) {
+                Pipe pipe;
+                for (long long item = item0; item < n_items; item += item_step)
+                    for (int st = 0; st < NCH * KA; st++) {
+                        mbar_wait(full_w(pipe.stage), pipe.phase);
+                        mbar_arrive_remote(peer_w(pipe.stage), 0);
+                        pipe.advance<S>();
+                    }
+            }
+        } else if (lane == 0) {
             Pipe pipe;
             int as = 0;
             u32 aphase = 0;
-            constexpr u32 idesc = umma_idesc<BN, NPASS == 2 ? 1 : 2>();
+            constexpr u32 idesc = umma_idesc<BN, NPASS == 2 ? 1 : 2, CG>();
             constexpr int BKE = bk_of(NPASS), KSTEP = NPASS == 2 ? 16 : 8;   // elements per k-atom / per MMA
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-                mbar_wait(acc_empty(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+            for (long long item = item0; item < n_items; item += item_step) {
+                if (CG == 2) mbar_wait_cluster(acc_empty(as), aphase ^ 1);
+                else mbar_wait(acc_empty(as), aphase ^ 1);  // epilogue has drained this accumulator stage
                 tc_fence_after();
                 for (int c = 0; c < NCH; c++) {
                     const u32 d = tmem_base + (u32)(as * ACC_COLS + c * BN);
                     for (int ka = 0; ka < KA; ka++) {
                         mbar_wait(full_w(pipe.stage), pipe.phase);
-                        mbar_wait(full_a(pipe.stage), pipe.phase);
+                        if (CG == 2) {
+                            mbar_wait_cluster(full_a(pipe.stage), pipe.phase);   // both CTAs' A tiles
+                            mbar_wait_cluster(peer_w(pipe.stage), pipe.phase);   // the peer's W half
+                        } else {
+                            mbar_wait(full_a(pipe.stage), pipe.phase);
+                        }
                         tc_fence_after();
                         // k-steps of 8 inside the atom; the last atom may be partially filled (zero padded)
                         const int ksteps = (ka == KA - 1) ? ((p.K - ka * BKE + KSTEP - 1) / KSTEP) : (BKE / KSTEP);
@@ -352,24 +469,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
                             if (NPASS == 3) {
                                 const u64 al = umma_desc(a_lo(pipe.stage) + kk * 32);
                                 const u64 wl = umma_desc(w_lo(pipe.stage) + kk * 32);
-                                umma_tf32(d, ah, wl, idesc, acc);   // small terms first
-                                umma_tf32(d, al, wh, idesc, 1u);
-                                umma_tf32(d, ah, wh, idesc, 1u);
+                                umma_tf32<CG>(d, ah, wl, idesc, acc);   // small terms first
+                                umma_tf32<CG>(d, al, wh, idesc, 1u);
+                                umma_tf32<CG>(d, ah, wh, idesc, 1u);
                             } else if (NPASS == 2) {
                                 const u64 al = umma_desc(a_lo(pipe.stage) + kk * 32);
                                 const u64 wl = umma_desc(w_lo(pipe.stage) + kk * 32);
-                                umma_bf16(d, ah, wl, idesc, acc);
-                                umma_bf16(d, al, wh, idesc, 1u);
-                                umma_bf16(d, ah, wh, idesc, 1u);
+                                umma_bf16<CG>(d, ah, wl, idesc, acc);
+                                umma_bf16<CG>(d, al, wh, idesc, 1u);
+                                umma_bf16<CG>(d, ah, wh, idesc, 1u);
                             } else {
-                                umma_tf32(d, ah, wh, idesc, acc);
+                                umma_tf32<CG>(d, ah, wh, idesc, acc);
                             }
                         }
-                        umma_commit(empty(pipe.stage));  // frees the smem stage once these MMAs have read it
+                        umma_commit<CG>(empty(pipe.stage));  // frees the smem stage (both CTAs) once these MMAs have read it
                         pipe.advance<S>();
                     }
                 }
-                umma_commit(acc_full(as));               // accumulator complete -> epilogue
+                umma_commit<CG>(acc_full(as));           // accumulator complete -> epilogue (both CTAs)
                 if (ACC_STAGES == 2) {
                     as ^= 1;
                     if (as == 0) aphase ^= 1;
@@ -400,15 +517,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
         int src_row[R];                       // A_GATHER: flat source point row (b*Nsrc + i) per owned row, -1 = padding
         long long meta_item = -1;
 
-        const long long my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const long long my_items = n_items > item0 ? (n_items - item0 + item_step - 1) / item_step : 0;
         const int steps_per_item = NCH * KA;
         const long long total = my_items * steps_per_item;
 
         for (long long step = g; step < total; step += G) {
             const long long li = step / steps_per_item;
             const int ka = (int)(step - li * steps_per_item) % KA;
-            const long long item = blockIdx.x + li * gridDim.x;
-            const long long m0 = (item / p.n_groups) * BM;
+            const long long item = item0 + li * item_step;
+            const long long m0 = row0_of(item);
             const int k = ka * BKE + chunk * 4 * V;       // first fp32 column this thread converts
             if (ALOAD == A_ROWS) {
 #pragma unroll
@@ -481,7 +598,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_a(stage));
+            if (lane == 0) {
+                if (CG == 2 && !leader) mbar_arrive_remote(full_a(stage), 0);  // the leader's MMA thread waits for both tiles
+                else mbar_arrive(full_a(stage));
+            }
         }
     } else {
         // ===================================================================== epilogue (128 threads)
@@ -580,8 +700,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
             }
         };
 
-        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const long long m0 = (item / p.n_groups) * BM;
+        for (long long item = item0; item < n_items; item += item_step) {
+            const long long m0 = row0_of(item);
             const int n_group = (int)(item % p.n_groups);
             const long long row = m0 + row_in_tile;
             const long long wrow0 = m0 + q * 32;     // first row of this warp's 32-row slab
@@ -681,7 +801,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
 
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(as));
+            if (lane == 0) {
+                if (CG == 2 && !leader) mbar_arrive_remote(acc_empty(as), 0);
+                else mbar_arrive(acc_empty(as));
+            }
             if (ACC_STAGES == 2) {
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
@@ -693,38 +816,60 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const GemmParams p
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc<CG>(tmem_base, kTmemCols);
     }
 }
 
 // CTAs of the persistent grid.  148 = every SM; a pipelined caller that overlaps this kernel with SM-filling latency
 // chains of another batch (FPS: one 192 KB-smem CTA per scene) lowers it so that no CTA of the grid waits for an SM.
 int g_persistent_ctas = pdab::kNumSMs;
+// 1: cta_group::2 CTA pairs (M = 256 per pair) whenever the problem has at least one full pair tile per pair; 0: single CTAs.
+int g_cta_pairs = 1;
 
-template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
-int launch(const GemmParams &p, cudaStream_t s) {
-    using C = Cfg<NPASS, BN>;
-    auto kern = tc_gemm_kernel<NPASS, BN, NCH, ALOAD, EPI>;
+template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
+int launch_cg(GemmParams p, cudaStream_t s) {
+    using C = Cfg<NPASS, BN, CG>;
+    auto kern = tc_gemm_kernel<NPASS, BN, NCH, ALOAD, EPI, CG>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    const long long grid = p.n_items < g_persistent_ctas ? p.n_items : g_persistent_ctas;
-    kern<<<(unsigned)grid, kThreads, C::SMEM_BYTES, s>>>(p);
+    p.n_items = ((p.T + BM * CG - 1) / (BM * CG)) * p.n_groups;
+    long long grid = p.n_items * CG < g_persistent_ctas ? p.n_items * CG : g_persistent_ctas;
+    if (CG == 2) grid &= ~1LL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PDAB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     PDAB_LAUNCH_CHECK();
     return 0;
+}
+
+template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
+int launch(const GemmParams &p, cudaStream_t s) {
+    // CTA pairs pay off once every pair has whole 256-row tiles to chew on; tiny problems stay on single CTAs
+    if (g_cta_pairs && g_persistent_ctas >= 2 && p.T >= 2 * BM * 8)
+        return launch_cg<NPASS, BN, NCH, ALOAD, EPI, 2>(p, s);
+    return launch_cg<NPASS, BN, NCH, ALOAD, EPI, 1>(p, s);
 }
 
 template <int NPASS, int ALOAD>
 int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
     const int chunks = (p.Nout + bn - 1) / bn;
-    auto items = [&](int nch) {
-        p.n_groups = chunks / nch;
-        p.n_items = ((p.T + BM - 1) / BM) * p.n_groups;
-    };
+    auto items = [&](int nch) { p.n_groups = chunks / nch; };
     if (epi == E_ADD_LN) {
         if (ALOAD != A_ROWS || bn != 256 || p.Nout % 256 || chunks > 2) return PDAB_EUNSUPPORTED;
         if (chunks == 1) {
@@ -758,6 +903,11 @@ int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
 extern "C" int pdab_set_persistent_ctas(int n) {
     if (n < 1 || n > pdab::kNumSMs) return PDAB_EINVAL;
     g_persistent_ctas = n;
+    return 0;
+}
+
+extern "C" int pdab_set_cta_pairs(int on) {
+    g_cta_pairs = on ? 1 : 0;
     return 0;
 }
 

@@ -179,3 +179,34 @@ def test_wide_sa_scale_matches_unfused_module(tc_passes):
         torch.backends.cudnn.allow_tf32 = prev
     err = float((fused - plain).abs().max() / plain.abs().max())
     assert err < (2e-5 if tc_passes == 3 else 3e-3), err
+
+
+@pytest.mark.parametrize("npass", [3, 2, 1])
+def test_cta_pairs_equal_single_ctas(npass):
+    """cta_group::2 CTA pairs (M = 256 across two SMs) are a schedule, not arithmetic: every epilogue / prologue gives
+    bit-identical results with pairs on and off (same MMAs in the same order per output element)."""
+    from pdanet_b200 import _lib
+    from pdanet_b200.tc_linear import (PackedLinear, EPI_STORE, EPI_RELU, EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_RELU_MAXPOOL)
+    dev = _dev()
+    rows, k = 6000 * 2 + 96, 256          # not a multiple of 256: the last pair tile is ragged, one CTA of it empty
+    x, w, b = _mk(rows, k, 512, seed=9)
+    res = torch.randn(rows, 512, generator=torch.Generator().manual_seed(10))
+    norm = torch.nn.LayerNorm(512).to(dev)
+    lin = PackedLinear(w.to(dev), b.to(dev), npass=npass)
+    lin128 = PackedLinear(w[:128].to(dev), b[:128].to(dev), npass=npass)
+    xd, rd = x.to(dev), res.to(dev)
+    outs = {}
+    try:
+        for pairs in (1, 0):
+            _lib.lib().pdab_set_cta_pairs(pairs)
+            outs[pairs] = [
+                lin(xd, EPI_STORE), lin(xd, EPI_RELU), lin(xd, EPI_ADD_LN, residual=rd, norm=norm),
+                lin(xd, EPI_ADD_MAXPOOL, residual=rd, nsample=32), lin(xd, EPI_RELU_MAXPOOL, nsample=16),
+                lin128(xd, EPI_RELU),
+            ]
+    finally:
+        _lib.lib().pdab_set_cta_pairs(1)
+    for a, c in zip(outs[1], outs[0]):
+        assert torch.equal(a, c)
+    ref = x.double() @ w.double().t() + b.double()
+    assert _rel(outs[1][0].cpu(), ref) < TOL[npass]

@@ -53,6 +53,11 @@ def main():
             ms = timeit(lambda: lin(x, EPI_STORE, out=out), args.iters)
             res[f"tc{npass}_ms"] = round(ms, 4)
             res[f"tc{npass}_tflops"] = round(flops / ms / 1e9, 1)
+        from pdanet_b200 import _lib
+        _lib.lib().pdab_set_cta_pairs(0)
+        lin = PackedLinear(w, b, npass=3)
+        res["tc3_single_cta_ms"] = round(timeit(lambda: lin(x, EPI_STORE, out=out), args.iters), 4)
+        _lib.lib().pdab_set_cta_pairs(1)
         wt = w.t().contiguous()
         hi = (wt.view(torch.int32) & -8192).view(torch.float32)
         lo = wt - hi
