@@ -7,13 +7,15 @@ the grouper kernel and the transformer:
   * the grouper kernel (`pdab_pda_group_tokens`) emits one contiguous row per (centre, neighbour) token;
   * every 1x1 convolution + eval BatchNorm becomes a folded linear layer on (tokens, channels) matrices;
   * every projection with K % 4 == 0 runs on the 5th-generation tensor cores through `PackedLinear`
-    (csrc/tc_gemm.cu: tcgen05.mma kind::tf32, fp32 accumulators in TMEM) as an error-compensated 3xTF32 product —
-    x = x_hi + x_lo, W = W_hi + W_lo split INSIDE the kernel, y = x_hi W_hi + x_hi W_lo + x_lo W_hi — i.e. with
-    fp32-level accuracy like the reference's nn.Linear / nn.MultiheadAttention, unlike plain TF32 (2^-11), which
-    moves the PDA features by ~1e-3 and flips class-aware top-k picks downstream;
+    (csrc/tc_gemm.cu: tcgen05.mma, fp32 accumulators in TMEM) as an error-compensated split product —
+    x = x_hi + x_lo, W = W_hi + W_lo split INSIDE the kernel, y = x_hi W_hi + x_hi W_lo + x_lo W_hi — with bf16 halves
+    (`tc_passes` = 2, default: ~1e-5 relative, bf16 tensor rate) or TF32 halves (`tc_passes` = 3: fp32-level 1e-6),
+    unlike plain TF32 (2^-11 = 5e-4, what the reference's cuDNN / cuBLAS calls use on tensor-core GPUs), which moves the
+    PDA features by ~1e-3 and flips class-aware top-k picks downstream;
   * what used to be separate launches between the GEMMs is fused into their epilogues:
     out_proj + residual + LayerNorm2, linear1 + ReLU, linear2 + residual + max-pool over the neighbourhood;
-  * attention itself (ns x ns per head, ns = 16/32) is one CUDA-core kernel in IEEE fp32 (`pdab_group_attention`).
+  * attention itself (ns x ns per head, ns = 16/32) is one kernel on warp-level mma.sync TF32 with 3x hi/lo
+    compensation, fp32 softmax (`pdab_group_attention`, csrc/pda_attn.cu).
 
 The module's parameters are used as they are (state_dict unchanged); folded / packed copies are cached per module
 and dropped on `.train()`.
@@ -50,7 +52,7 @@ def _fold(conv, bn):
 class PDAScalePlan:
     """Folded / packed parameters of scale `i` of a PDA SA module."""
 
-    def __init__(self, mod, i: int, npass: int = 3):
+    def __init__(self, mod, i: int, npass: int = 2):
         self.radius = mod.groupers[i].radius
         self.ns = mod.nsamples[i]
         pm, gm, fc = mod.position_mlp[i], mod.global_mlps[i], mod.fin_conv[i]

@@ -216,7 +216,10 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.mlps) > 0)
         self._folded = None  # BN-folded MLP parameters, built lazily in eval mode
         self._wide = {}      # scale -> packed tensor-core layers (tc_linear.PackedLinear), eval mode
-        self.tc_passes = 3   # 3 = error-compensated 3xTF32 (fp32-level); 1 = plain TF32 (cuDNN's default class)
+        # tensor-core product mode (tc_linear.PackedLinear): 2 = split-bf16 'bf16x3' (~1e-5 relative: 50x tighter than the
+        # TF32 the reference's cuDNN convolutions use by default, 100x inside the 1e-3 feature bar); 3 = 3xTF32 (fp32-level,
+        # 1e-6); 1 = plain TF32 (5e-4, the reference's own default class)
+        self.tc_passes = 2
 
     def train(self, mode: bool = True):
         self._folded = None
@@ -377,7 +380,7 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
         self.pool_method = pool_method
         self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.fin_conv) > 0)
         self.fast_eval = True   # token-major eval path (pda_block.py); False = the reference's statement order
-        self.tc_passes = 3      # tensor-core product mode of the fast path: 3 = 3xTF32, 2 = split-bf16, 1 = TF32
+        self.tc_passes = 2      # tensor-core product mode of the fast path: 2 = split-bf16 (1e-5), 3 = 3xTF32 (1e-6), 1 = TF32
         self._plans = {}
 
     def train(self, mode: bool = True):

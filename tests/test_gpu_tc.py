@@ -143,7 +143,7 @@ def test_group_attention_vs_torch_mha(ns, hd):
     assert _rel(ctx, ref) < 5e-6
 
 
-@pytest.mark.parametrize("tc_passes", [3, 1])
+@pytest.mark.parametrize("tc_passes", [3, 2, 1])
 def test_wide_sa_scale_matches_unfused_module(tc_passes):
     """Plain SA layer with wide MLPs (the L5 shape): tensor-core path vs the reference statement order
     (QueryAndGroup -> Conv2d/BN/ReLU x3 -> max_pool2d) of the same module with the same parameters."""
@@ -178,7 +178,7 @@ def test_wide_sa_scale_matches_unfused_module(tc_passes):
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     err = float((fused - plain).abs().max() / plain.abs().max())
-    assert err < (2e-5 if tc_passes == 3 else 3e-3), err
+    assert err < {3: 2e-5, 2: 2e-4, 1: 3e-3}[tc_passes], err
 
 
 @pytest.mark.parametrize("npass", [3, 2, 1])
