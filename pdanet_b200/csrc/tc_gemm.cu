@@ -712,6 +712,14 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                 sbias[i] = (p.bias && n < p.Nout) ? __ldg(p.bias + n) : 0.f;
             }
             __syncwarp();
+            // residual tiles: two register sets, each refilled as soon as it has been staged, so a tile has ~1.5 column
+            // blocks (and, for the first two, the whole accumulator wait) to arrive from L2 / HBM
+            float4 ra[8], rb[8];
+            if (EPI == E_ADD_MAXPOOL || EPI == E_ADD_LN) {
+                const int nb0 = n_group * NCH * BN;
+                issue_tile(ra, p.R, p.ldr, wrow0, p.T, nb0);
+                issue_tile(rb, p.R, p.ldr, wrow0, p.T, nb0 + 32);
+            }
             mbar_wait(acc_full(as), aphase);
             tc_fence_after();
             const u32 tacc = tmem_base + ((u32)(q * 32) << 16) + (u32)(as * ACC_COLS);
@@ -736,40 +744,44 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                 const int ns = p.ns;
                 const int nblk = NCH * (BN / 32);
                 auto n0_of = [&](int b) { return (n_group * NCH + b / (BN / 32)) * BN + (b % (BN / 32)) * 32; };
-                float4 rn[8];
-                if (EPI == E_ADD_MAXPOOL) issue_tile(rn, p.R, p.ldr, wrow0, p.T, n0_of(0));
-                for (int b = 0; b < nblk; b++) {
+                auto block = [&](int b, float4 (&r)[8]) {
                     const int n0 = n0_of(b);
-                    if (n0 >= p.Nout) break;
+                    if (n0 >= p.Nout) return;
                     float v[32];
                     tmem_ld32(tacc + (b / (BN / 32)) * BN + (b % (BN / 32)) * 32, v);
                     add_bias(v, b * 32);
                     if (EPI == E_ADD_MAXPOOL) {
-                        add_tile(v, rn);  // rn is dead once staged: refill it with the next tile right away
-                        if (b + 1 < nblk) issue_tile(rn, p.R, p.ldr, wrow0, p.T, n0_of(b + 1));
+                        add_tile(v, r);  // r is dead once staged: refill it with the tile two blocks ahead
+                        if (b + 2 < nblk) issue_tile(r, p.R, p.ldr, wrow0, p.T, n0_of(b + 2));
                     }
                     if (EPI == E_RELU_MAXPOOL) {
 #pragma unroll
                         for (int e = 0; e < 32; e++) v[e] = fmaxf(v[e], 0.f);
                     }
                     pool_store(v, wrow0, n0, ns);
+                };
+                for (int b = 0; b < nblk; b += 2) {
+                    block(b, ra);
+                    block(b + 1, rb);
                 }
             } else if (EPI == E_ADD_LN) {
                 // out = LayerNorm(acc + bias + R) over the full row of E = NCH * BN columns (n_groups == 1).
                 // Pass 1 parks v = acc + bias + R back in TMEM and sums it; pass 2: centred variance; pass 3: normalise.
                 constexpr int E = NCH * BN;
                 float sum = 0.f;
-                float4 rn[8];
-                issue_tile(rn, p.R, p.ldr, wrow0, p.T, 0);
-                for (int j = 0; j < E; j += 32) {
+                auto block = [&](int j, float4 (&r)[8]) {
                     float v[32];
                     tmem_ld32(tacc + j, v);
                     add_bias(v, j);
-                    add_tile(v, rn);  // rn is dead once staged: refill it with the next tile right away
-                    if (j + 32 < E) issue_tile(rn, p.R, p.ldr, wrow0, p.T, j + 32);
+                    add_tile(v, r);  // r is dead once staged: refill it with the tile two blocks ahead
+                    if (j + 64 < E) issue_tile(r, p.R, p.ldr, wrow0, p.T, j + 64);
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) sum += (v[e] + v[e + 1]) + (v[e + 2] + v[e + 3]);
                     tmem_st32(tacc + j, v);
+                };
+                for (int j = 0; j < E; j += 64) {
+                    block(j, ra);
+                    block(j + 32, rb);
                 }
                 const float mean = sum * (1.0f / E);
                 float sq = 0.f;
