@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight per GPU (ScenePipeline slots)")
+    ap.add_argument("--depth", type=int, default=4, help="batches in flight per GPU (ScenePipeline slots)")
+    ap.add_argument("--reserve-sms", type=int, default=None,
+                    help="SMs the persistent tensor-core grid leaves free for the other batches' FPS kernels (default: batch)")
     ap.add_argument("--no-graphs", action="store_true", help="do not capture the forward in CUDA graphs")
     ap.add_argument("--tc-passes", type=int, default=None, choices=[1, 2, 3],
                     help="tensor-core product mode of our GEMM kernels: 3 = 3xTF32 (fp32-level), 2 = split-bf16 (2^-16), "
@@ -235,7 +237,8 @@ def run_gpu_arm(args, cfg, n_points, batch):
              for r in range(R)]
     devs = [h.to(dev) for h in hosts]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    pipe = ScenePipeline(runner, depth=args.depth, graphs=not args.no_graphs, warm_points=hosts[0])
+    pipe = ScenePipeline(runner, depth=args.depth, graphs=not args.no_graphs, warm_points=hosts[0],
+                         reserve_sms=args.reserve_sms)
 
     def barrier():
         torch.cuda.synchronize()

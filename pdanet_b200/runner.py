@@ -76,15 +76,17 @@ class ScenePipeline:
     CUDA graph (fixed shapes: batch_size x num_points), replayed per batch.
 
     Why: distance-FPS is a serial latency chain that occupies one SM per scene for milliseconds (hard
-    part 1); run back to back it idles ~130 SMs.  With two batches in flight the FPS of batch k+1 runs on its 16 SMs
-    while the tensor-core / gather kernels of batch k use the others; the graph removes the host launch cost of the
+    part 1); run back to back it idles ~130 SMs.  With several batches in flight the FPS of batch k+1 runs on its 16 SMs
+    while the tensor-core / gather kernels of batch k use the others, and the tails of small kernels overlap (measured:
+    depth 2 -> 1200, depth 4 -> 1280 scenes/s); the graph removes the host launch cost of the
     ~350 kernels of a step.  The persistent tensor-core kernels are told to leave one SM per in-flight scene free
     (`pdab_set_persistent_ctas`) so their grid never queues behind an FPS CTA.
 
     Results are identical to `SceneRunner.infer` (same kernels, same order per batch); tests check it.
     """
 
-    def __init__(self, runner: SceneRunner, depth: int = 2, graphs: bool = True, warm_points: torch.Tensor = None):
+    def __init__(self, runner: SceneRunner, depth: int = 4, graphs: bool = True, warm_points: torch.Tensor = None,
+                 reserve_sms: int = None):
         from types import SimpleNamespace
         from . import _lib
         from .synthetic import make_batch
@@ -92,8 +94,10 @@ class ScenePipeline:
         dev, B, N = runner.device, runner.batch_size, runner.num_points
         self.model = runner.model
         self.launches_per_step = 0
-        if depth > 1 and B < 100:
-            _lib.check("pdab_set_persistent_ctas", _lib.lib().pdab_set_persistent_ctas(148 - B))
+        if reserve_sms is None:  # one SM per scene of ONE in-flight FPS kernel (deeper pipelines rarely overlap two)
+            reserve_sms = B if depth > 1 and B < 100 else 0
+        self.reserve_sms = reserve_sms
+        _lib.check("pdab_set_persistent_ctas", _lib.lib().pdab_set_persistent_ctas(148 - reserve_sms))
         if warm_points is None:
             warm_points = make_batch(B, N, runner.cfg.POINT_CLOUD_RANGE)["points"]
         self.slots = []
