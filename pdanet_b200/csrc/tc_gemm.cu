@@ -110,28 +110,19 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz; a healthy wait is microseconds
     }
 }
-// acquire at cluster scope: for barriers that CTAs of the pair arrive on remotely
-__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        u32 ok;
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
+// Barriers that the peer CTA of a pair arrives on remotely are waited on with the ordinary (CTA-scope acquire) form and
+// signalled with the default-semantics remote arrive below — the forms CUTLASS's ClusterBarrier uses for the same
+// producer / consumer hand-offs.  (The explicit .release.cluster / .acquire.cluster forms compile to MEMBAR.ALL.GPU and
+// CCTL.IVALL on every stage: measured in profiles/r01_ncu_tc_gemm_*.)  What is handed over is either shared memory the
+// peer wrote behind a fence.proxy.async and that the PEER's own tensor-core datapath reads, or TMEM the peer finished
+// reading behind tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) { mbar_wait(bar, parity); }
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(u32 bar, u32 cta) {
     asm volatile(
         "{\n.reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}" ::"r"(bar),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}" ::"r"(bar),
         "r"(cta)
         : "memory");
 }
@@ -260,6 +251,34 @@ __device__ __forceinline__ void tmem_st32(u32 taddr, const float (&v)[32]) {
         : "memory");
 }
 
+// 16 lanes x 32 columns in the MMA-C-fragment layout: register k*4 + j*2 + e of lane t holds TMEM lane
+// base + 8 j + t / 4, column base + 8 k + 2 (t % 4) + e   (cute SM100_TMEM_LOAD_16dp256b4x).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(u32 taddr, float (&v)[16]) {
+    u32 r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(u32 taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%16], "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};" ::"r"(__float_as_uint(v[0])),
+        "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+        "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor, canonical K-major SWIZZLE_128B tile (rows of 128 B, 8-row groups 1024 B apart):
 // start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 >> 4 | version 1 (sm_100) | layout 2 (SW128).
 __device__ __forceinline__ u64 umma_desc(u32 smem_addr) {
@@ -312,7 +331,6 @@ struct Cfg {
     static constexpr int PRODUCER_WARPS = CG == 2 ? 6 : 8;
     static constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + 4);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      4 * 32 * kStgPitch * 4 /*epilogue staging tiles*/ +
                                       4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/;
 };
 
@@ -381,7 +399,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
     if (CG == 2) cluster_sync_all();  // both CTAs of the pair resident, barriers initialised before any remote arrive
     if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
     if (EPI == E_ADD_LN) {  // LayerNorm scale / shift -> smem once (Nout = NCH * BN <= 512 columns)
-        float *sg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + 4 * 512;
+        float *sg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512;
         for (int i = threadIdx.x; i < NCH * BN; i += kThreads) {
             sg[i] = __ldg(p.gamma + i);
             sg[512 + i] = __ldg(p.beta + i);
@@ -605,116 +623,140 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
         }
     } else {
         // ===================================================================== epilogue (128 threads)
-        // tcgen05.ld hands every thread one ROW (TMEM lane) x 32 consecutive columns.  Global traffic goes through a
-        // per-warp 32x32 staging tile in shared memory so that every load / store instruction covers 4 rows x 128
-        // contiguous bytes (row-per-thread accesses touch 32 different lines per instruction and were 4x slower).
+        // The accumulator is read with the 16x256b TMEM load shape, which hands out an MMA-C-fragment layout: for a
+        // 32-row x 32-column block, lane (fr = lane / 4, fc = 2 * (lane % 4)) holds rows 16 h + 8 j + fr (h, j in {0,1})
+        // and columns 8 k + fc + {0, 1} (k = 0..3).  A quad of lanes therefore owns 32 contiguous bytes of a row: every
+        // global load / store instruction moves whole 32-byte sectors with no shared-memory transpose, a row statistic
+        // is two shuffles inside the quad, and a maximum over the rows of a neighbourhood is three shuffles.  (The first
+        // version used the 32x32b shape — thread = row — and staged every block through shared memory twice; it was
+        // instruction- and latency-bound: profiles/r01_ncu_tc_gemm_*.)
         const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-        const int row_in_tile = q * 32 + lane;
         const int ew = warp - (2 + kProducerWarps);   // 0..3
-        float *stg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + ew * (32 * kStgPitch);
-        // Per-column parameters live in shared memory: with ~216 KB of it carved out the L1 is ~12 KB and thrashed by
+        const int fr = lane >> 2, fc = (lane & 3) * 2;
+        // Per-column parameters live in shared memory: with ~200 KB of it carved out the L1 is a few KB and thrashed by
         // the A stream, so an __ldg of bias / gamma / beta inside the block loop was an L2 round trip on the critical path.
-        float *sbias = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + ew * 512;
-        const float *sgamma = reinterpret_cast<const float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 32 * kStgPitch + 4 * 512;
+        float *sbias = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + ew * 512;
+        const float *sgamma = reinterpret_cast<const float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512;
         const float *sbeta = sgamma + 512;
-        const int srow = lane >> 3, schunk = lane & 7;   // coalesced phase: lane -> (row it*4 + srow, 16-byte chunk)
         int as = 0;
         u32 aphase = 0;
 
-        // v (thread = row) -> global rows [grow0, grow0+32) x columns [n0, n0+32), coalesced
-        auto store_tile = [&](const float (&v)[32], float *base, int ld, long long grow0, long long nrows, int n0) {
-            __syncwarp();
+        // v[h][k*4 + j*2 + e]  <->  row 16h + 8j + fr, column 8k + fc + e   (register order of tcgen05.ld.16x256b.x4)
+        auto frag_ld = [&](u32 taddr, float (&v)[2][16]) {
+            tmem_ld_16x256b_x4(taddr, v[0]);
+            tmem_ld_16x256b_x4(taddr + (16u << 16), v[1]);
+            tmem_wait_ld();
+        };
+        auto frag_st = [&](u32 taddr, const float (&v)[2][16]) {
+            tmem_st_16x256b_x4(taddr, v[0]);
+            tmem_st_16x256b_x4(taddr + (16u << 16), v[1]);
+            tmem_wait_st();
+        };
+        // columns [c0, c0+32) of this item (c0 relative to the item's first column): bias staged per item below
+        auto add_bias = [&](float (&v)[2][16], int c0) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4 *>(stg + lane * kStgPitch + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            __syncwarp();
-            const int col = n0 + schunk * 4;
+            for (int k = 0; k < 4; k++) {
+                const float2 b2 = *reinterpret_cast<const float2 *>(sbias + c0 + 8 * k + fc);
 #pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int r = it * 4 + srow;
-                const float4 x = *reinterpret_cast<const float4 *>(stg + r * kStgPitch + schunk * 4);
-                if (grow0 + r < nrows && col < p.Nout)
-                    *reinterpret_cast<float4 *>(base + (grow0 + r) * ld + col) = x;
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        v[h][k * 4 + j * 2] += b2.x;
+                        v[h][k * 4 + j * 2 + 1] += b2.y;
+                    }
             }
         };
-        // Residual tiles: global rows [grow0, grow0+32) x columns [n0, n0+32), coalesced float4 loads into registers
-        // (issued one tile ahead of their use so the global latency hides behind the previous tile's work) ...
-        auto issue_tile = [&](float4 (&t)[8], const float *base, int ld, long long grow0, long long nrows, int n0) {
-            const int col = n0 + schunk * 4;
+        // global rows [grow0, grow0+32) x columns [n0, n0+32) in the fragment layout; zeros outside the matrix
+        auto issue_tile = [&](float2 (&t)[2][8], const float *base, int ld, long long grow0, long long nrows, int n0) {
 #pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int r = it * 4 + srow;
-                t[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (grow0 + r < nrows && col < p.Nout)
-                    t[it] = __ldg(reinterpret_cast<const float4 *>(base + (grow0 + r) * ld + col));
-            }
-        };
-        // ... then transposed through the staging tile to the thread = row layout and added to v
-        auto add_tile = [&](float (&v)[32], const float4 (&t)[8]) {
-            __syncwarp();
+            for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int it = 0; it < 8; it++)
-                *reinterpret_cast<float4 *>(stg + (it * 4 + srow) * kStgPitch + schunk * 4) = t[it];
-            __syncwarp();
+                for (int j = 0; j < 2; j++) {
+                    const long long r = grow0 + 16 * h + 8 * j + fr;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const float4 x = *reinterpret_cast<const float4 *>(stg + lane * kStgPitch + e);
-                v[e] += x.x;
-                v[e + 1] += x.y;
-                v[e + 2] += x.z;
-                v[e + 3] += x.w;
-            }
-        };
-        // max over the ns (16 or 32) consecutive rows of each neighbourhood: v (thread = row) goes through the staging
-        // tile, then lane = COLUMN reads its 32 rows (bank = 4 r + lane: conflict-free) and writes out[group, n0 + lane].
-        auto pool_store = [&](const float (&v)[32], long long grow0, int n0, int ns) {
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4 *>(stg + lane * kStgPitch + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            __syncwarp();
-            float m0 = -3.4e38f, m1 = -3.4e38f;
-#pragma unroll
-            for (int r = 0; r < 16; r++) {
-                m0 = fmaxf(m0, stg[r * kStgPitch + lane]);
-                m1 = fmaxf(m1, stg[(r + 16) * kStgPitch + lane]);
-            }
-            if (n0 + lane < p.Nout) {
-                if (ns == 32) {
-                    if (grow0 < p.T) p.out[(grow0 / 32) * p.ldo + n0 + lane] = fmaxf(m0, m1);
-                } else {
-                    if (grow0 < p.T) p.out[(grow0 / 16) * p.ldo + n0 + lane] = m0;
-                    if (grow0 + 16 < p.T) p.out[(grow0 / 16 + 1) * p.ldo + n0 + lane] = m1;
+                    for (int k = 0; k < 4; k++) {
+                        const int col = n0 + 8 * k + fc;
+                        t[h][k * 2 + j] = make_float2(0.f, 0.f);
+                        if (r < nrows && col < p.Nout)
+                            t[h][k * 2 + j] = __ldg(reinterpret_cast<const float2 *>(base + r * ld + col));
+                    }
                 }
-            }
         };
-        // bias of columns [c0, c0+32) of this item (c0 relative to the item's first column), staged per item below
-        auto add_bias = [&](float (&v)[32], int c0) {
+        auto add_tile = [&](float (&v)[2][16], const float2 (&t)[2][8]) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const float4 b4 = *reinterpret_cast<const float4 *>(sbias + c0 + e);
-                v[e] += b4.x;
-                v[e + 1] += b4.y;
-                v[e + 2] += b4.z;
-                v[e + 3] += b4.w;
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        v[h][k * 4 + j * 2] += t[h][k * 2 + j].x;
+                        v[h][k * 4 + j * 2 + 1] += t[h][k * 2 + j].y;
+                    }
+        };
+        auto store_tile = [&](const float (&v)[2][16], float *base, int ld, long long grow0, long long nrows, int n0) {
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const long long r = grow0 + 16 * h + 8 * j + fr;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int col = n0 + 8 * k + fc;
+                        if (r < nrows && col < p.Nout)
+                            *reinterpret_cast<float2 *>(base + r * ld + col) =
+                                make_float2(v[h][k * 4 + j * 2], v[h][k * 4 + j * 2 + 1]);
+                    }
+                }
+        };
+        // max over the ns (16 or 32) consecutive rows of each neighbourhood -> out[group, n0 + ...]
+        auto pool_store = [&](const float (&v)[2][16], long long grow0, int n0, int ns) {
+            float m[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        float x = fmaxf(v[h][k * 4 + e], v[h][k * 4 + 2 + e]);       // rows fr and fr + 8 of half h
+                        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
+                        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+                        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+                        m[h][k * 2 + e] = x;
+                    }
+            if (fr == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int col = n0 + 8 * k + fc;
+                    if (col >= p.Nout) continue;
+                    if (ns == 32) {
+                        if (grow0 < p.T)
+                            *reinterpret_cast<float2 *>(p.out + (grow0 / 32) * p.ldo + col) =
+                                make_float2(fmaxf(m[0][k * 2], m[1][k * 2]), fmaxf(m[0][k * 2 + 1], m[1][k * 2 + 1]));
+                    } else {
+                        if (grow0 < p.T)
+                            *reinterpret_cast<float2 *>(p.out + (grow0 / 16) * p.ldo + col) =
+                                make_float2(m[0][k * 2], m[0][k * 2 + 1]);
+                        if (grow0 + 16 < p.T)
+                            *reinterpret_cast<float2 *>(p.out + (grow0 / 16 + 1) * p.ldo + col) =
+                                make_float2(m[1][k * 2], m[1][k * 2 + 1]);
+                    }
+                }
             }
         };
 
         for (long long item = item0; item < n_items; item += item_step) {
             const long long m0 = row0_of(item);
             const int n_group = (int)(item % p.n_groups);
-            const long long row = m0 + row_in_tile;
             const long long wrow0 = m0 + q * 32;     // first row of this warp's 32-row slab
-            const bool row_ok = row < p.T;
             __syncwarp();
             for (int i = lane; i < NCH * BN; i += 32) {   // this item's bias -> smem while the MMAs still run
                 const int n = n_group * NCH * BN + i;
                 sbias[i] = (p.bias && n < p.Nout) ? __ldg(p.bias + n) : 0.f;
             }
             __syncwarp();
-            // residual tiles: two register sets, each refilled as soon as it has been staged, so a tile has ~1.5 column
+            // residual tiles: two register sets, each refilled as soon as it has been consumed, so a tile has ~1.5 column
             // blocks (and, for the first two, the whole accumulator wait) to arrive from L2 / HBM
-            float4 ra[8], rb[8];
+            float2 ra[2][8], rb[2][8];
             if (EPI == E_ADD_MAXPOOL || EPI == E_ADD_LN) {
                 const int nb0 = n_group * NCH * BN;
                 issue_tile(ra, p.R, p.ldr, wrow0, p.T, nb0);
@@ -729,12 +771,15 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                     for (int j = 0; j < BN; j += 32) {
                         const int n0 = (n_group * NCH + c) * BN + j;
                         if (n0 >= p.Nout) break;
-                        float v[32];
-                        tmem_ld32(tacc + c * BN + j, v);
+                        float v[2][16];
+                        frag_ld(tacc + c * BN + j, v);
                         add_bias(v, c * BN + j);
                         if (EPI == E_RELU) {
 #pragma unroll
-                            for (int e = 0; e < 32; e++) v[e] = fmaxf(v[e], 0.f);
+                            for (int e = 0; e < 16; e++) {
+                                v[0][e] = fmaxf(v[0][e], 0.f);
+                                v[1][e] = fmaxf(v[1][e], 0.f);
+                            }
                         }
                         store_tile(v, p.out, p.ldo, wrow0, p.T, n0);
                     }
@@ -744,19 +789,22 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                 const int ns = p.ns;
                 const int nblk = NCH * (BN / 32);
                 auto n0_of = [&](int b) { return (n_group * NCH + b / (BN / 32)) * BN + (b % (BN / 32)) * 32; };
-                auto block = [&](int b, float4 (&r)[8]) {
+                auto block = [&](int b, float2 (&r)[2][8]) {
                     const int n0 = n0_of(b);
                     if (n0 >= p.Nout) return;
-                    float v[32];
-                    tmem_ld32(tacc + (b / (BN / 32)) * BN + (b % (BN / 32)) * 32, v);
+                    float v[2][16];
+                    frag_ld(tacc + (b / (BN / 32)) * BN + (b % (BN / 32)) * 32, v);
                     add_bias(v, b * 32);
                     if (EPI == E_ADD_MAXPOOL) {
-                        add_tile(v, r);  // r is dead once staged: refill it with the tile two blocks ahead
+                        add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
                         if (b + 2 < nblk) issue_tile(r, p.R, p.ldr, wrow0, p.T, n0_of(b + 2));
                     }
                     if (EPI == E_RELU_MAXPOOL) {
 #pragma unroll
-                        for (int e = 0; e < 32; e++) v[e] = fmaxf(v[e], 0.f);
+                        for (int e = 0; e < 16; e++) {
+                            v[0][e] = fmaxf(v[0][e], 0.f);
+                            v[1][e] = fmaxf(v[1][e], 0.f);
+                        }
                     }
                     pool_store(v, wrow0, n0, ns);
                 };
@@ -767,47 +815,74 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
             } else if (EPI == E_ADD_LN) {
                 // out = LayerNorm(acc + bias + R) over the full row of E = NCH * BN columns (n_groups == 1).
                 // Pass 1 parks v = acc + bias + R back in TMEM and sums it; pass 2: centred variance; pass 3: normalise.
+                // A thread owns 4 rows (h, j); a row's 8 values per block are summed in the thread, then over the quad.
                 constexpr int E = NCH * BN;
-                float sum = 0.f;
-                auto block = [&](int j, float4 (&r)[8]) {
-                    float v[32];
-                    tmem_ld32(tacc + j, v);
-                    add_bias(v, j);
-                    add_tile(v, r);  // r is dead once staged: refill it with the tile two blocks ahead
-                    if (j + 64 < E) issue_tile(r, p.R, p.ldr, wrow0, p.T, j + 64);
+                float sum[4] = {0.f, 0.f, 0.f, 0.f};
+                auto block = [&](int j0, float2 (&r)[2][8]) {
+                    float v[2][16];
+                    frag_ld(tacc + j0, v);
+                    add_bias(v, j0);
+                    add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
+                    if (j0 + 64 < E) issue_tile(r, p.R, p.ldr, wrow0, p.T, j0 + 64);
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) sum += (v[e] + v[e + 1]) + (v[e + 2] + v[e + 3]);
-                    tmem_st32(tacc + j, v);
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) sum[h * 2 + j] += v[h][k * 4 + j * 2] + v[h][k * 4 + j * 2 + 1];
+                    frag_st(tacc + j0, v);
                 };
-                for (int j = 0; j < E; j += 64) {
-                    block(j, ra);
-                    block(j + 32, rb);
+                for (int j0 = 0; j0 < E; j0 += 64) {
+                    block(j0, ra);
+                    block(j0 + 32, rb);
                 }
-                const float mean = sum * (1.0f / E);
-                float sq = 0.f;
-                for (int j = 0; j < E; j += 32) {
-                    float v[32];
-                    tmem_ld32(tacc + j, v);
+                float mean[4], rstd[4], sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int e = 0; e < 32; e++) {
-                        const float d = v[e] - mean;
-                        sq = fmaf(d, d, sq);
-                    }
+                for (int i = 0; i < 4; i++) {
+                    float t = sum[i];
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    mean[i] = t * (1.0f / E);
                 }
-                const float rstd = rsqrtf(sq * (1.0f / E) + p.eps);
-                for (int j = 0; j < E; j += 32) {
-                    float v[32];
-                    tmem_ld32(tacc + j, v);
+                for (int j0 = 0; j0 < E; j0 += 32) {
+                    float v[2][16];
+                    frag_ld(tacc + j0, v);
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        const float4 g4 = *reinterpret_cast<const float4 *>(sgamma + j + e);
-                        const float4 b4 = *reinterpret_cast<const float4 *>(sbeta + j + e);
-                        v[e] = (v[e] - mean) * rstd * g4.x + b4.x;
-                        v[e + 1] = (v[e + 1] - mean) * rstd * g4.y + b4.y;
-                        v[e + 2] = (v[e + 2] - mean) * rstd * g4.z + b4.z;
-                        v[e + 3] = (v[e + 3] - mean) * rstd * g4.w + b4.w;
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    const float d = v[h][k * 4 + j * 2 + e] - mean[h * 2 + j];
+                                    sq[h * 2 + j] = fmaf(d, d, sq[h * 2 + j]);
+                                }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float t = sq[i];
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    rstd[i] = rsqrtf(t * (1.0f / E) + p.eps);
+                }
+                for (int j0 = 0; j0 < E; j0 += 32) {
+                    float v[2][16];
+                    frag_ld(tacc + j0, v);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 g2 = *reinterpret_cast<const float2 *>(sgamma + j0 + 8 * k + fc);
+                        const float2 b2 = *reinterpret_cast<const float2 *>(sbeta + j0 + 8 * k + fc);
+#pragma unroll
+                        for (int h = 0; h < 2; h++)
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const int i = h * 2 + j;
+                                v[h][k * 4 + j * 2] = (v[h][k * 4 + j * 2] - mean[i]) * rstd[i] * g2.x + b2.x;
+                                v[h][k * 4 + j * 2 + 1] = (v[h][k * 4 + j * 2 + 1] - mean[i]) * rstd[i] * g2.y + b2.y;
+                            }
                     }
-                    store_tile(v, p.out, p.ldo, wrow0, p.T, j);
+                    store_tile(v, p.out, p.ldo, wrow0, p.T, j0);
                 }
             }
 
