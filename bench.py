@@ -347,6 +347,13 @@ def run_gpu_arm(args, cfg, n_points, batch):
         common = {"kernel": name, "launches_per_step": g["launches"] / args.steps,
                   "avg_launch_ms": round(g["ms"] / g["launches"], 4), "share_of_step": round(g["ms"] / args.steps / step_ms, 4),
                   "traffic": None}
+        tr = ROOT / "profiles" / "r01_tc_gemm_traffic.json"
+        if name == "pdab_tc_linear" and tr.exists() and args.config == "kitti" and batch == 16:
+            t = json.loads(tr.read_text())  # ncu dram__bytes_read + write per launch, same workload (see its "source")
+            common["traffic"] = round(t["dram_bytes_per_launch"])
+            common["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's launches)"
+            common["algorithmic_bytes_per_launch"] = round(g["bytes"] / g["launches"])
+            common["traffic_source"] = "profiles/r01_tc_gemm_traffic.json"
         if g["flops"] > 0:  # tensor-core kernel: algorithmic flops = 2*rows*k*nout of the fp32 product it computes
             achieved = g["flops"] / g["ms"] / 1e9
             roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": tf32_peak, "unit": "TFLOP/s",

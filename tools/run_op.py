@@ -40,6 +40,18 @@ elif op == "sa_fused":
     bs = [torch.randn(dims[i + 1], device="cuda") * 0.1 for i in range(3)]
     for _ in range(3):
         ops.sa_fused(r, ns, xyz, xyz[:, :M].contiguous(), feats, ws, bs)
+elif op == "sa_pair":
+    import math
+    B, N, M = a
+    xyz = scene_xyz(N + M, B, N).cuda()
+    feats = torch.rand(B, 1, N, device="cuda")
+    ws, bs = [], []
+    for dims in ([4, 16, 16, 32], [4, 32, 32, 64]):
+        for i in range(3):
+            ws.append(torch.randn(dims[i + 1], dims[i], device="cuda") / math.sqrt(dims[i]))
+            bs.append(torch.randn(dims[i + 1], device="cuda") * 0.1)
+    for _ in range(3):
+        ops.sa_fused_pair((0.2, 0.8), (16, 32), xyz, xyz[:, :M].contiguous(), feats, ws, bs)
 elif op == "tc_linear":   # rows k nout npass epilogue  (epilogue: 0 store 1 relu 2 add+LN 3 add+maxpool 4 relu+maxpool)
     from pdanet_b200.tc_linear import PackedLinear
     rows, k, nout, npass, epi = a
