@@ -64,6 +64,7 @@ fps_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp
     extern __shared__ float smem[];
     __shared__ unsigned long long red[2][32];
     __shared__ Candidate xchg[2][kMaxCluster];
+    __shared__ __align__(8) unsigned long long xbar[2];  // mbarriers: candidates of all CL CTAs have landed in xchg[buf]
 
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
@@ -98,8 +99,16 @@ fps_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp
             }
         }
     }
-    if (CL > 1) cg::this_cluster().sync();  // peers must be resident before any DSMEM store
-    else __syncthreads();
+    if (CL > 1) {
+        if (t == 0) {
+            for (int i = 0; i < 2; i++)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&xbar[i])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cg::this_cluster().sync();  // peers resident and their barriers initialised before any DSMEM store
+    } else {
+        __syncthreads();
+    }
 
     int old = 0;
     float x1 = 0.f, y1 = 0.f, z1 = 0.f;
@@ -149,31 +158,57 @@ fps_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp
                 z1 = sz[slot];
             }
         } else {
+            // Exchange without a cluster barrier (barrier.cluster release/acquire costs ~2 us per step): every CTA
+            // pushes its 32-byte candidate into each peer's xchg[buf][rank] with st.async, which completes on the
+            // RECEIVER's mbarrier; a CTA waits for CL x 32 bytes on its own barrier.  Buffer reuse is safe: a peer can
+            // only send step it+2 after it has consumed step it+1, which needs this CTA's step it+1 candidate, which is
+            // sent after this CTA's block barrier of step it+1, i.e. after all its threads have read step it's buffer.
+            const unsigned bar_local = (unsigned)__cvta_generic_to_shared(&xbar[buf]);
+            if (t == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local), "r"(CL * 32)
+                             : "memory");
             if (t < CL) {
-                Candidate c;
-                c.key = cand;
-                c.x = c.y = c.z = c.pad = 0.f;
+                float cx = 0.f, cy = 0.f, cz = 0.f;
                 if (cand != 0ull) {
                     const int k = tie_key_decode(~(unsigned)cand, L);
                     const int slot = ((k >> 10) / CL) * kThreads + (k & (kThreads - 1));
-                    c.x = sx[slot];
-                    c.y = sy[slot];
-                    c.z = sz[slot];
+                    cx = sx[slot];
+                    cy = sy[slot];
+                    cz = sz[slot];
                 }
-                Candidate *remote = cg::this_cluster().map_shared_rank(&xchg[buf][rank], t);
-                *remote = c;
+                const unsigned dst_local = (unsigned)__cvta_generic_to_shared(&xchg[buf][rank]);
+                unsigned dst, rbar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(t));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_local), "r"(t));
+                asm volatile(
+                    "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                    "r"((unsigned)cand), "r"((unsigned)(cand >> 32)), "r"(__float_as_uint(cx)), "r"(__float_as_uint(cy)),
+                    "r"(rbar)
+                    : "memory");
+                asm volatile(
+                    "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst + 16),
+                    "r"(__float_as_uint(cz)), "r"(0u), "r"(0u), "r"(0u), "r"(rbar)
+                    : "memory");
             }
-            cg::this_cluster().sync();
-            unsigned long long w = 0ull;
-            int wi = 0;
-#pragma unroll 1
-            for (int i = 0; i < CL; i++) {
-                const unsigned long long v = xchg[buf][i].key;
-                if (v > w) {
-                    w = v;
-                    wi = i;
+            {
+                const unsigned parity = (unsigned)(((it - 1) >> 1) & 1);   // buffer `buf` is used every second step
+                unsigned ok = 0;
+                const long long t0 = clock64();
+                while (!ok) {
+                    asm volatile(
+                        "{\n.reg .pred p;\n"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                        "selp.u32 %0, 1, 0, p;\n}"
+                        : "=r"(ok)
+                        : "r"(bar_local), "r"(parity)
+                        : "memory");
+                    if (!ok && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU on a protocol bug
                 }
             }
+            // every warp picks the winner itself: lane i holds CTA i's key, REDUX max, lowest lane with the max
+            const unsigned long long mine = lane < CL ? xchg[buf][lane].key : 0ull;
+            const unsigned long long w = warp_max_u64(mine);
+            const int wi = __ffs(__ballot_sync(0xffffffffu, mine == w && lane < CL)) - 1;
             old = tie_key_decode(~(unsigned)w, L);
             x1 = xchg[buf][wi].x;
             y1 = xchg[buf][wi].y;
@@ -188,6 +223,7 @@ fps_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp
         const int k = t + kThreads * (rank + CL * j);
         if (k < n) temp[k] = dist[j];
     }
+    if (CL > 1) cg::this_cluster().sync();  // nobody exits while a peer's last st.async may still target its shared memory
 }
 
 template <int P, bool MATRIX>
@@ -237,6 +273,16 @@ int dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaS
         per = pdab::div_up(n, kThreads * CL);
     }
     if (per > 16 || (MATRIX && CL > 1)) return PDAB_EUNSUPPORTED;
+    if (!MATRIX && n > 16384) {
+        // A serial chain: more SMs per scene shorten every step (fewer points per thread) as long as the clusters of all
+        // scenes are resident together; grow the cluster while the grid still fits the 148 SMs.
+        // (clusters of 16 are placed one per GPC at best: stop at the portable size 8 unless the batch is tiny)
+        const int cl_cap = b <= 4 ? kMaxCluster : 8;
+        while (CL < cl_cap && b * CL * 2 <= pdab::kNumSMs && per > 1) {
+            CL *= 2;
+            per = pdab::div_up(n, kThreads * CL);
+        }
+    }
     const int L = ref_log2_block(n);
     if (!MATRIX && n >= 1024 && n <= 16384 && m > 64) {
         // spatially pruned variant: same results, ~N ln m instead of N m point updates
