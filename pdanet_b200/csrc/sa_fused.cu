@@ -47,52 +47,156 @@ __device__ __forceinline__ void dense(const float *__restrict__ W, const float *
 
 constexpr int kMlpThreads = 256;  // 128 scan threads + 128 helpers; all 8 warps run the MLP phase
 
-// Phase 2 of the fused kernels: one LANE per (centre, neighbour): a warp takes one centre (nsample = 32) or two
-// (nsample = 16) at a time, every lane pushes its neighbour through the three layers with the weights broadcast from
-// shared memory, and the channel maximum over the neighbourhood is a shuffle butterfly; results go to sout[C3][kStride].
+// ---- Phase 2 of the fused kernels on the warp-level tensor-core path --------------------------------------------------
+// The three layers of a narrow SA scale are 16..32 x {4..8, 16..32} x {16..64} contractions per neighbourhood: far below
+// a tcgen05 tile, but a perfect fit for mma.sync m16n8k8 (TF32 operands, fp32 accumulate) with the same 3x hi/lo error
+// compensation as the big GEMMs (fp32-level results: x = x_hi + x_lo, acc += x_hi w_lo + x_lo w_hi + x_hi w_hi).
+// A warp takes 32 (centre, neighbour) rows per pass = two m-tiles of 16 rows: one centre when nsample > 16, two centres
+// otherwise (rows beyond nsample repeat the last neighbour, harmless for a max).  Activations never leave registers: the
+// C fragments of one layer become the A fragments of the next through 8 shuffles per k-step; the max over the
+// neighbourhood is 3 shuffles per output column.  (The first version pushed one neighbour per lane through the layers
+// on the FMA pipe with broadcast weights: ~5400 instructions per pass against ~900 here.)
+// Weights live in shared memory with row pitch wpitch(K) floats so that B-fragment loads (row g, column t) are
+// conflict-free.
+__host__ __device__ constexpr int wpitch(int K) { return K == 4 ? 4 : K + 4; }
+
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_3x(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    unsigned ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) split_tf32(a[i], ah[i], al[i]);
+    split_tf32(b0, bh[0], bl[0]);
+    split_tf32(b1, bh[1], bl[1]);
+#define PDAB_MMA(A, B)                                                                                              \
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "     \
+                 "{%0,%1,%2,%3};"                                                                                   \
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])                                                   \
+                 : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(B[0]), "r"(B[1]))
+    PDAB_MMA(ah, bl);  // small terms first
+    PDAB_MMA(al, bh);
+    PDAB_MMA(ah, bh);
+#undef PDAB_MMA
+}
+
+// One layer on one m-tile: out[nt] (C fragments, N/8 tiles) = relu(A (16 x K) . W^T + bias).
+// A fragments come from `afrag(s, a)`, which fills a[4] for k-step s.
+template <int K, int N, class AFrag>
+__device__ __forceinline__ void mma_layer(const float *sW, const float *sb, int g, int t, AFrag afrag,
+                                          float (&out)[N / 8][4]) {
+    constexpr int WP = wpitch(K);
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++) {
+        const float b0 = sb[nt * 8 + 2 * t], b1 = sb[nt * 8 + 2 * t + 1];
+        out[nt][0] = b0;
+        out[nt][1] = b1;
+        out[nt][2] = b0;
+        out[nt][3] = b1;
+    }
+#pragma unroll
+    for (int s = 0; s < (K + 7) / 8; s++) {
+        float a[4];
+        afrag(s, a);
+#pragma unroll
+        for (int nt = 0; nt < N / 8; nt++) {
+            const float *w = sW + (nt * 8 + g) * WP + s * 8 + t;
+            const float w0 = w[0];
+            const float w1 = (s * 8 + 4 < K) ? w[4] : 0.f;   // K = 4: columns 4..7 do not exist
+            mma_tf32_3x(out[nt], a, w0, w1);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) out[nt][e] = fmaxf(out[nt][e], 0.f);
+}
+
+// A fragments of k-step s from the previous layer's C fragments h[s] (row g: h[s][0..1], row g+8: h[s][2..3]).
+__device__ __forceinline__ void c_to_a(const float (&h)[4], int g, int t, float (&a)[4]) {
+    const int src = g * 4 + (t >> 1);
+    const bool odd = t & 1;
+    const float x0 = __shfl_sync(0xffffffffu, h[0], src), x1 = __shfl_sync(0xffffffffu, h[1], src);
+    const float x2 = __shfl_sync(0xffffffffu, h[2], src), x3 = __shfl_sync(0xffffffffu, h[3], src);
+    const float y0 = __shfl_sync(0xffffffffu, h[0], src + 2), y1 = __shfl_sync(0xffffffffu, h[1], src + 2);
+    const float y2 = __shfl_sync(0xffffffffu, h[2], src + 2), y3 = __shfl_sync(0xffffffffu, h[3], src + 2);
+    a[0] = odd ? x1 : x0;   // (row g,   col 8s + t)
+    a[1] = odd ? x3 : x2;   // (row g+8, col 8s + t)
+    a[2] = odd ? y1 : y0;   // (row g,   col 8s + t + 4)
+    a[3] = odd ? y3 : y2;   // (row g+8, col 8s + t + 4)
+}
+
 template <int C0P, int C1, int C2, int C3>
 __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, const float *__restrict__ xyz,
                                           const float *__restrict__ features, const float *sW1, const float *sb1,
                                           const float *sW2, const float *sb2, const float *sW3, const float *sb3,
                                           const float *sctr, const int *sidx, float *sout) {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // lanes per centre: 32 (nsample 17..32: idle lanes repeat sample 0, harmless for a max), 16, 8, ...
-    const int lpc = nsample > 16 ? 32 : (nsample > 8 ? 16 : 8);
-    const int cpw = 32 / lpc;                       // centres per warp pass
-    const int sub = lane / lpc, sl = lane % lpc;    // which centre of the pass, which sample lane
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const bool whole = nsample > 16;                // one centre per pass (32 rows) or two (16 rows each)
+    const int cpw = whole ? 1 : 2;
     for (int base = warp * cpw; base < nctr; base += (kMlpThreads / 32) * cpw) {
-        const int jl = min(base + sub, nctr - 1);   // tail: duplicate the last centre (its store is idempotent)
-        const int s = min(sl, nsample - 1);         // nsample <= lpc <= 32: one neighbour per lane
-        const int k = sidx[s * kStride + jl];
-        float in[C0P];
-        in[0] = __ldg(xyz + (size_t)k * 3 + 0) - sctr[jl * 3 + 0];  // grouped_xyz -= new_xyz (PB/pointnet2_utils.py:692)
-        in[1] = __ldg(xyz + (size_t)k * 3 + 1) - sctr[jl * 3 + 1];
-        in[2] = __ldg(xyz + (size_t)k * 3 + 2) - sctr[jl * 3 + 2];
+        float best[C3 / 8][2];                      // running max over the m-tiles of one centre
 #pragma unroll
-        for (int q = 3; q < C0P; q++) in[q] = (q - 3 < c) ? __ldg(features + (size_t)(q - 3) * n + k) : 0.f;
-        float h1[C1], h2[C2];
-        dense<C0P, C1, true>(sW1, sb1, in, h1);
-        dense<C1, C2, true>(sW2, sb2, h1, h2);
-        // last layer: each output channel is reduced over the neighbourhood as soon as it is computed
-#pragma unroll 4
-        for (int r = 0; r < C3; r++) {
-            float acc = sb3[r];
-            const float4 *w4 = reinterpret_cast<const float4 *>(sW3 + r * C2);
+        for (int mt = 0; mt < 2; mt++) {
+            const int jl = min(base + (whole ? 0 : mt), nctr - 1);  // tail: duplicate the last centre (idempotent store)
+            // layer-1 A fragments straight from the cloud: rows r0 = 16 mt + g and r0 + 8, columns t (and t + 4)
+            float in[2][2];
 #pragma unroll
-            for (int q = 0; q < C2 / 4; q++) {
-                const float4 w = w4[q];
-                acc = fmaf(w.x, h2[4 * q + 0], acc);
-                acc = fmaf(w.y, h2[4 * q + 1], acc);
-                acc = fmaf(w.z, h2[4 * q + 2], acc);
-                acc = fmaf(w.w, h2[4 * q + 3], acc);
+            for (int rr = 0; rr < 2; rr++) {
+                const int row = (whole ? 16 * mt : 0) + g + 8 * rr;        // neighbour slot inside the centre
+                const int k = sidx[min(row, nsample - 1) * kStride + jl];
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const int col = t + 4 * cc;
+                    float v = 0.f;
+                    if (col < 3) v = __ldg(xyz + (size_t)k * 3 + col) - sctr[jl * 3 + col];  // grouped_xyz -= new_xyz
+                    else if (col - 3 < c && col < C0P) v = __ldg(features + (size_t)(col - 3) * n + k);
+                    in[rr][cc] = v;
+                }
             }
-            float v = fmaxf(acc, 0.f);
-            for (int off = lpc >> 1; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-            if (sl == (r % lpc)) sout[r * kStride + jl] = v;
+            float h1[C1 / 8][4], h2[C2 / 8][4], h3[C3 / 8][4];
+            mma_layer<C0P, C1>(sW1, sb1, g, t, [&](int, float (&a)[4]) {
+                a[0] = in[0][0];
+                a[1] = in[1][0];
+                a[2] = in[0][1];
+                a[3] = in[1][1];
+            }, h1);
+            mma_layer<C1, C2>(sW2, sb2, g, t, [&](int s, float (&a)[4]) { c_to_a(h1[s], g, t, a); }, h2);
+            mma_layer<C2, C3>(sW3, sb3, g, t, [&](int s, float (&a)[4]) { c_to_a(h2[s], g, t, a); }, h3);
+            // max over the 16 rows of this m-tile: rows g / g+8 in the thread, then over g by shuffles
+#pragma unroll
+            for (int nt = 0; nt < C3 / 8; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    float x = fmaxf(h3[nt][e], h3[nt][2 + e]);
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+                    best[nt][e] = (whole && mt == 1) ? fmaxf(best[nt][e], x) : x;
+                }
+            if ((!whole || mt == 1) && g == 0) {
+#pragma unroll
+                for (int nt = 0; nt < C3 / 8; nt++) {
+                    sout[(nt * 8 + 2 * t) * kStride + jl] = best[nt][0];
+                    sout[(nt * 8 + 2 * t + 1) * kStride + jl] = best[nt][1];
+                }
+            }
         }
     }
 }
 
+
+// W (rows x kreal, row-major, global) -> shared memory rows of pitch wpitch(K), zero padded to K columns
+template <int K>
+__device__ __forceinline__ void stage_weights(float *sW, const float *__restrict__ W, int rows, int kreal) {
+    constexpr int WP = wpitch(K);
+    for (int i = threadIdx.x; i < rows * WP; i += kMlpThreads) {
+        const int r = i / WP, q = i - r * WP;
+        sW[i] = q < kreal ? W[r * kreal + q] : 0.f;
+    }
+}
 
 // C0P: input width padded to a multiple of 4 (3 + C real channels, rest zero weights/inputs)
 //
@@ -112,9 +216,9 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
     float *sW1 = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);  // C1 x C0P
-    float *sW2 = sW1 + C1 * C0P;                                      // C2 x C1
-    float *sW3 = sW2 + C2 * C1;                                       // C3 x C2
-    float *sb1 = sW3 + C3 * C2;
+    float *sW2 = sW1 + C1 * wpitch(C0P);                              // C2 x wpitch(C1)
+    float *sW3 = sW2 + C2 * wpitch(C1);                               // C3 x wpitch(C2)
+    float *sb1 = sW3 + C3 * wpitch(C2);
     float *sb2 = sb1 + C1;
     float *sb3 = sb2 + C2;
     float *sctr = sb3 + C3;                                           // 3 x kThreads
@@ -130,12 +234,9 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     xyz += (size_t)scene * n * 3;
     if (c > 0) features += (size_t)scene * c * n;
 
-    for (int i = t; i < C1 * C0P; i += kMlpThreads) {
-        const int r = i / C0P, q = i - r * C0P;
-        sW1[i] = q < c0 ? W1[r * c0 + q] : 0.f;
-    }
-    for (int i = t; i < C2 * C1; i += kMlpThreads) sW2[i] = W2[i];
-    for (int i = t; i < C3 * C2; i += kMlpThreads) sW3[i] = W3[i];
+    stage_weights<C0P>(sW1, W1, C1, c0);
+    stage_weights<C1>(sW2, W2, C2, C1);
+    stage_weights<C2>(sW3, W3, C3, C2);
     for (int i = t; i < C1; i += kMlpThreads) sb1[i] = b1[i];
     for (int i = t; i < C2; i += kMlpThreads) sb2[i] = b2[i];
     for (int i = t; i < C3; i += kMlpThreads) sb3[i] = b3[i];
@@ -168,7 +269,8 @@ int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const f
                   const float *features, const float *const *W, const float *const *B, float *out,
                   cudaStream_t stream) {
     const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
-                        sizeof(float) * (C1 * C0P + C2 * C1 + C3 * C2 + C1 + C2 + C3 + 3 * kThreads + C3 * kStride) +
+                        sizeof(float) * (C1 * wpitch(C0P) + C2 * wpitch(C1) + C3 * wpitch(C2) + C1 + C2 + C3 +
+                                         3 * kThreads + C3 * kStride) +
                         sizeof(int) * (size_t)nsample * kStride;
     auto kern = sa_fused_narrow_kernel<C0P, C1, C2, C3>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -194,9 +296,9 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
     float *sWa1 = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);
-    float *sWa2 = sWa1 + A1 * C0P, *sWa3 = sWa2 + A2 * A1;
-    float *sWb1 = sWa3 + A3 * A2, *sWb2 = sWb1 + B1 * C0P, *sWb3 = sWb2 + B2 * B1;
-    float *sba1 = sWb3 + B3 * B2, *sba2 = sba1 + A1, *sba3 = sba2 + A2;
+    float *sWa2 = sWa1 + A1 * wpitch(C0P), *sWa3 = sWa2 + A2 * wpitch(A1);
+    float *sWb1 = sWa3 + A3 * wpitch(A2), *sWb2 = sWb1 + B1 * wpitch(C0P), *sWb3 = sWb2 + B2 * wpitch(B1);
+    float *sba1 = sWb3 + B3 * wpitch(B2), *sba2 = sba1 + A1, *sba3 = sba2 + A2;
     float *sbb1 = sba3 + A3, *sbb2 = sbb1 + B1, *sbb3 = sbb2 + B2;
     float *sctr = sbb3 + B3;                                          // 3 x kThreads
     float *sout = sctr + 3 * kThreads;                                // (A3 + B3) x kStride
@@ -212,12 +314,12 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     xyz += (size_t)scene * n * 3;
     if (c > 0) features += (size_t)scene * c * n;
 
-    for (int i = t; i < A1 * C0P; i += kMlpThreads) sWa1[i] = (i % C0P) < c0 ? Wa1[(i / C0P) * c0 + i % C0P] : 0.f;
-    for (int i = t; i < B1 * C0P; i += kMlpThreads) sWb1[i] = (i % C0P) < c0 ? Wb1[(i / C0P) * c0 + i % C0P] : 0.f;
-    for (int i = t; i < A2 * A1; i += kMlpThreads) sWa2[i] = Wa2[i];
-    for (int i = t; i < A3 * A2; i += kMlpThreads) sWa3[i] = Wa3[i];
-    for (int i = t; i < B2 * B1; i += kMlpThreads) sWb2[i] = Wb2[i];
-    for (int i = t; i < B3 * B2; i += kMlpThreads) sWb3[i] = Wb3[i];
+    stage_weights<C0P>(sWa1, Wa1, A1, c0);
+    stage_weights<C0P>(sWb1, Wb1, B1, c0);
+    stage_weights<A1>(sWa2, Wa2, A2, A1);
+    stage_weights<A2>(sWa3, Wa3, A3, A2);
+    stage_weights<B1>(sWb2, Wb2, B2, B1);
+    stage_weights<B2>(sWb3, Wb3, B3, B2);
     for (int i = t; i < A1; i += kMlpThreads) sba1[i] = ba1[i];
     for (int i = t; i < A2; i += kMlpThreads) sba2[i] = ba2[i];
     for (int i = t; i < A3; i += kMlpThreads) sba3[i] = ba3[i];
@@ -255,8 +357,9 @@ int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns
                 const float *new_xyz, const float *features, const float *const *W, const float *const *B, float *out,
                 cudaStream_t stream) {
     const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
-                        sizeof(float) * (A1 * C0P + A2 * A1 + A3 * A2 + B1 * C0P + B2 * B1 + B3 * B2 + A1 + A2 + A3 + B1 +
-                                         B2 + B3 + 3 * kThreads + (A3 + B3) * kStride) +
+                        sizeof(float) * (A1 * wpitch(C0P) + A2 * wpitch(A1) + A3 * wpitch(A2) + B1 * wpitch(C0P) +
+                                         B2 * wpitch(B1) + B3 * wpitch(B2) + A1 + A2 + A3 + B1 + B2 + B3 + 3 * kThreads +
+                                         (A3 + B3) * kStride) +
                         sizeof(int) * (size_t)(ns_a + ns_b) * kStride;
     auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
