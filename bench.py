@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=4, help="batches in flight per GPU (ScenePipeline slots)")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs the persistent tensor-core grid leaves free for the other batches' FPS kernels (default: batch)")
+    ap.add_argument("--kernels", type=int, default=12, help="how many per-kernel rows to keep in the JSON line")
     ap.add_argument("--no-graphs", action="store_true", help="do not capture the forward in CUDA graphs")
     ap.add_argument("--tc-passes", type=int, default=None, choices=[1, 2, 3],
                     help="tensor-core product mode of our GEMM kernels: 3 = 3xTF32 (fp32-level), 2 = split-bf16 (2^-16), "
@@ -396,7 +397,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_total / args.steps},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "kernels": per_kernel[:12],
+        "kernels": per_kernel[:args.kernels],
     }
     emit(line)
     if world > 1:

@@ -139,6 +139,21 @@ int pdab_pda_group_tokens(int b, int c, int n, int m, float radius, int nsample,
                           const float *new_xyz, const float *features_t, float *out, int *idx_out,
                           pdab_stream_t stream);
 
+/* Fused PDA token encoder: ordered ball query -> gather -> density + direction -> relative position encoding ->
+ * position MLP (12 -> c/2 -> c, folded BN, ReLU) ; density / neighbourhood max -> DensityNet (1 -> 16 -> 8 -> 1, ReLU);
+ * out row = LayerNorm(cat[pos, feat * scale, feat, glob[centre]]) — the (b*m*nsample, 4c) input of the transformer.
+ * xyz (B,N,3), new_xyz (B,M,3), features_t (B,N,c) point-major, glob (B*M, c), out (B*M*nsample, 4c); c in {64, 128},
+ * nsample in {16, 32}.  params = W1 [c/2][12] | b1 [c/2] | W2^T [c/2][c] | b2 [c] | DensityNet w1[16] b1[16] w2[8][16]
+ * b2[8] w3[8] b3[1] pad[3] | gamma [4c] | beta [4c]  (pdab_pda_encode_param_floats(c) floats, 0 = unsupported c).
+ * Same results as pdab_pda_group_tokens + the two position-MLP layers + DensityNet + pdab_pda_assemble_ln_split, with
+ * all products in fp32 FMA.
+ * replaces: PB/pointnet2_utils.py:567-614 (grouper), PB/pointnet2_modules.py:893-927 (encoding, position MLP, density
+ *           re-weighting, token cat), :958-1006 (DensityNet), PB/PointFormer.py:29 (norm1). */
+size_t pdab_pda_encode_param_floats(int c);
+int pdab_pda_encode_ln(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                       const float *features_t, const float *glob, const float *params, float eps, float *out,
+                       pdab_stream_t stream);
+
 /* Row-wise kernels of the PDA block, each fused with the hi/lo split (hi = top 19 bits, exactly representable in
  * TF32; lo = value - hi) that feeds error-compensated 3xTF32 tensor-core projections.  `tokens` rows of e = 4c
  * channels (e in {256, 512}); all tensors contiguous fp32.

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "pdab_pda_group": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_pda_group_tokens": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_pda_assemble_ln_split": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "pdab_pda_encode_param_floats": (_sz, [_i]),
+    "pdab_pda_encode_ln": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
     "pdab_add_ln_split": (_i, [C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "pdab_relu_split": (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
     "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),

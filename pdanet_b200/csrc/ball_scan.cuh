@@ -135,4 +135,76 @@ __device__ __forceinline__ void ball_scan2_to_smem(int n, const float *__restric
     __syncthreads();
 }
 
+// CTA-wide scan for 32 centres (lane = centre): the cloud is cut into WARPS contiguous slices, warp w scans slice w for
+// all 32 centres (every thread of the CTA tests points, instead of one warp in WARPS), and the per-slice hit lists are
+// concatenated in slice order — the same list a single in-order scan produces, since hits are taken in index order and
+// the list stops at nsample.  All threads of the CTA (WARPS * 32) must call it.
+//   tile  : shared float4[WARPS * kSplitTile]   slist : shared int[WARPS * nsample * 33]   scnt : shared int[WARPS * 32]
+//   sidx  : shared int[nsample * STRIDE] — result, same contract as ball_scan_to_smem (slot fill, empty ball -> 0)
+constexpr int kSplitTile = 128;
+
+template <int WARPS, int STRIDE>
+__device__ __forceinline__ void ball_scan_split_to_smem(int n, const float *__restrict__ xyz, bool active, float cx,
+                                                        float cy, float cz, float r2, int nsample, float4 *tile,
+                                                        int *slist, int *scnt, int *sidx) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int seg = ((n + WARPS - 1) / WARPS + 7) & ~7;
+    const int beg = min(n, w * seg), end = min(n, beg + seg);
+    float4 *mt = tile + w * kSplitTile;
+    int *ml = slist + w * nsample * 33;
+    int cnt = active ? 0 : nsample;
+    for (int base = beg; base < end; base += kSplitTile) {
+        if (__all_sync(0xffffffffu, cnt >= nsample)) break;
+        const int len = min(kSplitTile, end - base);
+        const int len8 = (len + 7) & ~7;
+        __syncwarp();
+        for (int i = lane; i < len8; i += 32) {
+            if (i < len) {
+                const float *q = xyz + (size_t)(base + i) * 3;
+                mt[i] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+            } else {
+                mt[i] = make_float4(1e30f, 1e30f, 1e30f, 0.f);  // padding: squared distance overflows to +inf, never a hit
+            }
+        }
+        __syncwarp();
+        for (int i = 0; i < len8; i += 8) {
+            float d2[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float4 q = mt[i + u];
+                d2[u] = sqdist3(cx, cy, cz, q.x, q.y, q.z);
+            }
+            const float mn = fminf(fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])),
+                                   fminf(fminf(d2[4], d2[5]), fminf(d2[6], d2[7])));
+            if (mn < r2 && cnt < nsample) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (d2[u] < r2 && cnt < nsample) {
+                        ml[cnt * 33 + lane] = base + i + u;
+                        cnt++;
+                    }
+                }
+            }
+        }
+    }
+    scnt[w * 32 + lane] = active ? cnt : 0;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < WARPS; q++) {
+        const int c = scnt[q * 32 + lane];
+        before += q < w ? c : 0;
+        total += c;
+    }
+    if (active)
+        for (int l = 0; l < cnt && before + l < nsample; l++) sidx[(before + l) * STRIDE + lane] = ml[l * 33 + lane];
+    __syncthreads();
+    if (w == 0) {
+        total = min(total, nsample);
+        const int first = (active && total > 0) ? sidx[lane] : 0;  // empty ball: the pre-zeroed row groups point 0
+        for (int l = active ? total : 0; l < nsample; l++) sidx[l * STRIDE + lane] = first;
+    }
+    __syncthreads();
+}
+
 }  // namespace pdab

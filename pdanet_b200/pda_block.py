@@ -69,6 +69,10 @@ class PDAScalePlan:
         self.lin1 = PackedLinear(tf.linear1.weight, tf.linear1.bias, npass=npass)
         self.lin2 = PackedLinear(tf.linear2.weight, tf.linear2.bias, npass=npass)
         self.norm1, self.norm2 = tf.norm1, tf.norm2
+        # fused token encoder (csrc/pda_encode.cu): grouper + position MLP + DensityNet + token assembly + LayerNorm 1
+        self.fused_encode = True
+        self._enc_params = None
+        self._enc_src = (_fold(pm[0], pm[1]), _fold(pm[3], pm[4]), [_fold(c, b) for c, b in zip(dn.mlp_convs, dn.mlp_bns)])
 
     @torch.no_grad()
     def __call__(self, ops, xyz, new_xyz, features_t, centre_feature_t):
@@ -77,6 +81,15 @@ class PDAScalePlan:
         ns = self.ns
         C = features_t.shape[2]
         G, T = B * M, B * M * ns
+        if self.fused_encode and hasattr(ops, "pda_encode_ln") and ops.pda_encode_supported(C, ns):
+            if self._enc_params is None:
+                (w1, b1), (w2, b2), dens_layers = self._enc_src
+                self._enc_params = ops.pda_encode_params(w1, b1, w2, b2, dens_layers, self.norm1.weight, self.norm1.bias)
+            glob = torch.cat([new_xyz.reshape(G, 3), centre_feature_t.reshape(G, C)], dim=1)
+            glob = F.relu_(self.global_[1](F.relu_(self.global_[0](glob))))
+            y = ops.pda_encode_ln(self.radius, ns, xyz, new_xyz, features_t, glob, self._enc_params, self.norm1.eps)
+            return self._transformer(ops, y, B, M, ns)
+
         X = ops.pda_group_tokens(self.radius, ns, xyz, new_xyz, features_t).view(T, 8 + C)
         nbr, dens, direction = X[:, 0:3], X[:, 3], X[:, 4:7]
 
@@ -97,7 +110,9 @@ class PDAScalePlan:
 
         # token assembly + LayerNorm 1 in one pass (csrc/pda_elem.cu)
         y = ops.pda_assemble_ln(pos, X, scale.reshape(T), glob, ns, self.norm1)
+        return self._transformer(ops, y, B, M, ns)
 
+    def _transformer(self, ops, y, B, M, ns):
         # pre-norm transformer over each neighbourhood (PB/PointFormer.py:28-38); residuals follow the LayerNorms
         qkv = self.in_proj(y, EPI_STORE)                                        # (T, 3E)
         ctx = ops.group_attention(qkv, ns, self.heads)                          # (T, E)

@@ -267,6 +267,45 @@ def pda_group_tokens(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
     return (out, idx) if return_idx else out
 
 
+def pda_encode_supported(c: int, nsample: int) -> bool:
+    """Shapes the fused token encoder covers (csrc/pda_encode.cu)."""
+    return c in (64, 128) and nsample in (16, 32)
+
+
+def pda_encode_params(w1, b1, w2, b2, dens, gamma, beta) -> torch.Tensor:
+    """Pack the parameters of `pda_encode_ln` (layout in include/pdab.h): position MLP (w1 (C/2,12), b1, w2 (C,C/2), b2),
+    DensityNet [(w (16,1), b), (w (8,16), b), (w (1,8), b)], LayerNorm gamma / beta (4C)."""
+    C = w2.shape[0]
+    assert w1.shape == (C // 2, 12) and w2.shape == (C, C // 2) and gamma.numel() == 4 * C
+    (dw1, db1), (dw2, db2), (dw3, db3) = dens
+    assert dw1.shape == (16, 1) and dw2.shape == (8, 16) and dw3.shape == (1, 8)
+    parts = [w1.reshape(-1), b1, w2.t().contiguous().reshape(-1), b2, dw1.reshape(-1), db1, dw2.reshape(-1), db2,
+             dw3.reshape(-1), db3.reshape(-1), torch.zeros(3, device=w1.device), gamma, beta]
+    out = torch.cat([q.detach().float().reshape(-1) for q in parts]).contiguous()
+    assert out.numel() == _lib.lib().pdab_pda_encode_param_floats(C)
+    return out
+
+
+def pda_encode_ln(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, features_t: torch.Tensor,
+                  glob: torch.Tensor, params: torch.Tensor, eps: float) -> torch.Tensor:
+    """Fused PDA token encoder (forward only): LayerNorm(cat[pos, feat*scale, feat, glob]) per (centre, neighbour)
+    token, (B*M*nsample, 4C); see include/pdab.h `pdab_pda_encode_ln`."""
+    for t in (xyz, new_xyz, features_t, glob, params):
+        if not t.is_cuda:
+            raise RuntimeError("pda_encode_ln needs CUDA tensors")
+        assert t.is_contiguous() and t.dtype == torch.float32
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = features_t.shape[2]
+    assert glob.shape == (B * M, C)
+    y = torch.empty(B * M * nsample, 4 * C, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.call("pdab_pda_encode_ln", B, C, N, M, float(radius), nsample, xyz.data_ptr(), new_xyz.data_ptr(),
+                  features_t.data_ptr(), glob.data_ptr(), params.data_ptr(), float(eps), y.data_ptr(),
+                  torch.cuda.current_stream(xyz.device).cuda_stream)
+    return y
+
+
 def _stream_of(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 

@@ -185,6 +185,49 @@ def test_pda_group_tokens_matches_channel_major_grouper():
         assert (tok[..., 7] == 0).all()
 
 
+def test_pda_encode_ln_matches_unfused_chain():
+    """Fused token encoder (csrc/pda_encode.cu) vs a float64 torch statement of the same chain built on the exact
+    grouper kernel's indices: ball query order, density, direction, position MLP, DensityNet, token cat, LayerNorm.
+    Ragged M (not a multiple of the CTA's centre count), empty balls (far-away centres) and both widths."""
+    from pdanet_b200 import pointnet2_utils as ops
+    g = torch.Generator().manual_seed(7)
+    for B, C, N, M, r, ns in [(2, 64, 4096, 1000, 0.8, 16), (3, 64, 2048, 77, 1.6, 32), (2, 128, 1024, 300, 4.8, 32),
+                              (16, 128, 1024, 512, 2.4, 16)]:
+        xyz = (torch.rand(B, N, 3, generator=g) * torch.tensor([30.0, 30.0, 2.0])).cuda()
+        feats_t = torch.randn(B, N, C, generator=g).cuda()
+        new_xyz = xyz[:, :M].clone()
+        new_xyz[:, -1] = xyz[:, 0]                     # an empty ball (above the cloud, farther than r from every
+        new_xyz[:, -1, 2] = 2.0 + 1.01 * r             # point): groups point 0, the pre-zeroed idx row
+        glob = torch.randn(B * M, C, generator=g).cuda()
+        H = C // 2
+        w1, b1 = torch.randn(H, 12, generator=g).cuda() * 0.3, torch.randn(H, generator=g).cuda() * 0.1
+        w2, b2 = torch.randn(C, H, generator=g).cuda() * 0.2, torch.randn(C, generator=g).cuda() * 0.1
+        dens = [(torch.randn(16, 1, generator=g).cuda(), torch.rand(16, generator=g).cuda()),
+                (torch.randn(8, 16, generator=g).cuda() * 0.5, torch.rand(8, generator=g).cuda()),
+                (torch.randn(1, 8, generator=g).cuda().abs(), torch.rand(1, generator=g).cuda())]
+        gamma, beta = torch.rand(4 * C, generator=g).cuda() + 0.5, torch.randn(4 * C, generator=g).cuda() * 0.1
+        params = ops.pda_encode_params(w1, b1, w2, b2, dens, gamma, beta)
+        y = ops.pda_encode_ln(r, ns, xyz, new_xyz, feats_t, glob, params, 1e-5)
+
+        X, idx = ops.pda_group_tokens(r, ns, xyz, new_xyz, feats_t, return_idx=True)
+        assert (idx[:, -1] == 0).all()
+        T = B * M * ns
+        d = lambda t: t.double()
+        Xd = d(X.view(T, 8 + C))
+        nbr, den, direction, f = Xd[:, 0:3], Xd[:, 3], Xd[:, 4:7], Xd[:, 8:]
+        ctr = d(new_xyz).reshape(B * M, 1, 3).expand(B * M, ns, 3).reshape(T, 3)
+        rppe = torch.cat([ctr, nbr, ctr - nbr, direction], dim=1)
+        pos = torch.relu(torch.relu(rppe @ d(w1).t() + d(b1)) @ d(w2).t() + d(b2))
+        dg = den.view(B * M, ns)
+        sc = (dg / dg.max(dim=1, keepdim=True)[0]).reshape(T, 1)
+        for w, b in dens:
+            sc = torch.relu(sc @ d(w).t() + d(b))
+        tok = torch.cat([pos, f * sc, f, d(glob).repeat_interleave(ns, dim=0)], dim=1)
+        want = torch.nn.functional.layer_norm(tok, (4 * C,), d(gamma), d(beta), 1e-5)
+        err = (d(y) - want).abs().max().item()
+        assert err <= 2e-5 * want.abs().max().item(), (B, C, N, M, ns, err)
+
+
 @pytest.mark.parametrize("graphs", [True, False])
 def test_pipelined_runner_equals_sequential_runner(graphs):
     """ScenePipeline (2 batches in flight, CUDA graphs, padded sync-free post-processing) returns exactly what
