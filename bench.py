@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=4, help="batches in flight per GPU (ScenePipeline slots)")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight per GPU (ScenePipeline slots)")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs the persistent tensor-core grid leaves free for the other batches' FPS kernels (default: batch)")
     ap.add_argument("--kernels", type=int, default=12, help="how many per-kernel rows to keep in the JSON line")
@@ -183,9 +183,10 @@ def algorithmic_bytes(key: str, batch: int):
         return b * (4 * n * c + 4 * k)
     if name == "pdab_tc_linear":
         rows, k, nout, npass, bn, epi = a[:6]
-        out_rows = rows if epi < 3 else rows // 16       # max-pool epilogues write one row per neighbourhood
+        out_rows = rows if epi not in (3, 4) else rows // 16   # max-pool epilogues write one row per neighbourhood
+        out_cols = nout // 3 if epi == 5 else nout             # attention epilogue: only ctx (rows, E) is written
         resid = rows * nout * 4 if epi in (2, 3) else 0
-        return rows * k * 4 + out_rows * nout * 4 + resid + nout * k * 4 * (2 if npass == 3 else 1)
+        return rows * k * 4 + out_rows * out_cols * 4 + resid + nout * k * 4 * (2 if npass == 3 else 1)
     if name == "pdab_tc_sa_gather_linear":
         b, c, n, m, ns, nout = a[:6]
         return b * (4 * c * n + 12 * n + 12 * m + 4 * m * ns) + b * m * ns * nout * 4

@@ -214,6 +214,12 @@ int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a
 #define PDAB_EPI_ADD_LN 2       /* out = LayerNorm(acc + bias + residual) over the full row (nout in {256, 512}) */
 #define PDAB_EPI_ADD_MAXPOOL 3  /* out[g] = max over the nsample rows of group g of (acc + bias + residual) */
 #define PDAB_EPI_RELU_MAXPOOL 4 /* out[g] = max over the nsample rows of group g of relu(acc + bias) */
+#define PDAB_EPI_ATTN 5         /* in_proj + neighbourhood self-attention (head_dim 64): W rows grouped head by head,
+                                 * [q_h | k_h | v_h] = one bn = 192 chunk per head (nout = 3E); out (rows, E) =
+                                 * softmax(q k^T / 8) v inside each group of nsample consecutive rows, heads
+                                 * concatenated — pdab_tc_linear(STORE) + pdab_group_attention in one kernel, the
+                                 * (rows, 3E) qkv matrix is never stored.  replaces: nn.MultiheadAttention in_proj +
+                                 * attention core, PB/PointFormer.py:30 */
 
 /* out = epilogue(a (rows,k) . W (nout,k)^T + bias) on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
  * fp32 accumulation in TMEM).  npass = 1: operands rounded to TF32 (the precision class of the reference's cuDNN
@@ -224,7 +230,7 @@ int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a
  *           of TransformerEncoderLayerPreNorm with the LayerNorm / residual / ReLU / max-pool between them,
  *           PB/PointFormer.py:28-38, PB/pointnet2_modules.py:929-931.
  * a (rows, lda) fp32; w_packed: W pre-packed by pdab_tc_pack_weights (bn = 128 or 256 columns per accumulator
- * chunk); bias (nout) or NULL; residual (rows, ldr) for the ADD_* epilogues; gamma/beta/eps for ADD_LN;
+ * chunk; 192 for PDAB_EPI_ATTN); bias (nout) or NULL; residual (rows, ldr) for the ADD_* epilogues; gamma/beta/eps for ADD_LN;
  * nsample in {16, 32} for the *_MAXPOOL epilogues (rows % nsample == 0; out has rows / nsample rows).
  * k, lda, ldo, ldr, nout multiples of 4; all pointers 16-byte aligned. */
 int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilogue, const float *a, int lda,

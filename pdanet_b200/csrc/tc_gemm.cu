@@ -32,6 +32,8 @@
 // row for the LayerNorm epilogue) so the epilogue of item i overlaps the main loop of item i+1.
 // Weights are packed once (host side, pdanet_b200/tc_pack.py) into the exact smem image of each (column chunk, k-atom)
 // tile — canonical K-major SWIZZLE_128B layout — so a stage's weights are ONE contiguous bulk copy.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -47,7 +49,8 @@ constexpr int kTmemCols = 512;
 constexpr int kStgPitch = 36;       // floats per row of an epilogue staging tile (32 + 4: 16-byte aligned, conflict-free)
 
 enum ALoad { A_ROWS = 0, A_GATHER = 1 };
-enum Epi { E_STORE = 0, E_RELU = 1, E_ADD_LN = 2, E_ADD_MAXPOOL = 3, E_RELU_MAXPOOL = 4 };
+enum Epi { E_STORE = 0, E_RELU = 1, E_ADD_LN = 2, E_ADD_MAXPOOL = 3, E_RELU_MAXPOOL = 4, E_ATTN = 5 };
+constexpr int kAttnVP = 68;         // floats per row of the attention epilogue's V staging tile (64 + 4: conflict-free B fragments)
 
 struct GemmParams {
     // A operand
@@ -318,7 +321,17 @@ __device__ __forceinline__ float tf32_rna(float v) {
 // CG = 1: one CTA per SM, M = 128.  CG = 2: CTA pair (cta_group::2), M = 256: each CTA produces its own 128 rows of A and
 // holds HALF of the W tile (rows [rank * BN/2, +BN/2) of the chunk); the tensor cores of the pair read both halves, so
 // per SM the MMA reads 8 KB of shared memory instead of 12 KB and receives half the weight bytes from L2.
-template <int NPASS, int BN, int CG>
+// EW: epilogue warps per CTA.  4 = one per TMEM lane quadrant.  8 (CTA pairs, attention epilogue) = two per quadrant,
+// each owning one 16-row m-tile; the CTA then has 16 warps = 4 warpgroups and the register file is re-divided with
+// setmaxnreg: the two warpgroups that hold the loader / MMA / A-producer warps grow to kProdRegs, the two epilogue
+// warpgroups shrink to kEpiRegs (128 * 2 * 152 + 128 * 2 * 104 = 65536).
+constexpr int kProdRegs = 152, kEpiRegs = 104;
+template <int EPI, int CG>
+struct EpiWarps {
+    static constexpr int value = (EPI == 5 /*E_ATTN*/ && CG == 2) ? 8 : 4;
+};
+
+template <int NPASS, int BN, int CG, int EW = 4>
 struct Cfg {
     static constexpr int W_TILE_BYTES = BN * 128 / CG;                     // one of {hi, lo}, per CTA
     static constexpr int STAGE_BYTES = (NPASS >= 2 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
@@ -329,9 +342,12 @@ struct Cfg {
     static constexpr int STAGES = CG == 2 ? (STAGES_RAW >= 6 ? 6 : 3) : (STAGES_RAW >= 4 ? 4 : 2);
     static constexpr int GROUPS = CG == 2 ? 3 : STAGES;
     static constexpr int PRODUCER_WARPS = CG == 2 ? 6 : 8;
-    static constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + 4);
+    static constexpr int EPI_WARPS = EW;
+    static constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + EW);
+    // BN = 192 is the attention epilogue (one head of [Q | K | V], head_dim 64, per chunk): + a V staging tile per warp
+    static constexpr int ATTN_BYTES = BN == 192 ? 4 * 32 * kAttnVP * 4 : 0;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/;
+                                      4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/ + ATTN_BYTES;
 };
 
 struct Pipe {
@@ -347,8 +363,9 @@ struct Pipe {
 };
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
-__global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel(const GemmParams p) {
-    using C = Cfg<NPASS, BN, CG>;
+__global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::THREADS, 1) tc_gemm_kernel(const GemmParams p) {
+    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>;
+    constexpr int EW = C::EPI_WARPS;
     constexpr int S = C::STAGES;
     constexpr int kThreads = C::THREADS, kProducerWarps = C::PRODUCER_WARPS;
     // CTA pair: rank 0 (leader) issues the MMAs for both SMs; work items are 256-row tiles, 128 rows per CTA
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), 4 * CG);
+            mbar_init(acc_empty(a), EW * CG);
         }
         fence_barrier_init();
     }
@@ -409,10 +426,17 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
     __syncthreads();
     tc_fence_after();
     const u32 tmem_base = *tmem_slot_ptr;
-
     const int KA = p.KA;
     const long long n_items = p.n_items;
 
+    // EW = 8: warps 0-7 (loader, MMA, 6 producers) and warps 8-15 (epilogue) are two pairs of warpgroups; each side
+    // re-sizes its registers INSIDE its own branch, so that the setmaxnreg dominates the code it governs (ptxas bounds
+    // the registers of a region by the setmaxnreg that dominates it) and a warpgroup executes one and the same instruction.
+    if (warp < 2 + kProducerWarps) {
+    if constexpr (EW == 8) {
+        static_assert(EW != 8 || C::PRODUCER_WARPS == 6, "register re-division assumes 4 warpgroups");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
+    }
     if (warp == 0) {
         // ===================================================================== W loader
         if (lane == 0) {
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
             constexpr int PARTS = NPASS >= 2 ? 2 : 1;
             constexpr u32 BYTES = PARTS * C::W_TILE_BYTES;          // bytes this CTA receives per stage
             constexpr size_t TILE = (size_t)PARTS * BN * 128;        // packed bytes of one (chunk, k-atom) tile
-            constexpr u32 PIECE = C::W_TILE_BYTES < 8192 ? C::W_TILE_BYTES : 8192;
+            constexpr u32 PIECE = C::W_TILE_BYTES < 8192 ? C::W_TILE_BYTES : (C::W_TILE_BYTES % 8192 ? 4096 : 8192);
             for (long long item = item0; item < n_items; item += item_step) {
                 const int n_group = (int)(item % p.n_groups);
                 for (int c = 0; c < NCH; c++) {
@@ -513,7 +537,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                 }
             }
         }
-    } else if (warp < 2 + kProducerWarps) {
+    } else {
         // ===================================================================== A producers (G groups of 8/G warps)
         // Group g owns k-atom steps g, g+G, g+2G, ... of this CTA's flattened (item, chunk pass, k-atom) sequence and
         // has exactly ONE batch of loads in flight per thread; the G groups together keep G k-atoms (16 KB each) in
@@ -621,7 +645,9 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                 else mbar_arrive(full_a(stage));
             }
         }
+    }
     } else {
+        if constexpr (EW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
         // ===================================================================== epilogue (128 threads)
         // The accumulator is read with the 16x256b TMEM load shape, which hands out an MMA-C-fragment layout: for a
         // 32-row x 32-column block, lane (fr = lane / 4, fc = 2 * (lane % 4)) holds rows 16 h + 8 j + fr (h, j in {0,1})
@@ -631,11 +657,11 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
         // version used the 32x32b shape — thread = row — and staged every block through shared memory twice; it was
         // instruction- and latency-bound: profiles/r01_ncu_tc_gemm_*.)
         const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-        const int ew = warp - (2 + kProducerWarps);   // 0..3
+        const int ew = warp - (2 + kProducerWarps);   // 0..EW-1 (EW = 8: ew & 3 == q, ew >> 2 = the warp's m-tile)
         const int fr = lane >> 2, fc = (lane & 3) * 2;
         // Per-column parameters live in shared memory: with ~200 KB of it carved out the L1 is a few KB and thrashed by
         // the A stream, so an __ldg of bias / gamma / beta inside the block loop was an L2 round trip on the critical path.
-        float *sbias = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + ew * 512;
+        float *sbias = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + ew * (2048 / EW);
         const float *sgamma = reinterpret_cast<const float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512;
         const float *sbeta = sgamma + 512;
         int as = 0;
@@ -884,13 +910,240 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG>::THREADS, 1) tc_gemm_kernel
                     }
                     store_tile(v, p.out, p.ldo, wrow0, p.T, j0);
                 }
+            } else if (EPI == E_ATTN) {
+                // One attention head per item: accumulator columns [0, HD) = Q, [HD, 2 HD) = K, [2 HD, 3 HD) = V of the
+                // quadrant's 32 tokens = one neighbourhood of 32 or two of 16 (the in_proj weight rows are permuted head
+                // by head on the host).  ctx = softmax(Q K^T / sqrt(HD)) V is computed here and only ctx (rows, heads * HD)
+                // is stored: the (rows, 3E) qkv matrix never exists.  Both contractions are 32 x 32 x HD per quadrant —
+                // far below a tcgen05 tile — so they run on mma.sync m16n8k8 TF32 with the 3x hi/lo compensation, fed
+                // straight from the TMEM fragments: the 16x256b load hands out C fragments (row g: columns 2t, 2t+1),
+                // which ARE A fragments (row g: k = t, t + 4) and B fragments (column n = g: k = t, t + 4) of the next
+                // MMA under the k-permutation t -> 2t, t + 4 -> 2t + 1, applied to both operands.  Only V, whose rows
+                // become the contraction index, goes through a shared-memory tile per quadrant.
+                // A warp owns MTW 16-row m-tiles of its quadrant: both (EW = 4) or one (EW = 8: two warps per quadrant).
+                // The k-bias is dropped (a per-row constant of the scores cancels in the softmax) and the v-bias is added
+                // to the output (the rows of P sum to one).
+                constexpr int HD = BN / 3;
+                static_assert(EPI != E_ATTN || (HD == 64 && NCH == 1), "attention epilogue: head_dim 64, one head per chunk");
+                constexpr int MTW = 8 / EW;                      // m-tiles per warp
+                const int mt0 = EW == 8 ? (ew >> 2) : 0;         // first m-tile of this warp
+                const int ns = p.ns;
+                const int g = fr, t2 = fc;  // fragment coordinates: row g, column pair t2 = 2 (lane % 4)
+                float *sV = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512 + 2 * 512 + q * 32 * kAttnVP;
+                auto split = [](float x, u32 &hi, u32 &lo) {
+                    hi = __float_as_uint(x) & 0xffffe000u;
+                    lo = __float_as_uint(x - __uint_as_float(hi));
+                };
+                auto mma = [](float (&d)[4], const u32 (&a)[4], const u32 (&b)[2]) {
+                    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                        "{%0,%1,%2,%3};"
+                        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+                };
+                auto pair_sync = [&]() {  // the two warps of a quadrant (EW = 8)
+                    if (EW == 8) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    else __syncwarp();
+                };
+                // FULL: one neighbourhood of 32 rows; otherwise two of 16 (each m-tile attends to its own 16 keys).  Compiled
+                // twice so that the MMA sweeps are branch-free and the scheduler can interleave them.
+                auto attend = [&](auto full_tag) {
+                    constexpr bool FULL = decltype(full_tag)::value;
+                    constexpr int NTW = FULL ? 4 : 2;            // key n-tiles per m-tile
+                    constexpr int KH = FULL ? 2 : MTW;           // 16-row halves of K this warp reads
+                    // ---- scores sc[mi][ni] : rows 16 (mt0 + mi) + {g, g + 8}, keys 8 nt + {t2, t2 + 1}
+                    // (two accumulator sets, even / odd k-steps: the tensor pipe is shared with the tcgen05 MMAs of the next
+                    // item, a dependent mma.sync waits ~100 cycles, so the epilogue is bound by its dependency chains)
+                    float sc[MTW][NTW][4], sc2[MTW][NTW][4];
+#pragma unroll
+                    for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                            for (int e = 0; e < 4; e++) sc[mi][ni][e] = sc2[mi][ni][e] = 0.f;
+#pragma unroll 1
+                    for (int kb = 0; kb < HD; kb += 32) {
+                        float qf[MTW][16], kf[KH][16];
+#pragma unroll
+                        for (int mi = 0; mi < MTW; mi++) tmem_ld_16x256b_x4(tacc + ((u32)(16 * (mt0 + mi)) << 16) + kb, qf[mi]);
+#pragma unroll
+                        for (int kh = 0; kh < KH; kh++)
+                            tmem_ld_16x256b_x4(tacc + ((u32)(16 * (FULL ? kh : mt0 + kh)) << 16) + HD + kb, kf[kh]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float2 bq = *reinterpret_cast<const float2 *>(sbias + kb + 8 * k + t2);
+                            u32 ah[MTW][4], al[MTW][4];
+#pragma unroll
+                            for (int mi = 0; mi < MTW; mi++) {
+                                split(qf[mi][4 * k + 0] + bq.x, ah[mi][0], al[mi][0]);   // (g,     k = t)
+                                split(qf[mi][4 * k + 2] + bq.x, ah[mi][1], al[mi][1]);   // (g + 8, k = t)
+                                split(qf[mi][4 * k + 1] + bq.y, ah[mi][2], al[mi][2]);   // (g,     k = t + 4)
+                                split(qf[mi][4 * k + 3] + bq.y, ah[mi][3], al[mi][3]);   // (g + 8, k = t + 4)
+                            }
+                            // B fragments of n-tile (half kh, sub-tile e): rows 16 kh + 8 e + g of K
+                            u32 bh[KH][2][2], bl[KH][2][2];
+#pragma unroll
+                            for (int kh = 0; kh < KH; kh++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    split(kf[kh][4 * k + 2 * e], bh[kh][e][0], bl[kh][e][0]);
+                                    split(kf[kh][4 * k + 2 * e + 1], bh[kh][e][1], bl[kh][e][1]);
+                                }
+                            // the three compensation terms as three sweeps over the independent accumulators (small
+                            // terms first), so that dependent MMAs on one accumulator are several instructions apart
+#pragma unroll
+                            for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+                                for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                                    for (int mi = 0; mi < MTW; mi++) {
+                                        const int kh = FULL ? (ni >> 1) : mi;
+                                        mma((k & 1) ? sc2[mi][ni] : sc[mi][ni], pass == 1 ? al[mi] : ah[mi],
+                                            pass == 0 ? bl[kh][ni & 1] : bh[kh][ni & 1]);
+                                    }
+                        }
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                            for (int e = 0; e < 4; e++) sc[mi][ni][e] += sc2[mi][ni][e];
+                    // ---- V -> the quadrant's staging tile [token][channel]; then the accumulator stage is free
+                    pair_sync();  // (EW = 8) the other warp has finished reading the tile for the previous item
+#pragma unroll
+                    for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+                        for (int cb = 0; cb < HD; cb += 32) {
+                            float v[16];
+                            tmem_ld_16x256b_x4(tacc + ((u32)(16 * (mt0 + mi)) << 16) + 2 * HD + cb, v);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+#pragma unroll
+                                for (int j = 0; j < 2; j++)
+                                    *reinterpret_cast<float2 *>(sV + (16 * (mt0 + mi) + 8 * j + g) * kAttnVP + cb + 8 * k + t2) =
+                                        make_float2(v[4 * k + 2 * j], v[4 * k + 2 * j + 1]);
+                        }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2 && !leader) mbar_arrive_remote(acc_empty(as), 0);
+                        else mbar_arrive(acc_empty(as));
+                    }
+                    // ---- softmax over the keys of each row (a row's values live in one quad); fp32, full-precision expf.
+                    // The head_dim ** -0.5 factor PyTorch applies to q is applied to the scores (one rounding later).
+                    constexpr float scaling = 0.125f;
+#pragma unroll
+                    for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            float mx = -3.4e38f;
+#pragma unroll
+                            for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    sc[mi][ni][2 * r + e] *= scaling;
+                                    mx = fmaxf(mx, sc[mi][ni][2 * r + e]);
+                                }
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                            float sum = 0.f;
+#pragma unroll
+                            for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    sc[mi][ni][2 * r + e] = expf(sc[mi][ni][2 * r + e] - mx);
+                                    sum += sc[mi][ni][2 * r + e];
+                                }
+                            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                            const float inv = 1.0f / sum;
+#pragma unroll
+                            for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) sc[mi][ni][2 * r + e] *= inv;
+                        }
+                    if (FULL) pair_sync();  // all 32 rows of V staged (two 16-row neighbourhoods read only their own rows)
+                    else __syncwarp();
+                    // ---- ctx = P V + bias_v : contraction over the keys; 32 output channels at a time
+                    float *obase = p.out + (size_t)n_group * HD;
+#pragma unroll
+                    for (int nb = 0; nb < HD / 32; nb++) {   // (unrolled: the two channel halves are independent chains)
+                        float o[MTW][4][4];
+#pragma unroll
+                        for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+                            for (int n4 = 0; n4 < 4; n4++) o[mi][n4][0] = o[mi][n4][1] = o[mi][n4][2] = o[mi][n4][3] = 0.f;
+                        auto bfrag = [&](int ks, u32 (&bh)[4][2], u32 (&bl)[4][2]) {
+#pragma unroll
+                            for (int n4 = 0; n4 < 4; n4++) {
+                                split(sV[(8 * ks + t2) * kAttnVP + 32 * nb + 8 * n4 + g], bh[n4][0], bl[n4][0]);
+                                split(sV[(8 * ks + t2 + 1) * kAttnVP + 32 * nb + 8 * n4 + g], bh[n4][1], bl[n4][1]);
+                            }
+                        };
+                        auto afrag = [&](const float (&pf)[4], u32 (&ah)[4], u32 (&al)[4]) {
+                            split(pf[0], ah[0], al[0]);
+                            split(pf[2], ah[1], al[1]);
+                            split(pf[1], ah[2], al[2]);
+                            split(pf[3], ah[3], al[3]);
+                        };
+#pragma unroll
+                        for (int ksl = 0; ksl < NTW; ksl++) {
+                            if constexpr (FULL) {
+                                u32 bh[4][2], bl[4][2], ah[MTW][4], al[MTW][4];
+                                bfrag(ksl, bh, bl);
+#pragma unroll
+                                for (int mi = 0; mi < MTW; mi++) afrag(sc[mi][ksl], ah[mi], al[mi]);
+#pragma unroll
+                                for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+                                    for (int n4 = 0; n4 < 4; n4++)
+#pragma unroll
+                                        for (int mi = 0; mi < MTW; mi++)
+                                            mma(o[mi][n4], pass == 1 ? al[mi] : ah[mi], pass == 0 ? bl[n4] : bh[n4]);
+                            } else {
+#pragma unroll
+                                for (int mi = 0; mi < MTW; mi++) {
+                                    u32 bh[4][2], bl[4][2], ah[4], al[4];
+                                    bfrag(2 * (mt0 + mi) + ksl, bh, bl);
+                                    afrag(sc[mi][ksl], ah, al);
+#pragma unroll
+                                    for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+                                        for (int n4 = 0; n4 < 4; n4++)
+                                            mma(o[mi][n4], pass == 1 ? al : ah, pass == 0 ? bl[n4] : bh[n4]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+                            for (int r = 0; r < 2; r++) {
+                                const long long row = wrow0 + 16 * (mt0 + mi) + 8 * r + g;
+                                if (row < p.T) {
+#pragma unroll
+                                    for (int n4 = 0; n4 < 4; n4++) {
+                                        const float2 bv = *reinterpret_cast<const float2 *>(sbias + 2 * HD + 32 * nb + 8 * n4 + t2);
+                                        *reinterpret_cast<float2 *>(obase + row * p.ldo + 32 * nb + 8 * n4 + t2) =
+                                            make_float2(o[mi][n4][2 * r] + bv.x, o[mi][n4][2 * r + 1] + bv.y);
+                                    }
+                                }
+                            }
+                    }
+                };
+                if (ns == 32) attend(std::true_type{});
+                else attend(std::false_type{});
+                __syncwarp();  // sbias and (EW = 4) the staging tile are rewritten for the next item
             }
 
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CG == 2 && !leader) mbar_arrive_remote(acc_empty(as), 0);
-                else mbar_arrive(acc_empty(as));
+            if (EPI != E_ATTN) {  // (the attention epilogue released its accumulator stage as soon as V was staged)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2 && !leader) mbar_arrive_remote(acc_empty(as), 0);
+                    else mbar_arrive(acc_empty(as));
+                }
             }
             if (ACC_STAGES == 2) {
                 as ^= 1;
@@ -918,7 +1171,7 @@ int g_cta_pairs = 1;
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
 int launch_cg(GemmParams p, cudaStream_t s) {
-    using C = Cfg<NPASS, BN, CG>;
+    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>;
     auto kern = tc_gemm_kernel<NPASS, BN, NCH, ALOAD, EPI, CG>;
     static bool configured = false;  // per instantiation
     if (!configured) {
@@ -967,6 +1220,11 @@ int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
         return launch<NPASS, 256, 2, A_ROWS, E_ADD_LN>(p, s);
     }
     items(1);
+    if (epi == E_ATTN) {
+        if (ALOAD != A_ROWS || bn != 192 || p.Nout % 192) return PDAB_EUNSUPPORTED;
+        return launch<NPASS, 192, 1, A_ROWS, E_ATTN>(p, s);
+    }
+    if (bn == 192 && epi == E_STORE && ALOAD == A_ROWS) return launch<NPASS, 192, 1, A_ROWS, E_STORE>(p, s);
     if (bn == 256) {
         switch (epi) {
             case E_STORE: return launch<NPASS, 256, 1, ALOAD, E_STORE>(p, s);
@@ -1008,7 +1266,9 @@ extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn
     if ((k & 3) || (lda & 3) || (ldo & 3) || (nout & 3) || lda < k) return PDAB_EINVAL;
     if (npass < 1 || npass > 3) return PDAB_EINVAL;
     if (npass == 2 && (k & 7)) return PDAB_EINVAL;
-    if (bn != 128 && bn != 256) return PDAB_EINVAL;
+    if (bn != 128 && bn != 256 && !(bn == 192 && (epilogue == E_ATTN || epilogue == E_STORE))) return PDAB_EINVAL;
+    if (epilogue == E_ATTN && (bn != 192 || nout % 192 || (nsample != 16 && nsample != 32) || rows % nsample))
+        return PDAB_EUNSUPPORTED;
     if ((epilogue == E_ADD_LN || epilogue == E_ADD_MAXPOOL) && (!residual || (ldr & 3))) return PDAB_EINVAL;
     if (epilogue == E_ADD_LN && (!gamma || !beta)) return PDAB_EINVAL;
     if ((epilogue == E_ADD_MAXPOOL || epilogue == E_RELU_MAXPOOL) && ((nsample != 16 && nsample != 32) || rows % nsample))

@@ -71,7 +71,7 @@ extern "C" size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn) {
 extern "C" int pdab_tc_pack_weights(int nout, int k, int npass, int bn, int xyz_last, const float *w, float *packed,
                                     pdab_stream_t stream) {
     if (nout < 1 || k < 1 || !w || !packed || xyz_last < 0 || xyz_last > k) return PDAB_EINVAL;
-    if (npass < 1 || npass > 3 || (bn != 128 && bn != 256)) return PDAB_EINVAL;
+    if (npass < 1 || npass > 3 || (bn != 128 && bn != 192 && bn != 256)) return PDAB_EINVAL;
     const long long total = (long long)pdab_tc_packed_floats(nout, k, npass, bn);
     const long long blocks = (total + 255) / 256;
     pack_kernel<<<(unsigned)blocks, 256, 0, pdab::to_stream(stream)>>>(nout, k, npass, bn, xyz_last, w, packed, total);

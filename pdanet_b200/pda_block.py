@@ -25,7 +25,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from .tc_linear import (EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_RELU, EPI_STORE, PackedLinear)
+from .tc_linear import (EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_ATTN, EPI_RELU, EPI_STORE, PackedLinear, attn_in_proj)
 
 
 class LinearExact:
@@ -65,6 +65,10 @@ class PDAScalePlan:
         attn = tf.self_attn
         self.heads = attn.num_heads
         self.in_proj = PackedLinear(attn.in_proj_weight, attn.in_proj_bias, npass=npass)
+        # head_dim 64: in_proj and the attention core are ONE kernel (attention in the GEMM epilogue, qkv never stored)
+        self.fused_attention = attn.embed_dim // attn.num_heads == 64
+        self.in_proj_attn = (attn_in_proj(attn.in_proj_weight, attn.in_proj_bias, attn.num_heads, npass=npass)
+                             if self.fused_attention else None)
         self.out_proj = PackedLinear(attn.out_proj.weight, attn.out_proj.bias, npass=npass)
         self.lin1 = PackedLinear(tf.linear1.weight, tf.linear1.bias, npass=npass)
         self.lin2 = PackedLinear(tf.linear2.weight, tf.linear2.bias, npass=npass)
@@ -114,8 +118,11 @@ class PDAScalePlan:
 
     def _transformer(self, ops, y, B, M, ns):
         # pre-norm transformer over each neighbourhood (PB/PointFormer.py:28-38); residuals follow the LayerNorms
-        qkv = self.in_proj(y, EPI_STORE)                                        # (T, 3E)
-        ctx = ops.group_attention(qkv, ns, self.heads)                          # (T, E)
+        if self.fused_attention and self.in_proj_attn.npass == self.in_proj.npass:
+            ctx = self.in_proj_attn(y, EPI_ATTN, nsample=ns)                    # (T, E); qkv never exists
+        else:
+            qkv = self.in_proj(y, EPI_STORE)                                    # (T, 3E)
+            ctx = ops.group_attention(qkv, ns, self.heads)                      # (T, E)
         z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2)         # LN2(y + attn)
         h = self.lin1(z, EPI_RELU)
         pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)          # max_s (z + ffn), (:931)

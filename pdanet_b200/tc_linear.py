@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-EPI_STORE, EPI_RELU, EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_RELU_MAXPOOL = range(5)
+EPI_STORE, EPI_RELU, EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_RELU_MAXPOOL, EPI_ATTN = range(6)
 
 
 def _stream(t: torch.Tensor):
@@ -50,6 +50,9 @@ class PackedLinear:
         rows = x.shape[0]
         pooled = epilogue in (EPI_ADD_MAXPOOL, EPI_RELU_MAXPOOL)
         out_rows = rows // nsample if pooled else rows
+        if epilogue == EPI_ATTN:   # in_proj + neighbourhood attention: weight rows head-major [q_h | k_h | v_h] (attn_in_proj)
+            assert self.bn == 192 and self.nout % 192 == 0 and out is None
+            out = torch.empty(rows, self.nout // 3, dtype=torch.float32, device=x.device)
         if out is None:
             out = torch.empty(out_rows, self.nout, dtype=torch.float32, device=x.device)
         assert out.stride(1) == 1 and out.shape[0] == out_rows
@@ -81,3 +84,15 @@ class PackedLinear:
                       self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(), out.data_ptr(),
                       out.stride(0), _stream(xyz))
         return out
+
+
+def attn_in_proj(in_proj_weight: torch.Tensor, in_proj_bias: torch.Tensor, heads: int, npass: int = 2) -> "PackedLinear":
+    """in_proj of nn.MultiheadAttention packed for the fused attention epilogue (EPI_ATTN, head_dim 64): the rows of the
+    (3E, E) weight are regrouped head by head, [q_h | k_h | v_h] = one 192-column accumulator chunk per head, so that
+    `lin(y, EPI_ATTN, nsample=ns)` returns softmax(q k^T / sqrt(hd)) v per neighbourhood, heads concatenated (T, E)."""
+    E = in_proj_weight.shape[1]
+    hd = E // heads
+    assert hd == 64 and in_proj_weight.shape[0] == 3 * E
+    order = torch.cat([torch.arange(part * E + h * hd, part * E + (h + 1) * hd) for h in range(heads) for part in range(3)])
+    order = order.to(in_proj_weight.device)
+    return PackedLinear(in_proj_weight.detach()[order], in_proj_bias.detach()[order], npass=npass, bn=192)

@@ -143,6 +143,37 @@ def test_group_attention_vs_torch_mha(ns, hd):
     assert _rel(ctx, ref) < 5e-6
 
 
+@pytest.mark.parametrize("npass", [3, 2, 1])
+@pytest.mark.parametrize("ns", [16, 32])
+@pytest.mark.parametrize("pairs", [1, 0])
+def test_in_proj_attention_epilogue(npass, ns, pairs):
+    """EPI_ATTN (in_proj + neighbourhood attention in one kernel, head_dim 64) == nn.MultiheadAttention's in_proj followed
+    by its attention core, in float64.  Ragged row count (last pair tile half empty), CTA pairs and single CTAs."""
+    from pdanet_b200 import _lib
+    from pdanet_b200.tc_linear import EPI_ATTN, attn_in_proj
+    dev = _dev()
+    heads, hd = 4, 64
+    E = heads * hd
+    groups = 4000 // ns * 3 + 5
+    rows = groups * ns
+    g = torch.Generator().manual_seed(ns + npass)
+    x = torch.randn(rows, E, generator=g)
+    w = torch.randn(3 * E, E, generator=g) / E ** 0.5 * 1.5
+    b = torch.randn(3 * E, generator=g) * 0.3
+    try:
+        _lib.lib().pdab_set_cta_pairs(pairs)
+        lin = attn_in_proj(w.to(dev), b.to(dev), heads, npass=npass)
+        ctx = lin(x.to(dev), EPI_ATTN, nsample=ns).cpu()
+    finally:
+        _lib.lib().pdab_set_cta_pairs(1)
+    qkv = x.double() @ w.double().t() + b.double()
+    q, k, v = [t.view(groups, ns, heads, hd).permute(0, 2, 1, 3) for t in qkv.split(E, dim=1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(rows, E)
+    assert ctx.shape == ref.shape
+    assert _rel(ctx, ref) < 3 * TOL[npass]     # three chained contractions
+
+
 @pytest.mark.parametrize("tc_passes", [3, 2, 1])
 def test_wide_sa_scale_matches_unfused_module(tc_passes):
     """Plain SA layer with wide MLPs (the L5 shape): tensor-core path vs the reference statement order
