@@ -64,13 +64,13 @@ def peaks():
 
 
 def tensor_peak():
-    """TF32 dense peak in TFLOP/s: half the measured bf16 cuBLAS throughput (sustained figure: the kernel is timed inside
-    a long step); kind::tf32 MMAs run at half the bf16 rate on sm_100."""
+    """Dense bf16 tensor peak in TFLOP/s: the measured cuBLAS bf16 throughput (sustained figure: the kernel is timed
+    inside a long step)."""
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["bf16_tflops_sustained"]) / 2, "measured bf16_tflops_sustained / 2 (MEASURED_PEAKS.json; TF32 = half the bf16 rate)"
-    return 1590.0 / 2, "fallback 1.59 PFLOP/s bf16 / 2 (B200_PROFILING.md)"
+        return float(d["bf16_tflops_sustained"]), "measured bf16_tflops_sustained (MEASURED_PEAKS.json)"
+    return 1590.0, "fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -199,18 +199,23 @@ def algorithmic_bytes(key: str, batch: int):
     return None
 
 
+# tensor-pipe work per algorithmic flop, in bf16-MMA flops: split-bf16 ("bf16x3") issues 3 bf16 MMAs per product, 3xTF32
+# issues 3 TF32 MMAs (a TF32 MMA occupies the pipe like 2 bf16 MMAs), plain TF32 one
+MMA_COST = {2: 3.0, 3: 6.0, 1: 2.0}
+
+
 def algorithmic_flops(key: str):
-    """(algorithmic flops, tensor-pipe flops issued) of one launch of a tensor-core entry point, else None."""
+    """(algorithmic flops, tensor-pipe work in bf16-MMA-equivalent flops) of one launch of a tensor-core entry point."""
     name, _, rest = key.partition("(")
     a = [int(x) for x in rest.strip(")").split(",") if x.strip()]
     if name == "pdab_tc_linear":
         rows, k, nout, npass = a[:4]
         f = 2.0 * rows * k * nout
-        return f, f * npass
+        return f, f * MMA_COST[npass]
     if name == "pdab_tc_sa_gather_linear":
         b, c, n, m, ns, nout, npass = a[:7]
         f = 2.0 * b * m * ns * (c + 3) * nout
-        return f, f * npass
+        return f, f * MMA_COST[npass]
     return None
 
 
@@ -322,7 +327,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
     # Launches are grouped by C-ABI entry point (= by kernel): the tensor-core GEMM kernel runs ~25 times per step at
     # different shapes and is judged as one kernel: sum of algorithmic work / sum of launch durations.
     hbm_peak, peak_src = peaks()
-    tf32_peak, tf32_src = tensor_peak()
+    tc_peak, tc_src = tensor_peak()
     per_kernel, groups = [], {}
     for key, ms in kernel_ms.items():
         if not ms:
@@ -342,6 +347,18 @@ def run_gpu_arm(args, cfg, n_points, batch):
             g["flops"] += flops[0] * len(ms)
             g["mma"] += flops[1] * len(ms)
     per_kernel.sort(key=lambda r: -r["ms_per_step"])
+    # BASELINE.json's second figure: FPS + group + MLP microseconds per scene (sequential instrumented steps, our kernels)
+    stage_of = {"pdab_fps": "fps", "pdab_fps_with_dist": "fps", "pdab_topk_ctr": "topk_sampling",
+                "pdab_ball_query": "group", "pdab_gather_points": "group", "pdab_group_points": "group",
+                "pdab_pda_group": "group", "pdab_pda_group_tokens": "group", "pdab_pda_encode_ln": "group_encode_pda",
+                "pdab_pda_assemble_ln_split": "group_encode_pda", "pdab_sa_fused": "fused_group_mlp_maxpool",
+                "pdab_sa_fused_pair": "fused_group_mlp_maxpool", "pdab_tc_sa_gather_linear": "fused_group_mlp_maxpool",
+                "pdab_tc_linear": "mlp_gemm", "pdab_group_attention": "attention", "pdab_nms_batched": "nms"}
+    stages = {}
+    for name, g in groups.items():
+        st = stage_of.get(name, "other")
+        stages[st] = stages.get(st, 0.0) + g["ms"] / args.steps / batch * 1e3
+    stages = {k: round(v, 1) for k, v in sorted(stages.items())}
     roofline = None
     if groups:
         name, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
@@ -358,14 +375,15 @@ def run_gpu_arm(args, cfg, n_points, batch):
             common["traffic_source"] = "profiles/r01_tc_gemm_traffic.json"
         if g["flops"] > 0:  # tensor-core kernel: algorithmic flops = 2*rows*k*nout of the fp32 product it computes
             achieved = g["flops"] / g["ms"] / 1e9
-            roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": round(achieved / tf32_peak, 4), "peak_source": tf32_src,
+            roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": tc_peak, "unit": "TFLOP/s",
+                        "frac": round(achieved / tc_peak, 4), "peak_source": tc_src,
                         "mma_issued_TFLOPs": round(g["mma"] / g["ms"] / 1e9, 1),
-                        "mma_issued_frac": round(g["mma"] / g["ms"] / 1e9 / tf32_peak, 4),
+                        "mma_issued_frac": round(g["mma"] / g["ms"] / 1e9 / tc_peak, 4),
                         "hbm_GBps": round(g["bytes"] / g["ms"] / 1e6, 1),
-                        "note": "fp32-level products on TF32 tensor cores need 3 MMAs per product (error-compensated "
-                                "3xTF32): `achieved` counts the product once (algorithmic), `mma_issued_*` counts "
-                                "the MMAs the tensor pipe executed", **common}
+                        "note": "`achieved` = algorithmic flops (2*rows*k*nout, each fp32-level product counted once) / "
+                                "launch time against the dense bf16 peak; an fp32-level product costs 3 bf16 MMAs "
+                                "(split-bf16), so a perfectly tensor-bound launch reaches frac = 1/3; `mma_issued_frac` "
+                                "= share of the tensor pipe's bf16 rate the issued MMAs occupy", **common}
         else:
             achieved = g["bytes"] / g["ms"] / 1e6
             roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
@@ -398,7 +416,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_total / args.steps},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "kernels": per_kernel[:args.kernels],
+        "stage_us_per_scene": stages, "kernels": per_kernel[:args.kernels],
     }
     emit(line)
     if world > 1:
