@@ -207,4 +207,72 @@ __device__ __forceinline__ void ball_scan_split_to_smem(int n, const float *__re
     __syncthreads();
 }
 
+// ---- hashed cell list -------------------------------------------------------------------------------------------
+// A brute-force ordered scan costs M * N distance tests per scene whatever the radius.  With the points of a scene
+// bucketed by cell (edge kCellSlack * radius, spatial hash into kGridBuckets buckets per scene) a centre only has to
+// test the points of the 27 cells around it; the ball query's contract (the first nsample hits IN INDEX ORDER) is
+// kept by inserting every hit into a bounded ascending list — the nsample smallest indices among all hits are exactly
+// what the in-order scan collects.  Hash collisions only add candidates (every candidate is distance-tested with the
+// reference's expression), a bucket visited twice only re-offers indices the list already holds or has already
+// dropped, so the lists, and everything computed from them, are bit-identical to the scan's.
+// Coverage: cell(x) = floor(fl(x * inv_edge)) is monotone in x and edge exceeds the radius by 0.1 %, far more than the
+// rounding of the product for |x| < 2^20 cells, so two points closer than the radius are at most one cell apart per axis.
+constexpr int kGridBuckets = 1 << 16;
+constexpr float kCellSlack = 1.001f;
+
+__device__ __forceinline__ int grid_cell(float x, float inv_edge) { return (int)floorf(x * inv_edge); }
+__device__ __forceinline__ unsigned grid_hash(int ix, int iy, int iz) {
+    return ((unsigned)ix * 73856093u ^ (unsigned)iy * 19349663u ^ (unsigned)iz * 83492791u) & (kGridBuckets - 1);
+}
+
+// Workspace per scene: start[kGridBuckets + 1] | cursor[kGridBuckets] ints, then float4 sorted[n] = (x, y, z, index bits).
+__host__ __device__ inline size_t grid_scene_ints() { return 2 * (size_t)kGridBuckets + 4; }
+__host__ __device__ inline size_t grid_scene_bytes(int n) { return grid_scene_ints() * sizeof(int) + (size_t)n * sizeof(float4); }
+
+// Insert `idx` into the ascending list column `t` (pitch STRIDE) holding `cnt` <= cap entries; keeps the cap smallest.
+template <int STRIDE>
+__device__ __forceinline__ void sorted_insert(int *list, int t, int &cnt, int cap, int idx) {
+    int pos = cnt;
+    while (pos > 0 && list[(pos - 1) * STRIDE + t] > idx) pos--;
+    if (pos >= cap || (pos > 0 && list[(pos - 1) * STRIDE + t] == idx)) return;   // beyond the cap, or already there
+    const int last = cnt < cap ? cnt : cap - 1;
+    for (int j = last; j > pos; j--) list[j * STRIDE + t] = list[(j - 1) * STRIDE + t];
+    list[pos * STRIDE + t] = idx;
+    if (cnt < cap) cnt++;
+}
+
+// Two-radius query against the cell list: same results as ball_scan2_to_smem.  All threads of the CTA must call it.
+template <int THREADS, int STRIDE>
+__device__ __forceinline__ void grid_scan2_to_smem(const int *__restrict__ start, const float4 *__restrict__ sorted,
+                                                   float inv_edge, bool active, float cx, float cy, float cz, float r2a,
+                                                   int ns_a, float r2b, int ns_b, int *__restrict__ sidx_a,
+                                                   int *__restrict__ sidx_b) {
+    const int t = threadIdx.x;
+    active = active && t < THREADS;
+    int ca = 0, cb = 0;
+    if (active) {
+        const int ix = grid_cell(cx, inv_edge), iy = grid_cell(cy, inv_edge), iz = grid_cell(cz, inv_edge);
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const unsigned bkt = grid_hash(ix + dx, iy + dy, iz + dz);
+                    const int beg = __ldg(start + bkt), end = __ldg(start + bkt + 1);
+                    for (int i = beg; i < end; i++) {
+                        const float4 q = __ldg(sorted + i);
+                        const float d2 = sqdist3(cx, cy, cz, q.x, q.y, q.z);
+                        if (d2 < r2b) sorted_insert<STRIDE>(sidx_b, t, cb, ns_b, __float_as_int(q.w));
+                        if (d2 < r2a) sorted_insert<STRIDE>(sidx_a, t, ca, ns_a, __float_as_int(q.w));
+                    }
+                }
+        const int fa = ca > 0 ? sidx_a[t] : 0;  // empty ball: the pre-zeroed row groups point 0
+        for (int l = ca; l < ns_a; l++) sidx_a[l * STRIDE + t] = fa;
+        const int fb = cb > 0 ? sidx_b[t] : 0;
+        for (int l = cb; l < ns_b; l++) sidx_b[l * STRIDE + t] = fb;
+    } else if (t < THREADS) {
+        for (int l = 0; l < ns_a; l++) sidx_a[l * STRIDE + t] = 0;
+        for (int l = 0; l < ns_b; l++) sidx_b[l * STRIDE + t] = 0;
+    }
+    __syncthreads();
+}
+
 }  // namespace pdab

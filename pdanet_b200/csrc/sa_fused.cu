@@ -284,9 +284,12 @@ int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const f
 // Both scales of an SA layer in one kernel: ONE scan of the cloud fills the two hit lists (ball_scan2_to_smem), then the
 // two MLP + max-pool phases run back to back; the outputs land in one (B, A3 + B3, M) tensor, i.e. already concatenated
 // along the channel axis as PB/pointnet2_modules.py:1674 (torch.cat of the scales) wants it.
-template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3>
+// GRID: the hit lists come from the scene's hashed cell list (grid_build_kernel, ball_scan.cuh) instead of a scan of the
+// whole cloud — 27 cells per centre instead of N points; same lists, bit-identical outputs.
+template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3, bool GRID>
 __global__ void __launch_bounds__(kMlpThreads, 2)
-sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns_b, const float *__restrict__ xyz,
+sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns_b, const unsigned char *__restrict__ ws,
+                     float inv_edge, const float *__restrict__ xyz,
                      const float *__restrict__ new_xyz, const float *__restrict__ features,
                      const float *__restrict__ Wa1, const float *__restrict__ ba1, const float *__restrict__ Wa2,
                      const float *__restrict__ ba2, const float *__restrict__ Wa3, const float *__restrict__ ba3,
@@ -339,7 +342,15 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
         sctr[t * 3 + 1] = cy;
         sctr[t * 3 + 2] = cz;
     }
-    pdab::ball_scan2_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2a, ns_a, r2b, ns_b, tile, sidx_a, sidx_b);
+    if (GRID) {
+        const unsigned char *wscene = ws + (size_t)scene * pdab::grid_scene_bytes(n);
+        __syncthreads();  // weights / centres staged
+        pdab::grid_scan2_to_smem<kThreads, kStride>(reinterpret_cast<const int *>(wscene),
+                                                    reinterpret_cast<const float4 *>(wscene + pdab::grid_scene_ints() * sizeof(int)),
+                                                    inv_edge, active, cx, cy, cz, r2a, ns_a, r2b, ns_b, sidx_a, sidx_b);
+    } else {
+        pdab::ball_scan2_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2a, ns_a, r2b, ns_b, tile, sidx_a, sidx_b);
+    }
 
     const int nctr = min(kThreads, m - j0);
     mlp_phase<C0P, A1, A2, A3>(c, n, ns_a, nctr, xyz, features, sWa1, sba1, sWa2, sba2, sWa3, sba3, sctr, sidx_a, sout);
@@ -352,20 +363,96 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     }
 }
 
+// One CTA per scene builds the scene's cell list: bucket counts (global atomics), exclusive scan, scatter of
+// (x, y, z, index) into bucket order.  ~20 us for 16 x 16384 points; the order inside a bucket is arbitrary (the query
+// keeps hits sorted by index).
+constexpr int kBuildThreads = 1024;
+__global__ void __launch_bounds__(kBuildThreads)
+grid_build_kernel(int n, float inv_edge, const float *__restrict__ xyz_all, unsigned char *__restrict__ ws) {
+    constexpr int NB = pdab::kGridBuckets, PER = NB / kBuildThreads;
+    __shared__ int warp_sums[kBuildThreads / 32];
+    const int scene = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *xyz = xyz_all + (size_t)scene * n * 3;
+    unsigned char *wscene = ws + (size_t)scene * pdab::grid_scene_bytes(n);
+    int *start = reinterpret_cast<int *>(wscene);
+    int *cursor = start + NB + 4;
+    float4 *sorted = reinterpret_cast<float4 *>(wscene + pdab::grid_scene_ints() * sizeof(int));
+    for (int i = t; i < NB; i += kBuildThreads) cursor[i] = 0;
+    __syncthreads();
+    for (int k = t; k < n; k += kBuildThreads) {
+        const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
+        atomicAdd(cursor + pdab::grid_hash(pdab::grid_cell(x, inv_edge), pdab::grid_cell(y, inv_edge),
+                                           pdab::grid_cell(z, inv_edge)), 1);
+    }
+    __syncthreads();
+    // exclusive scan of the NB counts: PER consecutive buckets per thread, then warp / CTA prefix
+    int local[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        local[i] = cursor[t * PER + i];
+        sum += local[i];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += v;
+        }
+        warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        start[t * PER + i] = run;
+        cursor[t * PER + i] = run;
+        run += local[i];
+    }
+    if (t == kBuildThreads - 1) start[NB] = run;
+    __syncthreads();
+    for (int k = t; k < n; k += kBuildThreads) {
+        const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
+        const int pos = atomicAdd(cursor + pdab::grid_hash(pdab::grid_cell(x, inv_edge), pdab::grid_cell(y, inv_edge),
+                                                           pdab::grid_cell(z, inv_edge)), 1);
+        sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+}
+
 template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3>
 int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns_b, const float *xyz,
                 const float *new_xyz, const float *features, const float *const *W, const float *const *B, float *out,
-                cudaStream_t stream) {
+                void *workspace, cudaStream_t stream) {
     const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
                         sizeof(float) * (A1 * wpitch(C0P) + A2 * wpitch(A1) + A3 * wpitch(A2) + B1 * wpitch(C0P) +
                                          B2 * wpitch(B1) + B3 * wpitch(B2) + A1 + A2 + A3 + B1 + B2 + B3 + 3 * kThreads +
                                          (A3 + B3) * kStride) +
                         sizeof(int) * (size_t)(ns_a + ns_b) * kStride;
-    auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3>;
-    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(pdab::div_up(m, kThreads), b);
-    kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, ra * ra, ns_a, rb * rb, ns_b, xyz, new_xyz, features, W[0], B[0],
-                                              W[1], B[1], W[2], B[2], W[3], B[3], W[4], B[4], W[5], B[5], out);
+    if (workspace) {
+        const float inv_edge = 1.0f / (pdab::kCellSlack * fmaxf(ra, rb));
+        unsigned char *ws = static_cast<unsigned char *>(workspace);
+        grid_build_kernel<<<b, kBuildThreads, 0, stream>>>(n, inv_edge, xyz, ws);
+        PDAB_LAUNCH_CHECK();
+        auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, true>;
+        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, ra * ra, ns_a, rb * rb, ns_b, ws, inv_edge, xyz, new_xyz, features,
+                                                  W[0], B[0], W[1], B[1], W[2], B[2], W[3], B[3], W[4], B[4], W[5], B[5], out);
+        PDAB_LAUNCH_CHECK();
+        return 0;
+    }
+    auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, false>;
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, ra * ra, ns_a, rb * rb, ns_b, nullptr, 0.f, xyz, new_xyz, features,
+                                              W[0], B[0], W[1], B[1], W[2], B[2], W[3], B[3], W[4], B[4], W[5], B[5], out);
     PDAB_LAUNCH_CHECK();
     return 0;
 }
@@ -401,7 +488,7 @@ extern "C" int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsamp
 extern "C" int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b,
                                   int nsample_b, const float *xyz, const float *new_xyz, const float *features,
                                   const int *dims_a_host, const int *dims_b_host, const float *const *weights_host,
-                                  const float *const *biases_host, float *out, pdab_stream_t stream) {
+                                  const float *const *biases_host, float *out, void *workspace, pdab_stream_t stream) {
     if (b < 0 || c < 0 || n < 1 || m < 0 || nsample_a < 1 || nsample_b < 1 || !xyz || !new_xyz || !out || !dims_a_host ||
         !dims_b_host || !weights_host || !biases_host || (c > 0 && !features))
         return PDAB_EINVAL;
@@ -416,9 +503,14 @@ extern "C" int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, in
     const bool b_large = dims_b_host[1] == 32 && dims_b_host[2] == 32 && dims_b_host[3] == 64;
     if (a_small && b_large && d0 <= 4)
         return launch_pair<4, 16, 16, 32, 32, 32, 64>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
-                                                      features, weights_host, biases_host, out, s);
+                                                      features, weights_host, biases_host, out, workspace, s);
     if (a_small && b_large && d0 <= 8)
         return launch_pair<8, 16, 16, 32, 32, 32, 64>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
-                                                      features, weights_host, biases_host, out, s);
+                                                      features, weights_host, biases_host, out, workspace, s);
     return PDAB_EUNSUPPORTED;
+}
+
+extern "C" size_t pdab_sa_grid_workspace_bytes(int b, int n) {
+    if (b < 1 || n < 1) return 0;
+    return (size_t)b * pdab::grid_scene_bytes(n);
 }

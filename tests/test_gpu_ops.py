@@ -393,10 +393,17 @@ def test_sa_fused_pair_equals_two_single_scale_kernels(n, m):
             ws.append((torch.randn(dims[i + 1], dims[i], generator=g) / math.sqrt(dims[i])).to(dev))
             bs.append((torch.randn(dims[i + 1], generator=g) * 0.1).to(dev))
     for radii, ns in (((0.2, 0.8), (16, 32)), ((2.5, 1.0), (5, 32))):
-        pair = ops.sa_fused_pair(radii, ns, xyz, ctr, feats, ws, bs)
+        pair = ops.sa_fused_pair(radii, ns, xyz, ctr, feats, ws, bs, cell_list=False)
         a = ops.sa_fused(radii[0], ns[0], xyz, ctr, feats, ws[:3], bs[:3])
         b = ops.sa_fused(radii[1], ns[1], xyz, ctr, feats, ws[3:], bs[3:])
         assert torch.equal(pair, torch.cat([a, b], dim=1))
+        # hashed cell list instead of the scan of the whole cloud: the same neighbour lists, so the same bits — also with
+        # the cloud shifted to negative coordinates and squeezed until every ball overflows its nsample
+        assert torch.equal(ops.sa_fused_pair(radii, ns, xyz, ctr, feats, ws, bs, cell_list=True), pair)
+    for shift, scale in ((-37.3, 1.0), (0.0, 0.05), (-3.0, 0.004)):
+        x2, c2 = (xyz * scale + shift).contiguous(), (ctr * scale + shift).contiguous()
+        want = ops.sa_fused_pair((0.2, 0.8), (16, 32), x2, c2, feats, ws, bs, cell_list=False)
+        assert torch.equal(ops.sa_fused_pair((0.2, 0.8), (16, 32), x2, c2, feats, ws, bs, cell_list=True), want)
 
 
 # ------------------------------------------------------------------ feature propagation, points in boxes
