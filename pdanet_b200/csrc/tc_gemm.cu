@@ -328,7 +328,9 @@ __device__ __forceinline__ float tf32_rna(float v) {
 constexpr int kProdRegs = 152, kEpiRegs = 104;
 template <int EPI, int CG>
 struct EpiWarps {
-    static constexpr int value = (EPI == 5 /*E_ATTN*/ && CG == 2) ? 8 : 4;
+    // (tried for the residual + max-pool epilogues too: slower — they wait for residual tiles, not for issue slots, and
+    // 104 registers leave one tile in flight per warp instead of two)
+    static constexpr int value = (CG == 2 && EPI == 5) ? 8 : 4;
 };
 
 template <int NPASS, int BN, int CG, int EW = 4>
@@ -376,6 +378,10 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
     auto row0_of = [&](long long item) { return (item / p.n_groups) * (long long)(BM * CG) + (long long)rank * BM; };
     constexpr int ACC_STAGES = (NCH * BN * 2 <= kTmemCols) ? 2 : 1;
     constexpr int ACC_COLS = kTmemCols / ACC_STAGES;  // column stride between accumulator stages
+    // LayerNorm over a 512-column row fills TMEM: no second accumulator stage.  The two 256-column chunks are then handed
+    // over one by one (acc_full / acc_empty slot c = chunk c), so the first statistics pass of chunk 0 overlaps the MMAs of
+    // chunk 1 and the last normalise pass of chunk 1 overlaps the MMAs of the next tile's chunk 0.
+    constexpr bool CHUNKED = EPI == E_ADD_LN && NCH == 2;
 
     extern __shared__ uint8_t smem_raw[];
     const u32 smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -488,10 +494,16 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
             constexpr u32 idesc = umma_idesc<BN, NPASS == 2 ? 1 : 2, CG>();
             constexpr int BKE = bk_of(NPASS), KSTEP = NPASS == 2 ? 16 : 8;   // elements per k-atom / per MMA
             for (long long item = item0; item < n_items; item += item_step) {
-                if (CG == 2) mbar_wait_cluster(acc_empty(as), aphase ^ 1);
-                else mbar_wait(acc_empty(as), aphase ^ 1);  // epilogue has drained this accumulator stage
-                tc_fence_after();
+                if (!CHUNKED) {
+                    if (CG == 2) mbar_wait_cluster(acc_empty(as), aphase ^ 1);
+                    else mbar_wait(acc_empty(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+                    tc_fence_after();
+                }
                 for (int c = 0; c < NCH; c++) {
+                    if (CHUNKED) {
+                        mbar_wait(acc_empty(c), aphase ^ 1);    // epilogue has drained chunk c of the previous tile
+                        tc_fence_after();
+                    }
                     const u32 d = tmem_base + (u32)(as * ACC_COLS + c * BN);
                     for (int ka = 0; ka < KA; ka++) {
                         mbar_wait(full_w(pipe.stage), pipe.phase);
@@ -527,8 +539,9 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                         umma_commit<CG>(empty(pipe.stage));  // frees the smem stage (both CTAs) once these MMAs have read it
                         pipe.advance<S>();
                     }
+                    if (CHUNKED) umma_commit<CG>(acc_full(c));   // chunk c complete -> epilogue (both CTAs)
                 }
-                umma_commit<CG>(acc_full(as));           // accumulator complete -> epilogue (both CTAs)
+                if (!CHUNKED) umma_commit<CG>(acc_full(as));     // accumulator complete -> epilogue (both CTAs)
                 if (ACC_STAGES == 2) {
                     as ^= 1;
                     if (as == 0) aphase ^= 1;
@@ -782,14 +795,27 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
             __syncwarp();
             // residual tiles: two register sets, each refilled as soon as it has been consumed, so a tile has ~1.5 column
             // blocks (and, for the first two, the whole accumulator wait) to arrive from L2 / HBM
+            // (EW = 8: the two warps of a quadrant take the even / odd 32-column blocks, one register set each)
+            constexpr int NW = EW / 4;                       // warps per quadrant
+            const int half = EW == 8 ? (ew >> 2) : 0;        // which of them this warp is
             float2 ra[2][8], rb[2][8];
             if (EPI == E_ADD_MAXPOOL || EPI == E_ADD_LN) {
                 const int nb0 = n_group * NCH * BN;
-                issue_tile(ra, p.R, p.ldr, wrow0, p.T, nb0);
-                issue_tile(rb, p.R, p.ldr, wrow0, p.T, nb0 + 32);
+                // pull this warp's whole residual slab (32 rows x NCH * BN columns) towards L2 while the MMAs still run:
+                // the register tiles below are then fed at L2 latency, not DRAM latency
+                if (wrow0 + lane < p.T) {
+                    const float *rrow = p.R + (wrow0 + lane) * p.ldr + nb0;
+#pragma unroll
+                    for (int c = 0; c < NCH * BN; c += 32)
+                        if (nb0 + c < p.Nout) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
+                }
+                issue_tile(ra, p.R, p.ldr, wrow0, p.T, nb0 + 32 * half);
+                if (NW == 1) issue_tile(rb, p.R, p.ldr, wrow0, p.T, nb0 + 32);
             }
-            mbar_wait(acc_full(as), aphase);
-            tc_fence_after();
+            if (!CHUNKED) {
+                mbar_wait(acc_full(as), aphase);
+                tc_fence_after();
+            }
             const u32 tacc = tmem_base + ((u32)(q * 32) << 16) + (u32)(as * ACC_COLS);
 
             if (EPI == E_STORE || EPI == E_RELU) {
@@ -834,14 +860,20 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     }
                     pool_store(v, wrow0, n0, ns);
                 };
-                for (int b = 0; b < nblk; b += 2) {
-                    block(b, ra);
-                    block(b + 1, rb);
+                if (NW == 1) {
+                    for (int b = 0; b < nblk; b += 2) {
+                        block(b, ra);
+                        block(b + 1, rb);
+                    }
+                } else {
+                    for (int b = half; b < nblk; b += 2) block(b, ra);
                 }
             } else if (EPI == E_ADD_LN) {
                 // out = LayerNorm(acc + bias + R) over the full row of E = NCH * BN columns (n_groups == 1).
                 // Pass 1 parks v = acc + bias + R back in TMEM and sums it; pass 2: centred variance; pass 3: normalise.
                 // A thread owns 4 rows (h, j); a row's 8 values per block are summed in the thread, then over the quad.
+                // (Software-pipelining the passes over two fragment buffers — TMEM load of block b + 1 in flight while
+                // block b is processed — was measured slower: the extra 32 registers spill.)
                 constexpr int E = NCH * BN;
                 float sum[4] = {0.f, 0.f, 0.f, 0.f};
                 auto block = [&](int j0, float2 (&r)[2][8]) {
@@ -859,6 +891,10 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     frag_st(tacc + j0, v);
                 };
                 for (int j0 = 0; j0 < E; j0 += 64) {
+                    if (CHUNKED && j0 % BN == 0) {          // chunk j0 / BN has just been completed by the MMAs
+                        mbar_wait(acc_full(j0 / BN), aphase);
+                        tc_fence_after();
+                    }
                     block(j0, ra);
                     block(j0 + 32, rb);
                 }
@@ -909,6 +945,14 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                             }
                     }
                     store_tile(v, p.out, p.ldo, wrow0, p.T, j0);
+                    if (CHUNKED && (j0 + 32) % BN == 0) {   // last block of a chunk: hand the chunk back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2 && !leader) mbar_arrive_remote(acc_empty(j0 / BN), 0);
+                            else mbar_arrive(acc_empty(j0 / BN));
+                        }
+                    }
                 }
             } else if (EPI == E_ATTN) {
                 // One attention head per item: accumulator columns [0, HD) = Q, [HD, 2 HD) = K, [2 HD, 3 HD) = V of the
@@ -1137,7 +1181,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                 __syncwarp();  // sbias and (EW = 4) the staging tile are rewritten for the next item
             }
 
-            if (EPI != E_ATTN) {  // (the attention epilogue released its accumulator stage as soon as V was staged)
+            if (EPI != E_ATTN && !CHUNKED) {  // (the attention and chunked LayerNorm epilogues release earlier)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
