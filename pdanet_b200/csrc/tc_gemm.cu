@@ -32,6 +32,7 @@
 // row for the LayerNorm epilogue) so the epilogue of item i overlaps the main loop of item i+1.
 // Weights are packed once (host side, pdanet_b200/tc_pack.py) into the exact smem image of each (column chunk, k-atom)
 // tile — canonical K-major SWIZZLE_128B layout — so a stage's weights are ONE contiguous bulk copy.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -79,6 +80,7 @@ struct GemmParams {
     const float *gamma, *beta;
     float eps;
     long long n_items;
+    long long store_rows;  // rows of the output actually written: T, or 0 with PDAB_TC_NOSTORE=1 (timing aid: main loop only)
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                 v[1][e] = fmaxf(v[1][e], 0.f);
                             }
                         }
-                        store_tile(v, p.out, p.ldo, wrow0, p.T, n0);
+                        store_tile(v, p.out, p.ldo, wrow0, p.store_rows, n0);
                     }
                 }
             } else if (EPI == E_ADD_MAXPOOL || EPI == E_RELU_MAXPOOL) {
@@ -984,6 +986,23 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
                 };
+                // NPASS = 2 (split-bf16 GEMM): the attention contractions use the same product class — bf16 hi / lo pairs,
+                // m16n8k16, three MMAs per k-step — which halves the mma.sync count.  The legacy mma.sync shares the tensor
+                // pipe with the tcgen05 MMAs of the next item and does not overlap with them (measured: the kernel takes
+                // main loop + ~18 cycles per HMMA), so the instruction count is what the epilogue costs.  A 16x256b
+                // fragment pair (column blocks 2s, 2s + 1) IS the k16 A / B fragment, no permutation needed.
+                constexpr bool BF = NPASS == 2;
+                auto split2 = [](float x0, float x1, u32 &hi, u32 &lo) {   // (x0, x1) -> packed bf16 pairs, x0 in the low half
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+                    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+                };
+                auto mma16 = [](float (&d)[4], const u32 (&a)[4], const u32 (&b)[2]) {
+                    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                        "{%0,%1,%2,%3};"
+                        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+                };
                 auto pair_sync = [&]() {  // the two warps of a quadrant (EW = 8)
                     if (EW == 8) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
                     else __syncwarp();
@@ -1013,6 +1032,39 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                         for (int kh = 0; kh < KH; kh++)
                             tmem_ld_16x256b_x4(tacc + ((u32)(16 * (FULL ? kh : mt0 + kh)) << 16) + HD + kb, kf[kh]);
                         tmem_wait_ld();
+                        if constexpr (BF) {
+#pragma unroll
+                            for (int k = 0; k < 4; k += 2) {       // one k16 step = column blocks k, k + 1
+                                const float2 bq0 = *reinterpret_cast<const float2 *>(sbias + kb + 8 * k + t2);
+                                const float2 bq1 = *reinterpret_cast<const float2 *>(sbias + kb + 8 * k + 8 + t2);
+                                u32 ah[MTW][4], al[MTW][4];
+#pragma unroll
+                                for (int mi = 0; mi < MTW; mi++) {
+                                    split2(qf[mi][4 * k + 0] + bq0.x, qf[mi][4 * k + 1] + bq0.y, ah[mi][0], al[mi][0]);
+                                    split2(qf[mi][4 * k + 2] + bq0.x, qf[mi][4 * k + 3] + bq0.y, ah[mi][1], al[mi][1]);
+                                    split2(qf[mi][4 * k + 4] + bq1.x, qf[mi][4 * k + 5] + bq1.y, ah[mi][2], al[mi][2]);
+                                    split2(qf[mi][4 * k + 6] + bq1.x, qf[mi][4 * k + 7] + bq1.y, ah[mi][3], al[mi][3]);
+                                }
+                                u32 bh[KH][2][2], bl[KH][2][2];
+#pragma unroll
+                                for (int kh = 0; kh < KH; kh++)
+#pragma unroll
+                                    for (int e = 0; e < 2; e++) {
+                                        split2(kf[kh][4 * k + 2 * e], kf[kh][4 * k + 2 * e + 1], bh[kh][e][0], bl[kh][e][0]);
+                                        split2(kf[kh][4 * k + 4 + 2 * e], kf[kh][4 * k + 5 + 2 * e], bh[kh][e][1], bl[kh][e][1]);
+                                    }
+#pragma unroll
+                                for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+                                    for (int ni = 0; ni < NTW; ni++)
+#pragma unroll
+                                        for (int mi = 0; mi < MTW; mi++) {
+                                            const int kh = FULL ? (ni >> 1) : mi;
+                                            mma16((k & 2) ? sc2[mi][ni] : sc[mi][ni], pass == 1 ? al[mi] : ah[mi],
+                                                  pass == 0 ? bl[kh][ni & 1] : bh[kh][ni & 1]);
+                                        }
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const float2 bq = *reinterpret_cast<const float2 *>(sbias + kb + 8 * k + t2);
@@ -1045,6 +1097,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                         mma((k & 1) ? sc2[mi][ni] : sc[mi][ni], pass == 1 ? al[mi] : ah[mi],
                                             pass == 0 ? bl[kh][ni & 1] : bh[kh][ni & 1]);
                                     }
+                        }
                         }
                     }
 #pragma unroll
@@ -1132,6 +1185,51 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                             split(pf[1], ah[2], al[2]);
                             split(pf[3], ah[3], al[3]);
                         };
+                        if constexpr (BF) {
+                            // keys 16 s .. 16 s + 15 per step: A = two score n-tiles packed, B = four V rows packed in pairs
+                            auto bfrag16 = [&](int s16, u32 (&bh)[4][2], u32 (&bl)[4][2]) {
+#pragma unroll
+                                for (int n4 = 0; n4 < 4; n4++) {
+                                    const float *vp = sV + (16 * s16 + t2) * kAttnVP + 32 * nb + 8 * n4 + g;
+                                    split2(vp[0], vp[kAttnVP], bh[n4][0], bl[n4][0]);
+                                    split2(vp[8 * kAttnVP], vp[9 * kAttnVP], bh[n4][1], bl[n4][1]);
+                                }
+                            };
+                            auto afrag16 = [&](const float (&p0)[4], const float (&p1)[4], u32 (&ah)[4], u32 (&al)[4]) {
+                                split2(p0[0], p0[1], ah[0], al[0]);
+                                split2(p0[2], p0[3], ah[1], al[1]);
+                                split2(p1[0], p1[1], ah[2], al[2]);
+                                split2(p1[2], p1[3], ah[3], al[3]);
+                            };
+                            if constexpr (FULL) {
+#pragma unroll
+                                for (int s16 = 0; s16 < 2; s16++) {
+                                    u32 bh[4][2], bl[4][2], ah[MTW][4], al[MTW][4];
+                                    bfrag16(s16, bh, bl);
+#pragma unroll
+                                    for (int mi = 0; mi < MTW; mi++) afrag16(sc[mi][2 * s16], sc[mi][2 * s16 + 1], ah[mi], al[mi]);
+#pragma unroll
+                                    for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+                                        for (int n4 = 0; n4 < 4; n4++)
+#pragma unroll
+                                            for (int mi = 0; mi < MTW; mi++)
+                                                mma16(o[mi][n4], pass == 1 ? al[mi] : ah[mi], pass == 0 ? bl[n4] : bh[n4]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int mi = 0; mi < MTW; mi++) {
+                                    u32 bh[4][2], bl[4][2], ah[4], al[4];
+                                    bfrag16(mt0 + mi, bh, bl);
+                                    afrag16(sc[mi][0], sc[mi][1], ah, al);
+#pragma unroll
+                                    for (int pass = 0; pass < 3; pass++)
+#pragma unroll
+                                        for (int n4 = 0; n4 < 4; n4++)
+                                            mma16(o[mi][n4], pass == 1 ? al : ah, pass == 0 ? bl[n4] : bh[n4]);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int ksl = 0; ksl < NTW; ksl++) {
                             if constexpr (FULL) {
@@ -1160,12 +1258,13 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                 }
                             }
                         }
+                        }
 #pragma unroll
                         for (int mi = 0; mi < MTW; mi++)
 #pragma unroll
                             for (int r = 0; r < 2; r++) {
                                 const long long row = wrow0 + 16 * (mt0 + mi) + 8 * r + g;
-                                if (row < p.T) {
+                                if (row < p.store_rows) {
 #pragma unroll
                                     for (int n4 = 0; n4 < 4; n4++) {
                                         const float2 bv = *reinterpret_cast<const float2 *>(sbias + 2 * HD + 32 * nb + 8 * n4 + t2);
@@ -1223,6 +1322,8 @@ int launch_cg(GemmParams p, cudaStream_t s) {
         configured = true;
     }
     p.n_items = ((p.T + BM * CG - 1) / (BM * CG)) * p.n_groups;
+    static const bool nostore = getenv("PDAB_TC_NOSTORE") != nullptr;
+    p.store_rows = nostore ? 0 : p.T;
     long long grid = p.n_items * CG < g_persistent_ctas ? p.n_items * CG : g_persistent_ctas;
     if (CG == 2) grid &= ~1LL;
     cudaLaunchConfig_t cfg{};
