@@ -127,10 +127,63 @@ __device__ __forceinline__ void c_to_a(const float (&h)[4], int g, int t, float 
     a[3] = odd ? y3 : y2;   // (row g+8, col 8s + t + 4)
 }
 
+// ---- layers 2 and 3 on bf16 m16n8k16 split products ("bf16x3": x = hi + lo in bf16, acc += hi w_lo + lo w_hi + hi w_hi,
+// ~2^-17 relative per product, fp32 accumulation — the product class of the big split-bf16 GEMMs).  Two reasons: half the
+// mma.sync count of m16n8k8 (the phase is bound by the legacy tensor path, ~18 cycles per instruction), and the C fragments
+// of the previous layer (row g: channels 2t, 2t+1 of each 8-channel tile) ARE the k16 A fragments once packed — the eight
+// shuffles per k-step of the TF32 re-layout (c_to_a) disappear.  Weights are split once per CTA into packed (hi, lo) pairs.
+__host__ __device__ constexpr int p16(int K) { return K / 2 + 4; }   // row pitch in 32-bit words: 4 * odd -> conflict-free B loads
+
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, unsigned &hi, unsigned &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// out (C fragments, N/8 tiles) = relu(in (C fragments, K/8 tiles) . W^T + bias); sWh / sWl: packed bf16 pairs, pitch p16(K)
+template <int K, int N>
+__device__ __forceinline__ void mma_layer16(const unsigned *sWh, const unsigned *sWl, const float *sb, int g, int t,
+                                            const float (&in)[K / 8][4], float (&out)[N / 8][4]) {
+    constexpr int P = p16(K);
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++) {
+        const float b0 = sb[nt * 8 + 2 * t], b1 = sb[nt * 8 + 2 * t + 1];
+        out[nt][0] = b0;
+        out[nt][1] = b1;
+        out[nt][2] = b0;
+        out[nt][3] = b1;
+    }
+#pragma unroll
+    for (int s = 0; s < K / 16; s++) {
+        unsigned ah[4], al[4];
+        split_bf16x2(in[2 * s][0], in[2 * s][1], ah[0], al[0]);          // row g,     k = 2t, 2t+1
+        split_bf16x2(in[2 * s][2], in[2 * s][3], ah[1], al[1]);          // row g + 8
+        split_bf16x2(in[2 * s + 1][0], in[2 * s + 1][1], ah[2], al[2]);  // row g,     k = 2t+8, 2t+9
+        split_bf16x2(in[2 * s + 1][2], in[2 * s + 1][3], ah[3], al[3]);  // row g + 8
+#pragma unroll
+        for (int pass = 0; pass < 3; pass++)                              // small terms first; independent tiles interleaved
+#pragma unroll
+            for (int nt = 0; nt < N / 8; nt++) {
+                const int w = (nt * 8 + g) * P + s * 8 + t;
+                const unsigned *sw = pass == 0 ? sWl : sWh;
+                mma_bf16(out[nt], pass == 1 ? al : ah, sw[w], sw[w + 4]);
+            }
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) out[nt][e] = fmaxf(out[nt][e], 0.f);
+}
+
 template <int C0P, int C1, int C2, int C3>
 __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, const float *__restrict__ xyz,
                                           const float *__restrict__ features, const float *sW1, const float *sb1,
-                                          const float *sW2, const float *sb2, const float *sW3, const float *sb3,
+                                          const unsigned *sW2, const float *sb2, const unsigned *sW3, const float *sb3,
                                           const float *sctr, const int *sidx, float *sout) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -163,8 +216,8 @@ __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, c
                 a[2] = in[0][1];
                 a[3] = in[1][1];
             }, h1);
-            mma_layer<C1, C2>(sW2, sb2, g, t, [&](int s, float (&a)[4]) { c_to_a(h1[s], g, t, a); }, h2);
-            mma_layer<C2, C3>(sW3, sb3, g, t, [&](int s, float (&a)[4]) { c_to_a(h2[s], g, t, a); }, h3);
+            mma_layer16<C1, C2>(sW2, sW2 + C2 * p16(C1), sb2, g, t, h1, h2);
+            mma_layer16<C2, C3>(sW3, sW3 + C3 * p16(C2), sb3, g, t, h2, h3);
             // max over the 16 rows of this m-tile: rows g / g+8 in the thread, then over g by shuffles
 #pragma unroll
             for (int nt = 0; nt < C3 / 8; nt++)
@@ -198,6 +251,20 @@ __device__ __forceinline__ void stage_weights(float *sW, const float *__restrict
     }
 }
 
+// W (rows x K, row-major, global) -> packed bf16 (hi | lo) images of pitch p16(K): word (r, j) = columns 2j, 2j+1 of row r
+template <int K>
+__device__ __forceinline__ void stage_weights16(unsigned *sW, const float *__restrict__ W, int rows) {
+    constexpr int P = p16(K);
+    unsigned *sWl = sW + rows * P;
+    for (int i = threadIdx.x; i < rows * (K / 2); i += kMlpThreads) {
+        const int r = i / (K / 2), j = i - r * (K / 2);
+        unsigned hi, lo;
+        split_bf16x2(W[r * K + 2 * j], W[r * K + 2 * j + 1], hi, lo);
+        sW[r * P + j] = hi;
+        sWl[r * P + j] = lo;
+    }
+}
+
 // C0P: input width padded to a multiple of 4 (3 + C real channels, rest zero weights/inputs)
 //
 // Phase 1: threads 0..127 each scan the cloud for one centre (hit lists in shared memory).
@@ -217,8 +284,8 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
     float *sW1 = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);  // C1 x C0P
     float *sW2 = sW1 + C1 * wpitch(C0P);                              // C2 x wpitch(C1)
-    float *sW3 = sW2 + C2 * wpitch(C1);                               // C3 x wpitch(C2)
-    float *sb1 = sW3 + C3 * wpitch(C2);
+    float *sW3 = sW2 + C2 * 2 * p16(C1);                              // packed (hi | lo) bf16 pairs, C3 x 2 p16(C2) words
+    float *sb1 = sW3 + C3 * 2 * p16(C2);
     float *sb2 = sb1 + C1;
     float *sb3 = sb2 + C2;
     float *sctr = sb3 + C3;                                           // 3 x kThreads
@@ -235,8 +302,8 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     if (c > 0) features += (size_t)scene * c * n;
 
     stage_weights<C0P>(sW1, W1, C1, c0);
-    stage_weights<C1>(sW2, W2, C2, C1);
-    stage_weights<C2>(sW3, W3, C3, C2);
+    stage_weights16<C1>(reinterpret_cast<unsigned *>(sW2), W2, C2);
+    stage_weights16<C2>(reinterpret_cast<unsigned *>(sW3), W3, C3);
     for (int i = t; i < C1; i += kMlpThreads) sb1[i] = b1[i];
     for (int i = t; i < C2; i += kMlpThreads) sb2[i] = b2[i];
     for (int i = t; i < C3; i += kMlpThreads) sb3[i] = b3[i];
@@ -256,7 +323,8 @@ sa_fused_narrow_kernel(int c, int n, int m, float r2, int nsample, const float *
     pdab::ball_scan_to_smem<kThreads, kStride>(n, xyz, active, cx, cy, cz, r2, nsample, tile, sidx);
 
     const int nctr = min(kThreads, m - j0);
-    mlp_phase<C0P, C1, C2, C3>(c, n, nsample, nctr, xyz, features, sW1, sb1, sW2, sb2, sW3, sb3, sctr, sidx, sout);
+    mlp_phase<C0P, C1, C2, C3>(c, n, nsample, nctr, xyz, features, sW1, sb1, reinterpret_cast<const unsigned *>(sW2), sb2,
+                               reinterpret_cast<const unsigned *>(sW3), sb3, sctr, sidx, sout);
     __syncthreads();
     for (int i = t; i < C3 * nctr; i += kMlpThreads) {
         const int r = i / nctr, jl = i - r * nctr;
@@ -269,7 +337,7 @@ int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const f
                   const float *features, const float *const *W, const float *const *B, float *out,
                   cudaStream_t stream) {
     const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
-                        sizeof(float) * (C1 * wpitch(C0P) + C2 * wpitch(C1) + C3 * wpitch(C2) + C1 + C2 + C3 +
+                        sizeof(float) * (C1 * wpitch(C0P) + C2 * 2 * p16(C1) + C3 * 2 * p16(C2) + C1 + C2 + C3 +
                                          3 * kThreads + C3 * kStride) +
                         sizeof(int) * (size_t)nsample * kStride;
     auto kern = sa_fused_narrow_kernel<C0P, C1, C2, C3>;
@@ -299,9 +367,9 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
     float *sWa1 = reinterpret_cast<float *>(tile + pdab::kScanTile + 8);
-    float *sWa2 = sWa1 + A1 * wpitch(C0P), *sWa3 = sWa2 + A2 * wpitch(A1);
-    float *sWb1 = sWa3 + A3 * wpitch(A2), *sWb2 = sWb1 + B1 * wpitch(C0P), *sWb3 = sWb2 + B2 * wpitch(B1);
-    float *sba1 = sWb3 + B3 * wpitch(B2), *sba2 = sba1 + A1, *sba3 = sba2 + A2;
+    float *sWa2 = sWa1 + A1 * wpitch(C0P), *sWa3 = sWa2 + A2 * 2 * p16(A1);      // layers 2, 3: packed bf16 (hi | lo)
+    float *sWb1 = sWa3 + A3 * 2 * p16(A2), *sWb2 = sWb1 + B1 * wpitch(C0P), *sWb3 = sWb2 + B2 * 2 * p16(B1);
+    float *sba1 = sWb3 + B3 * 2 * p16(B2), *sba2 = sba1 + A1, *sba3 = sba2 + A2;
     float *sbb1 = sba3 + A3, *sbb2 = sbb1 + B1, *sbb3 = sbb2 + B2;
     float *sctr = sbb3 + B3;                                          // 3 x kThreads
     float *sout = sctr + 3 * kThreads;                                // (A3 + B3) x kStride
@@ -319,10 +387,10 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
 
     stage_weights<C0P>(sWa1, Wa1, A1, c0);
     stage_weights<C0P>(sWb1, Wb1, B1, c0);
-    stage_weights<A1>(sWa2, Wa2, A2, A1);
-    stage_weights<A2>(sWa3, Wa3, A3, A2);
-    stage_weights<B1>(sWb2, Wb2, B2, B1);
-    stage_weights<B2>(sWb3, Wb3, B3, B2);
+    stage_weights16<A1>(reinterpret_cast<unsigned *>(sWa2), Wa2, A2);
+    stage_weights16<A2>(reinterpret_cast<unsigned *>(sWa3), Wa3, A3);
+    stage_weights16<B1>(reinterpret_cast<unsigned *>(sWb2), Wb2, B2);
+    stage_weights16<B2>(reinterpret_cast<unsigned *>(sWb3), Wb3, B3);
     for (int i = t; i < A1; i += kMlpThreads) sba1[i] = ba1[i];
     for (int i = t; i < A2; i += kMlpThreads) sba2[i] = ba2[i];
     for (int i = t; i < A3; i += kMlpThreads) sba3[i] = ba3[i];
@@ -353,9 +421,10 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     }
 
     const int nctr = min(kThreads, m - j0);
-    mlp_phase<C0P, A1, A2, A3>(c, n, ns_a, nctr, xyz, features, sWa1, sba1, sWa2, sba2, sWa3, sba3, sctr, sidx_a, sout);
-    mlp_phase<C0P, B1, B2, B3>(c, n, ns_b, nctr, xyz, features, sWb1, sbb1, sWb2, sbb2, sWb3, sbb3, sctr, sidx_b,
-                               sout + A3 * kStride);
+    mlp_phase<C0P, A1, A2, A3>(c, n, ns_a, nctr, xyz, features, sWa1, sba1, reinterpret_cast<const unsigned *>(sWa2), sba2,
+                               reinterpret_cast<const unsigned *>(sWa3), sba3, sctr, sidx_a, sout);
+    mlp_phase<C0P, B1, B2, B3>(c, n, ns_b, nctr, xyz, features, sWb1, sbb1, reinterpret_cast<const unsigned *>(sWb2), sbb2,
+                               reinterpret_cast<const unsigned *>(sWb3), sbb3, sctr, sidx_b, sout + A3 * kStride);
     __syncthreads();
     for (int i = t; i < (A3 + B3) * nctr; i += kMlpThreads) {
         const int r = i / nctr, jl = i - r * nctr;
@@ -432,8 +501,8 @@ int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns
                 const float *new_xyz, const float *features, const float *const *W, const float *const *B, float *out,
                 void *workspace, cudaStream_t stream) {
     const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) +
-                        sizeof(float) * (A1 * wpitch(C0P) + A2 * wpitch(A1) + A3 * wpitch(A2) + B1 * wpitch(C0P) +
-                                         B2 * wpitch(B1) + B3 * wpitch(B2) + A1 + A2 + A3 + B1 + B2 + B3 + 3 * kThreads +
+                        sizeof(float) * (A1 * wpitch(C0P) + A2 * 2 * p16(A1) + A3 * 2 * p16(A2) + B1 * wpitch(C0P) +
+                                         B2 * 2 * p16(B1) + B3 * 2 * p16(B2) + A1 + A2 + A3 + B1 + B2 + B3 + 3 * kThreads +
                                          (A3 + B3) * kStride) +
                         sizeof(int) * (size_t)(ns_a + ns_b) * kStride;
     dim3 grid(pdab::div_up(m, kThreads), b);
