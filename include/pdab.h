@@ -242,6 +242,11 @@ int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilo
                    const float *w_packed, const float *bias, const float *residual, int ldr, const float *gamma,
                    const float *beta, float eps, int nsample, float *out, int ldo, pdab_stream_t stream);
 
+/* Largest thread-block cluster (CTAs per scene) the n > 16384 FPS path may use beyond the minimum that holds the scene
+ * (default 16: shortest chain).  A caller that pipelines batches lowers it so one batch's FPS chain occupies few SMs and runs
+ * beside the other batches' kernels; results do not change.  Process-wide; 1 <= n <= 16. */
+int pdab_set_fps_max_cluster(int n);
+
 /* Grid size of the persistent tensor-core kernels (default 148 = one CTA per SM).  A caller that pipelines batches on
  * several streams lowers it (e.g. 148 - scenes per batch) so the persistent grid never queues behind the one-CTA-per-
  * scene FPS kernels of another batch.  Process-wide; 1 <= n <= 148. */

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "pdab_sa_grid_workspace_bytes": (_sz, [_i, _i]),
     "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
     "pdab_set_persistent_ctas": (_i, [_i]),
+    "pdab_set_fps_max_cluster": (_i, [_i]),
     "pdab_set_cta_pairs": (_i, [_i]),
     "pdab_tc_packed_floats": (_sz, [_i, _i, _i, _i]),
     "pdab_tc_pack_weights": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),

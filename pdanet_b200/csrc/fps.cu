@@ -23,13 +23,17 @@
 namespace cg = cooperative_groups;
 
 namespace pdab {
-int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream);
+int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, int CL, cudaStream_t stream);
 }
 
 namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kMaxCluster = 16;
+// Largest cluster (CTAs per scene) the N > 16384 path may grow to.  Default 16: as many SMs per scene as fit, shortest chain.
+// A caller that pipelines batches lowers it (pdab_set_fps_max_cluster) so that the FPS chain of one batch occupies few SMs
+// and runs beside the other batches' kernels instead of taking the whole GPU.
+int g_max_cluster = kMaxCluster;
 
 struct __align__(16) Candidate {
     unsigned long long key;  // [dist bits | ~tiekey]; 0 = no candidate
@@ -277,7 +281,8 @@ int dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaS
         // A serial chain: more SMs per scene shorten every step (fewer points per thread) as long as the clusters of all
         // scenes are resident together; grow the cluster while the grid still fits the 148 SMs.
         // (clusters of 16 are placed one per GPC at best: stop at the portable size 8 unless the batch is tiny)
-        const int cl_cap = b <= 4 ? kMaxCluster : 8;
+        int cl_cap = b <= 4 ? kMaxCluster : 8;
+        if (cl_cap > g_max_cluster) cl_cap = g_max_cluster;
         while (CL < cl_cap && b * CL * 2 <= pdab::kNumSMs && per > 1) {
             CL *= 2;
             per = pdab::div_up(n, kThreads * CL);
@@ -286,8 +291,20 @@ int dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaS
     const int L = ref_log2_block(n);
     if (!MATRIX && n >= 1024 && n <= 16384 && m > 64) {
         // spatially pruned variant: same results, ~N ln m instead of N m point updates
-        const int rc = pdab::fps_pruned(b, n, m, src, temp, idx, L, stream);
+        const int rc = pdab::fps_pruned(b, n, m, src, temp, idx, L, 1, stream);
         if (rc != PDAB_EUNSUPPORTED) return rc;
+    }
+    if (!MATRIX && n > 16384 && m > 64) {
+        // clustered pruned variant: CTA r prunes its own slice of <= 16384 points, the CL local winners are exchanged over
+        // DSMEM.  The smallest cluster that holds the scene, doubled once (8192-point slices: shorter local steps) when
+        // the policy (pdab_set_fps_max_cluster) and the SM count allow.
+        int clp = 1;
+        while (clp * 16384 < n) clp *= 2;
+        if (clp * 2 <= g_max_cluster && b * clp * 2 <= pdab::kNumSMs) clp *= 2;
+        if (clp <= kMaxCluster) {
+            const int rc = pdab::fps_pruned(b, n, m, src, temp, idx, L, clp, stream);
+            if (rc != PDAB_EUNSUPPORTED) return rc;
+        }
     }
     if (per <= 1) return launch<1, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
     if (per <= 2) return launch<2, MATRIX>(b, n, m, src, temp, idx, L, CL, stream);
@@ -297,6 +314,12 @@ int dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaS
 }
 
 }  // namespace
+
+extern "C" int pdab_set_fps_max_cluster(int n) {
+    if (n < 1 || n > kMaxCluster) return PDAB_EINVAL;
+    g_max_cluster = n;
+    return 0;
+}
 
 extern "C" int pdab_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, pdab_stream_t stream) {
     return dispatch<false>(b, n, m, xyz, temp, idx, pdab::to_stream(stream));

@@ -1,4 +1,7 @@
-// Pruned farthest-point sampling for sm_100a (N <= 16384 per scene, one CTA per scene).
+// Pruned farthest-point sampling for sm_100a: one CTA per scene for N <= 16384, a thread-block cluster of CL CTAs per scene
+// beyond that (CTA r owns the contiguous slice [r * ceil(N / CL), ...) of the scene, Morton-sorted and pruned locally; the CL
+// local winners of a step are exchanged through distributed shared memory — st.async into every peer's buffer, completion on
+// the receiver's mbarrier, no cluster barrier in the loop — and every CTA picks the same global winner).
 //
 // FPS is a serial chain of m-1 steps; the plain kernel (fps.cu) touches all N points in every
 // step although a new sample only lowers the min-distance of the points in its own neighbourhood
@@ -59,6 +62,13 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every 
 }
 
 
+struct __align__(16) Candidate {
+    unsigned long long key;  // [dist bits | ~tiekey]; 0 = no candidate
+    float x, y, z;
+    float pad;
+};
+constexpr int kMaxCluster = 16;
+
 struct __align__(16) WarpBest {
     unsigned long long key;
     int slot;
@@ -71,10 +81,10 @@ struct __align__(16) WarpBest {
 // loop: BPW = 64 on 8 warps measured 3.4 us/step because the 60 KB body thrashed the instruction
 // cache; 16 buckets on 32 warps keeps it near 14 KB.
 // PPL points per lane per bucket: a bucket is 32*PPL Morton-consecutive points.
-template <int WARPS, int BPW, int PPL>
+template <int WARPS, int BPW, int PPL, bool CLUSTER>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
-                  int *__restrict__ idx_all, int L) {
+fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
+                  int *__restrict__ idx_all, int L, int CL) {
     constexpr int kWarps = WARPS, kInitThreads = WARPS * 32;
     constexpr int CAP = kWarps * BPW * 32 * PPL;
     constexpr int BPL = 1;  // buckets tested per lane
@@ -86,12 +96,31 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     unsigned short *sorig = reinterpret_cast<unsigned short *>(smem_raw + (size_t)12 * CAP);
     __shared__ int sbox[6];
     __shared__ WarpBest red[2][kWarps];
+    __shared__ Candidate xchg[2][kMaxCluster];
+    __shared__ __align__(8) unsigned long long xbar[2];  // mbarriers: the candidates of all CL CTAs have landed in xchg[buf]
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int scene = blockIdx.x;
-    const float *xyz = xyz_all + (size_t)scene * n * 3;
-    float *temp = temp_all + (size_t)scene * n;
+    unsigned rank = 0;
+    if (CLUSTER) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int scene = CLUSTER ? blockIdx.x / CL : blockIdx.x;
+    // this CTA's slice of the scene: local point k <-> scene point base + k
+    const int chunk = CLUSTER ? (n_scene + CL - 1) / CL : n_scene;
+    const int base = (int)rank * chunk;
+    const int n = max(0, min(chunk, n_scene - base));
+    const float *xyz0 = xyz_all + (size_t)scene * n_scene * 3;   // the scene (point 0 seeds the chain)
+    const float *xyz = xyz0 + (size_t)base * 3;
+    float *temp = temp_all + (size_t)scene * n_scene + base;
     int *idxs = idx_all + (size_t)scene * m;
+    if (CLUSTER) {
+        if (t == 0) {
+            for (int i = 0; i < 2; i++)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&xbar[i])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // peers resident and their barriers initialised before any DSMEM store (the sort below gives plenty of slack, but
+        // correctness must not depend on it)
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
 
     // ---- 0. scene bounding box -------------------------------------------------------------
     if (t < 3) sbox[t] = 0x7fffffff;
@@ -199,7 +228,7 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
 #pragma unroll
             for (int q = 0; q < PPL; q++)
                 if (dv[q] == mv) {
-                    const unsigned c = ~tie_key((int)sorig[slot_of(i, q)], L);
+                    const unsigned c = ~tie_key(base + (int)sorig[slot_of(i, q)], L);
                     if (c > lo) {
                         lo = c;
                         myq = q;
@@ -254,8 +283,8 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
     }
 
     int old = 0;
-    float x1 = __ldg(xyz + 0), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
-    if (t == 0) idxs[0] = 0;
+    float x1 = __ldg(xyz0 + 0), y1 = __ldg(xyz0 + 1), z1 = __ldg(xyz0 + 2);
+    if (t == 0 && rank == 0) idxs[0] = 0;
 
     int buf = 0;
     for (int it = 1; it < m; it++) {
@@ -320,11 +349,66 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
         const unsigned long long best = warp_max_u64(rkey);
         const unsigned src = __ballot_sync(0xffffffffu, rkey == best && lane < kWarps);
         const int slot = __shfl_sync(0xffffffffu, rslot, __ffs(src) - 1);
-        old = tie_key_decode(~(unsigned)best, L);
-        x1 = sx[slot];
-        y1 = sy[slot];
-        z1 = sz[slot];
-        if (t == 0) idxs[it] = old;
+        if (!CLUSTER) {
+            old = tie_key_decode(~(unsigned)best, L);
+            x1 = sx[slot];
+            y1 = sy[slot];
+            z1 = sz[slot];
+        } else {
+            // every CTA pushes its 32-byte candidate into each peer's xchg[buf][rank] with st.async, which completes on the
+            // RECEIVER's mbarrier; a CTA waits for CL x 32 bytes on its own barrier.  Buffer reuse is safe: a peer can only
+            // send step it+2 after it has consumed step it+1, which needs this CTA's step it+1 candidate, which is sent
+            // after this CTA's block barrier of step it+1, i.e. after all its threads have read step it's buffer.
+            const unsigned bar_local = (unsigned)__cvta_generic_to_shared(&xbar[buf]);
+            if (t == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local), "r"(CL * 32)
+                             : "memory");
+            if (t < CL) {
+                float cx = 0.f, cy = 0.f, cz = 0.f;
+                if (best != 0ull) {
+                    cx = sx[slot];
+                    cy = sy[slot];
+                    cz = sz[slot];
+                }
+                const unsigned dst_local = (unsigned)__cvta_generic_to_shared(&xchg[buf][rank]);
+                unsigned dst, rbar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(t));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_local), "r"(t));
+                asm volatile(
+                    "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                    "r"((unsigned)best), "r"((unsigned)(best >> 32)), "r"(__float_as_uint(cx)), "r"(__float_as_uint(cy)),
+                    "r"(rbar)
+                    : "memory");
+                asm volatile(
+                    "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst + 16),
+                    "r"(__float_as_uint(cz)), "r"(0u), "r"(0u), "r"(0u), "r"(rbar)
+                    : "memory");
+            }
+            {
+                const unsigned parity = (unsigned)(((it - 1) >> 1) & 1);   // buffer `buf` is used every second step
+                unsigned ok = 0;
+                const long long t0 = clock64();
+                while (!ok) {
+                    asm volatile(
+                        "{\n.reg .pred p;\n"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                        "selp.u32 %0, 1, 0, p;\n}"
+                        : "=r"(ok)
+                        : "r"(bar_local), "r"(parity)
+                        : "memory");
+                    if (!ok && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU on a protocol bug
+                }
+            }
+            // every warp picks the winner itself: lane i holds CTA i's key, REDUX max, lowest lane with the max
+            const unsigned long long mine = lane < CL ? xchg[buf][lane].key : 0ull;
+            const unsigned long long w = warp_max_u64(mine);
+            const int wi = __ffs(__ballot_sync(0xffffffffu, mine == w && lane < CL)) - 1;
+            old = tie_key_decode(~(unsigned)w, L);
+            x1 = xchg[buf][wi].x;
+            y1 = xchg[buf][wi].y;
+            z1 = xchg[buf][wi].z;
+        }
+        if (t == 0 && rank == 0) idxs[it] = old;
         buf ^= 1;
     }
 
@@ -335,16 +419,38 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ xyz_all, float *__rest
             const int slot = slot_of(i, q);
             if (slot < n) temp[sorig[slot]] = d[i][q];
         }
+    // nobody exits while a peer's last st.async may still target its shared memory
+    if (CLUSTER) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 template <int WARPS, int BPW, int PPL>
-int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
+int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, int CL, cudaStream_t stream) {
     constexpr int CAP = WARPS * BPW * 32 * PPL;
     constexpr int kInitThreads = WARPS * 32;
     const size_t smem = (size_t)12 * CAP + (size_t)2 * CAP;
-    auto kern = fps_pruned_kernel<WARPS, BPW, PPL>;
+    if (CL == 1) {
+        auto kern = fps_pruned_kernel<WARPS, BPW, PPL, false>;
+        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<b, kInitThreads, smem, stream>>>(n, m, xyz, temp, idx, L, 1);
+        PDAB_LAUNCH_CHECK();
+        return 0;
+    }
+    auto kern = fps_pruned_kernel<WARPS, BPW, PPL, true>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<b, kInitThreads, smem, stream>>>(n, m, xyz, temp, idx, L);
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(b * CL);
+    cfg.blockDim = dim3(kInitThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PDAB_CUDA(cudaLaunchKernelEx(&cfg, kern, n, m, xyz, temp, idx, L, CL));
     PDAB_LAUNCH_CHECK();
     return 0;
 }
@@ -354,16 +460,19 @@ int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, 
 namespace pdab {
 
 // Returns PDAB_EUNSUPPORTED when the pruned kernel does not cover the size (caller falls back to fps.cu).
-int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, cudaStream_t stream) {
-    if (n > 16384 || n < 1) return PDAB_EUNSUPPORTED;
+// CL > 1: a cluster of CL CTAs per scene, each holding ceil(n / CL) <= 16384 points.
+int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, int CL, cudaStream_t stream) {
+    if (CL < 1 || CL > kMaxCluster || n < 1) return PDAB_EUNSUPPORTED;
+    const int per_cta = (n + CL - 1) / CL;
+    if (per_cta > 16384) return PDAB_EUNSUPPORTED;
     static const int variant = getenv("PDAB_FPS_VARIANT") ? atoi(getenv("PDAB_FPS_VARIANT")) : 0;  // tuning aid
-    const int sz = n <= 2048 ? 0 : n <= 4096 ? 1 : n <= 8192 ? 2 : 3;
+    const int sz = per_cta <= 2048 ? 0 : per_cta <= 4096 ? 1 : per_cta <= 8192 ? 2 : 3;
 #define PDAB_FPS_CASE(V, W, B0, B1, B2, B3, P)                                        \
     if (variant == V) {                                                                \
-        if (sz == 0) return launch<W, B0, P>(b, n, m, xyz, temp, idx, L, stream);      \
-        if (sz == 1) return launch<W, B1, P>(b, n, m, xyz, temp, idx, L, stream);      \
-        if (sz == 2) return launch<W, B2, P>(b, n, m, xyz, temp, idx, L, stream);      \
-        return launch<W, B3, P>(b, n, m, xyz, temp, idx, L, stream);                   \
+        if (sz == 0) return launch<W, B0, P>(b, n, m, xyz, temp, idx, L, CL, stream);      \
+        if (sz == 1) return launch<W, B1, P>(b, n, m, xyz, temp, idx, L, CL, stream);      \
+        if (sz == 2) return launch<W, B2, P>(b, n, m, xyz, temp, idx, L, CL, stream);      \
+        return launch<W, B3, P>(b, n, m, xyz, temp, idx, L, CL, stream);                   \
     }
     PDAB_FPS_CASE(1, 32, 2, 4, 8, 16, 1)   // 32 warps, 32-point buckets
     PDAB_FPS_CASE(2, 16, 2, 4, 8, 16, 2)   // 16 warps, 64-point buckets

@@ -94,8 +94,17 @@ class ScenePipeline:
         dev, B, N = runner.device, runner.batch_size, runner.num_points
         self.model = runner.model
         self.launches_per_step = 0
-        if reserve_sms is None:  # one SM per scene of ONE in-flight FPS kernel (deeper pipelines rarely overlap two)
-            reserve_sms = B if depth > 1 and B < 100 else 0
+        # N > 16384: a scene's FPS runs on a cluster of CTAs; pipelined, the smallest cluster that holds the scene (16384
+        # points per CTA) keeps the chain on few SMs beside the other batches' kernels instead of taking the whole GPU
+        fps_ctas = -(-N // 16384)
+        if depth > 1 and fps_ctas > 1:
+            cl = 1
+            while cl < fps_ctas:
+                cl *= 2
+            fps_ctas = cl
+            _lib.check("pdab_set_fps_max_cluster", _lib.lib().pdab_set_fps_max_cluster(min(16, cl)))
+        if reserve_sms is None:  # one SM per FPS CTA of ONE in-flight FPS kernel (deeper pipelines rarely overlap two)
+            reserve_sms = B * fps_ctas if depth > 1 and B * fps_ctas < 100 else 0
         self.reserve_sms = reserve_sms
         _lib.check("pdab_set_persistent_ctas", _lib.lib().pdab_set_persistent_ctas(148 - reserve_sms))
         if warm_points is None:
