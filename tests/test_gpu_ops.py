@@ -84,6 +84,10 @@ FPS_CASES = [
     ("flat_plane", 1, 6000, 700, dict(lo=(0.0, -40.0, -1.7), hi=(70.4, 40.0, -1.7))),
     ("cluster2_20000", 1, 20000, 256, dict(duplicate_frac=0.05)),
     ("cluster4_once", 1, 65536, 128, {}),
+    # clustered pruned kernel (slice per CTA, winners exchanged over DSMEM): ties across slices, ragged last slice
+    ("cluster_grid_ties", 1, 40000, 300, dict(quantize=1.0, duplicate_frac=0.2)),
+    ("cluster_ragged_33333", 2, 33333, 200, dict(quantize=2.0)),
+    ("cluster_all_equal", 1, 20000, 80, dict(lo=(1.0, 1.0, 1.0), hi=(1.0, 1.0, 1.0))),
 ]
 
 
