@@ -178,8 +178,10 @@ int pdab_add_maxpool(long long groups, int nsample, int e, const float *a_hi, co
  * replaces: the attention core of nn.MultiheadAttention in TransformerEncoderLayerPreNorm (q/k/v permutes, 2 bmm,
  *           softmax, permute back), PB/PointFormer.py:30, PB/pointnet2_modules.py:929.
  * qkv (groups*nsample, 3*heads*head_dim) = [q | k | v] rows as in_proj leaves them; the nsample rows of a group are
- * consecutive; ctx (groups*nsample, heads*head_dim).  nsample in {16, 32}, head_dim in {64, 128}. */
-int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, const float *qkv, float *ctx,
+ * consecutive; ctx (groups*nsample, heads*head_dim).  nsample in {16, 32}, head_dim in {64, 128}.
+ * npass: product class of the two contractions on mma.sync — 3 (or 1): error-compensated 3xTF32 (fp32-level); 2: split-bf16
+ * m16n8k16 (hi / lo bf16 pairs, ~2^-17 per product, the class of the split-bf16 GEMMs; half the instructions). */
+int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, int npass, const float *qkv, float *ctx,
                          pdab_stream_t stream);
 
 /* Fused plain set-abstraction scale: ball query -> group (xyz centred) -> shared MLP

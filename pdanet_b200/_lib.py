@@ -41,7 +41,7 @@ _SIGNATURES = {
     "pdab_add_ln_split": (_i, [C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "pdab_relu_split": (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
     "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "pdab_group_attention": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
+    "pdab_group_attention": (_i, [C.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_fused_pair": (_i, [_i, _i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_grid_workspace_bytes": (_sz, [_i, _i]),

@@ -27,11 +27,13 @@ namespace {
 
 constexpr int kThreads = 128;
 
-template <int NS, int HD>
+// BF: bf16 m16n8k16 split products (hi / lo bf16 pairs, three MMAs per k-step: the product class of the split-bf16 GEMMs, half
+// the mma.sync count of the TF32 path).  Its fragments are 8-byte pairs, which want other conflict-free pitches.
+template <int NS, int HD, bool BF = false>
 struct AttnSmem {
-    static constexpr int QP = HD + 4;   // Q, K row pitch (floats)
-    static constexpr int VP = HD + 8;   // V row pitch
-    static constexpr int PP = NS + 4;   // S / P row pitch
+    static constexpr int QP = BF ? HD + 8 : HD + 4;   // Q, K row pitch (floats)
+    static constexpr int VP = BF ? HD + 4 : HD + 8;   // V row pitch
+    static constexpr int PP = BF ? NS + 8 : NS + 4;   // S / P row pitch
     static constexpr int FLOATS = 2 * NS * QP + NS * VP + NS * PP;
     static constexpr int BYTES = FLOATS * 4;
 };
@@ -56,10 +58,33 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
     mma_tf32(d, ah, bh);
 }
 
-template <int NS, int HD>
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma16_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                         const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_bf16(d, ah, bl);  // small terms first
+    mma_bf16(d, al, bh);
+    mma_bf16(d, ah, bh);
+}
+// packed (hi, lo) pair of two consecutive floats at p
+__device__ __forceinline__ void pair_at(const float *p, uint32_t &hi, uint32_t &lo) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    split_bf16x2(v.x, v.y, hi, lo);
+}
+
+template <int NS, int HD, bool BF>
 __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long groups, int heads, const float *__restrict__ qkv,
                                                                    float *__restrict__ ctx) {
-    using SM = AttnSmem<NS, HD>;
+    using SM = AttnSmem<NS, HD, BF>;
     constexpr int QP = SM::QP, VP = SM::VP, PP = SM::PP;
     constexpr int MT = NS / 16;             // m-tiles (16 query rows each): 1 or 2
     constexpr int NW = 4 / MT;              // warps along n
@@ -104,6 +129,24 @@ __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long gro
         float acc[S_NT][4];
 #pragma unroll
         for (int n = 0; n < S_NT; n++) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        if constexpr (BF) {
+#pragma unroll 4
+            for (int k0 = 0; k0 < HD; k0 += 16) {   // A: rows g, g + 8, columns k0 + 2t (+1) and k0 + 8 + 2t (+1)
+                uint32_t ah[4], al[4];
+                pair_at(sQ + (m0 + g) * QP + k0 + 2 * t, ah[0], al[0]);
+                pair_at(sQ + (m0 + g + 8) * QP + k0 + 2 * t, ah[1], al[1]);
+                pair_at(sQ + (m0 + g) * QP + k0 + 8 + 2 * t, ah[2], al[2]);
+                pair_at(sQ + (m0 + g + 8) * QP + k0 + 8 + 2 * t, ah[3], al[3]);
+#pragma unroll
+                for (int n = 0; n < S_NT; n++) {
+                    const int n0 = (nw * S_NT + n) * 8;
+                    uint32_t bh[2], bl[2];
+                    pair_at(sK + (n0 + g) * QP + k0 + 2 * t, bh[0], bl[0]);
+                    pair_at(sK + (n0 + g) * QP + k0 + 8 + 2 * t, bh[1], bl[1]);
+                    mma16_3x(acc[n], ah, al, bh, bl);
+                }
+            }
+        } else {
 #pragma unroll 4
         for (int k0 = 0; k0 < HD; k0 += 8) {
             uint32_t ah[4], al[4];
@@ -119,6 +162,7 @@ __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long gro
                 split_tf32(sK[(n0 + g) * QP + k0 + t + 4], bh[1], bl[1]);
                 mma_3x(acc[n], ah, al, bh, bl);
             }
+        }
         }
 #pragma unroll
         for (int n = 0; n < S_NT; n++) {
@@ -162,6 +206,24 @@ __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long gro
         float acc[O_NT][4];
 #pragma unroll
         for (int n = 0; n < O_NT; n++) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        if constexpr (BF) {
+#pragma unroll
+            for (int k0 = 0; k0 < NS; k0 += 16) {
+                uint32_t ah[4], al[4];
+                pair_at(sP + (m0 + g) * PP + k0 + 2 * t, ah[0], al[0]);
+                pair_at(sP + (m0 + g + 8) * PP + k0 + 2 * t, ah[1], al[1]);
+                pair_at(sP + (m0 + g) * PP + k0 + 8 + 2 * t, ah[2], al[2]);
+                pair_at(sP + (m0 + g + 8) * PP + k0 + 8 + 2 * t, ah[3], al[3]);
+#pragma unroll
+                for (int n = 0; n < O_NT; n++) {
+                    const int n0 = (nw * O_NT + n) * 8;
+                    uint32_t bh[2], bl[2];   // B: keys k0 + 2t, + 1 (and + 8, + 9), channel n0 + g
+                    split_bf16x2(sV[(k0 + 2 * t) * VP + n0 + g], sV[(k0 + 2 * t + 1) * VP + n0 + g], bh[0], bl[0]);
+                    split_bf16x2(sV[(k0 + 8 + 2 * t) * VP + n0 + g], sV[(k0 + 9 + 2 * t) * VP + n0 + g], bh[1], bl[1]);
+                    mma16_3x(acc[n], ah, al, bh, bl);
+                }
+            }
+        } else {
 #pragma unroll
         for (int k0 = 0; k0 < NS; k0 += 8) {
             uint32_t ah[4], al[4];
@@ -178,6 +240,7 @@ __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long gro
                 mma_3x(acc[n], ah, al, bh, bl);
             }
         }
+        }
         float *orow0 = ctx + (grp * NS + m0 + g) * (long long)E + h * HD;
         float *orow1 = orow0 + 8LL * E;
 #pragma unroll
@@ -189,10 +252,10 @@ __global__ void __launch_bounds__(kThreads) group_attention_kernel(long long gro
     }
 }
 
-template <int NS, int HD>
+template <int NS, int HD, bool BF>
 int launch(long long groups, int heads, const float *qkv, float *ctx, cudaStream_t s) {
-    using SM = AttnSmem<NS, HD>;
-    auto kern = group_attention_kernel<NS, HD>;
+    using SM = AttnSmem<NS, HD, BF>;
+    auto kern = group_attention_kernel<NS, HD, BF>;
     static bool configured = false;
     if (!configured) {
         PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
@@ -207,14 +270,19 @@ int launch(long long groups, int heads, const float *qkv, float *ctx, cudaStream
 
 }  // namespace
 
-extern "C" int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, const float *qkv,
+extern "C" int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, int npass, const float *qkv,
                                     float *ctx, pdab_stream_t stream) {
-    if (groups < 0 || heads < 1 || !qkv || !ctx) return PDAB_EINVAL;
+    if (groups < 0 || heads < 1 || !qkv || !ctx || npass < 1 || npass > 3) return PDAB_EINVAL;
     if (groups == 0) return 0;
     cudaStream_t s = pdab::to_stream(stream);
-    if (nsample == 16 && head_dim == 64) return launch<16, 64>(groups, heads, qkv, ctx, s);
-    if (nsample == 32 && head_dim == 64) return launch<32, 64>(groups, heads, qkv, ctx, s);
-    if (nsample == 16 && head_dim == 128) return launch<16, 128>(groups, heads, qkv, ctx, s);
-    if (nsample == 32 && head_dim == 128) return launch<32, 128>(groups, heads, qkv, ctx, s);
+    const bool bf = npass == 2;
+#define PDAB_ATTN(NS_, HD_)                                                        \
+    if (nsample == NS_ && head_dim == HD_)                                         \
+        return bf ? launch<NS_, HD_, true>(groups, heads, qkv, ctx, s) : launch<NS_, HD_, false>(groups, heads, qkv, ctx, s);
+    PDAB_ATTN(16, 64)
+    PDAB_ATTN(32, 64)
+    PDAB_ATTN(16, 128)
+    PDAB_ATTN(32, 128)
+#undef PDAB_ATTN
     return PDAB_EUNSUPPORTED;
 }

@@ -122,7 +122,7 @@ class PDAScalePlan:
             ctx = self.in_proj_attn(y, EPI_ATTN, nsample=ns)                    # (T, E); qkv never exists
         else:
             qkv = self.in_proj(y, EPI_STORE)                                    # (T, 3E)
-            ctx = ops.group_attention(qkv, ns, self.heads)                      # (T, E)
+            ctx = ops.group_attention(qkv, ns, self.heads, npass=self.in_proj.npass)   # (T, E)
         z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2)         # LN2(y + attn)
         h = self.lin1(z, EPI_RELU)
         pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)          # max_s (z + ffn), (:931)

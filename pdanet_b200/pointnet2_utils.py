@@ -335,8 +335,9 @@ def pda_assemble_ln(pos, X, scale, glob, nsample, norm):
     return y
 
 
-def group_attention(qkv, nsample, heads):
-    """softmax(q k^T / sqrt(hd)) v inside each neighbourhood of `nsample` consecutive tokens; qkv (T, 3E) -> (T, E)."""
+def group_attention(qkv, nsample, heads, npass: int = 3):
+    """softmax(q k^T / sqrt(hd)) v inside each neighbourhood of `nsample` consecutive tokens; qkv (T, 3E) -> (T, E).
+    npass: 3 = 3xTF32 products (fp32-level), 2 = split-bf16 products (the class of the split-bf16 GEMMs)."""
     if not qkv.is_cuda:
         raise RuntimeError("group_attention needs CUDA tensors")
     T, E3 = qkv.shape
@@ -344,8 +345,8 @@ def group_attention(qkv, nsample, heads):
     assert qkv.is_contiguous() and T % nsample == 0 and E % heads == 0
     ctx = torch.empty(T, E, dtype=torch.float32, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        _lib.call("pdab_group_attention", T // nsample, nsample, heads, E // heads, qkv.data_ptr(), ctx.data_ptr(),
-                  _stream_of(qkv))
+        _lib.call("pdab_group_attention", T // nsample, nsample, heads, E // heads, int(npass), qkv.data_ptr(),
+                  ctx.data_ptr(), _stream_of(qkv))
     return ctx
 
 

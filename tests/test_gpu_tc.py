@@ -127,8 +127,9 @@ def test_large_persistent_many_items():
     assert _rel(out.cpu(), ref.cpu()) < TOL[3]
 
 
+@pytest.mark.parametrize("npass", [3, 2])
 @pytest.mark.parametrize("ns,hd", [(16, 64), (32, 64), (16, 128), (32, 128)])
-def test_group_attention_vs_torch_mha(ns, hd):
+def test_group_attention_vs_torch_mha(ns, hd, npass):
     """pdab_group_attention == the attention core of nn.MultiheadAttention on (ns, groups, E) sequences."""
     from pdanet_b200 import pointnet2_utils as ops
     dev = _dev()
@@ -136,11 +137,11 @@ def test_group_attention_vs_torch_mha(ns, hd):
     E = heads * hd
     g = torch.Generator().manual_seed(ns + hd)
     qkv = torch.randn(groups * ns, 3 * E, generator=g) * 1.5
-    ctx = ops.group_attention(qkv.to(dev), ns, heads).cpu()
+    ctx = ops.group_attention(qkv.to(dev), ns, heads, npass=npass).cpu()
     q, k, v = [t.double().view(groups, ns, heads, hd).permute(0, 2, 1, 3) for t in qkv.split(E, dim=1)]
     att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(groups * ns, E)
-    assert _rel(ctx, ref) < 5e-6
+    assert _rel(ctx, ref) < (5e-6 if npass == 3 else 2 * TOL[2])
 
 
 @pytest.mark.parametrize("npass", [3, 2, 1])
