@@ -12,17 +12,19 @@
 // chain — pdab_pda_group_tokens, 2 GEMM launches, ~10 PyTorch elementwise launches, pdab_pda_assemble_ln_split —
 // moved ~4.9 KB per token at C = 128; this kernel moves 2 KB + L2-resident gathers.)
 //
-// Mapping.  A CTA owns CTR consecutive centres of one scene.  Phase 1: thread per centre scans the cloud in index
-// order (ball_scan.cuh; hit list in shared memory).  Phase 2: a warp takes 32 tokens (32 / nsample neighbourhoods)
-// at a time:
-//   lane = token  : geometry, density, neighbourhood max (segmented shuffles), DensityNet, 12-float encoding -> smem
-//   lane = unit   : hidden layer of the position MLP for 16 tokens (W1 rows live in registers) -> smem
-//   lane = CPL consecutive output channels, 8 tokens in registers: second layer from a transposed smem copy of W2
-//                   (one 16-byte weight read feeds 8 x CPL FMAs; hidden activations are broadcast reads)
-//   then per token the row [pos | feat * scale | feat | glob] is in the lane = 4-consecutive-channels layout, the
-//   two LayerNorm reductions are shuffle sums (8 tokens interleaved for ILP) and the row is stored with fully
-//   coalesced 16-byte writes.
-// CUDA cores by design (north_star: "the PDA distribution-aware feature encoding stays on CUDA cores"); all fp32.
+// Mapping.  A CTA owns 32 consecutive centres of one scene.  Phase 1: CTA-wide ordered ball scan (ball_scan.cuh: lane =
+// centre, every warp scans its own slice of the cloud; hit lists in shared memory).  Phase 2: a warp takes 32 tokens (32 /
+// nsample neighbourhoods) at a time:
+//   lane = token            : geometry, density, neighbourhood max (segmented shuffles), DensityNet, 12-float encoding -> smem
+//   per 16-token m-tile     : position MLP on the warp-level tensor-core path — layer 1 (12 -> C/2) on mma.sync m16n8k8 TF32 with
+//                             the 3x hi/lo compensation, layer 2 (C/2 -> C) on bf16 m16n8k16 split products (the product class
+//                             of the split-bf16 GEMMs; its A fragments are the packed C fragments of layer 1, no re-layout).  The
+//                             first version pushed the layers through the FMA pipe (lane = 4 output channels x 4 tokens): it was
+//                             FMA-issue bound at 43 % pipe utilisation (profiles/r01_ncu_pda_encode_ln_*).
+//   per token row           : [pos | feat * scale | feat | glob] in the MMA C-fragment layout (a quad of lanes owns 32 contiguous
+//                             bytes of a row): LayerNorm statistics are two shuffles inside the quad, the row is written as
+//                             full 32-byte sectors.
+// The encoding itself (density, direction, DensityNet, LayerNorm) stays on CUDA cores (north_star); all accumulation in fp32.
 #include "ball_scan.cuh"
 
 namespace {
@@ -68,6 +70,29 @@ __device__ __forceinline__ void vstore(float *p, const float (&d)[CPL]) {
     else *reinterpret_cast<float2 *>(p) = make_float2(d[0], d[1]);
 }
 
+__host__ __device__ constexpr int p16(int K) { return K / 2 + 4; }   // packed-pair row pitch (words): 4 * odd -> conflict-free
+constexpr int kW1Pitch = 20;                                         // layer-1 weights: 12 inputs padded to 16, + 4
+
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, unsigned &hi, unsigned &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 struct EncParams {
     int n, m, nsample;
     float radius, r2, two_r2, dens_norm, eps;
@@ -78,57 +103,59 @@ struct EncParams {
 // params (floats): W1 [H][12] | b1 [H] | W2t [H][C] | b2 [C] | dens (kDensFloats) | gamma [4C] | beta [4C],  H = C / 2
 template <int C>
 __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncParams p) {
-    constexpr int H = C / 2, CPL = C / 32, HPL = H / 32, E = 4 * C, CTR = 32, STRIDE = CTR + 1;
-    constexpr int TB = CPL == 4 ? 4 : 8;  // tokens per register block of the second layer (TB * CPL accumulators)
+    constexpr int H = C / 2, E = 4 * C, CTR = 32, STRIDE = CTR + 1, P2 = p16(H);
+    constexpr int CPL = C / 32;        // row phase: channels per lane and part
+    constexpr int PP = C + 8;          // pitch of a staged position row: conflict-free float2 fragment stores, 16-byte aligned rows
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *tile = reinterpret_cast<float4 *>(smem_raw);                   // kWarps * kSplitTile
-    float *sW2t = reinterpret_cast<float *>(tile + kWarps * pdab::kSplitTile);  // H * C
-    float *sb2 = sW2t + H * C;                                             // C
+    unsigned *sW2h = reinterpret_cast<unsigned *>(smem_raw);               // C x P2 packed bf16 pairs (hi)
+    unsigned *sW2l = sW2h + C * P2;                                        // C x P2 (lo)
+    float *sW1 = reinterpret_cast<float *>(sW2l + C * P2);                 // H x kW1Pitch (12 inputs padded to 16 with zeros)
+    float *sb1 = sW1 + H * kW1Pitch;                                       // H
+    float *sb2 = sb1 + H;                                                  // C
     float *sgamma = sb2 + C;                                               // E
     float *sbeta = sgamma + E;                                             // E
     float *sdens = sbeta + E;                                              // kDensFloats
-    float *sb1 = sdens + kDensFloats;                                      // H
-    float *sW1t = sb1 + H;                                                 // 12 * H (transposed; used when HPL == 2)
-    float *sctr = sW1t + 12 * H;                                           // 3 * CTR
+    float *sctr = sdens + kDensFloats;                                     // 3 * CTR
     int *sidx = reinterpret_cast<int *>(sctr + 3 * CTR);                   // nsample * STRIDE
-    // phase-1 scratch (per-slice hit lists) and phase-2 scratch (encodings, hidden activations) share one region
-    float *srppe_all = reinterpret_cast<float *>(sidx + p.nsample * STRIDE);   // kWarps * 32 * 12
-    float *sh_all = srppe_all + kWarps * 32 * 12;                          // kWarps * 16 * H
-    int *slist = reinterpret_cast<int *>(srppe_all);                       // kWarps * nsample * 33
+    // one region for the phase-1 scratch (staging tiles, per-slice hit lists) and the phase-2 scratch (encodings, position rows)
+    unsigned char *uni = reinterpret_cast<unsigned char *>(sidx + ((p.nsample * STRIDE + 3) & ~3));
+    float4 *tile = reinterpret_cast<float4 *>(uni);                        // kWarps * kSplitTile
+    int *slist = reinterpret_cast<int *>(tile + kWarps * pdab::kSplitTile);  // kWarps * nsample * 33
     int *scnt = slist + kWarps * p.nsample * 33;                           // kWarps * 32
+    float *srppe_all = reinterpret_cast<float *>(uni);                     // kWarps * 32 * 12
+    float *spos_all = srppe_all + kWarps * 32 * 12;                        // kWarps * 8 * PP
 
     const int scene = blockIdx.y;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g = lane >> 2, t4 = lane & 3;                                // MMA fragment coordinates
     const int j0 = blockIdx.x * CTR;
     const int ns = p.nsample;
     const float *xyz = p.xyz + (size_t)scene * p.n * 3;
     const float *features_t = p.features_t + (size_t)scene * p.n * C;
 
-    // ---- parameters -> shared memory / registers
+    // ---- parameters -> shared memory
     const float *gW1 = p.params, *gb1 = gW1 + H * 12, *gW2t = gb1 + H, *gb2 = gW2t + H * C, *gdens = gb2 + C,
                 *ggamma = gdens + kDensFloats, *gbeta = ggamma + E;
-    for (int i = t; i < H * C / 4; i += kThreads)
-        reinterpret_cast<float4 *>(sW2t)[i] = __ldg(reinterpret_cast<const float4 *>(gW2t) + i);
+    for (int i = t; i < H * kW1Pitch; i += kThreads) {
+        const int r = i / kW1Pitch, q = i - r * kW1Pitch;
+        sW1[i] = q < 12 ? __ldg(gW1 + r * 12 + q) : 0.f;
+    }
+    for (int i = t; i < C * (H / 2); i += kThreads) {      // W2 (C x H) = W2t^T, packed: word (n, j) = inputs 2j, 2j + 1 of output n
+        const int n = i / (H / 2), j = i - n * (H / 2);
+        unsigned hi, lo;
+        split_bf16x2(__ldg(gW2t + (2 * j) * C + n), __ldg(gW2t + (2 * j + 1) * C + n), hi, lo);
+        sW2h[n * P2 + j] = hi;
+        sW2l[n * P2 + j] = lo;
+    }
+    for (int i = t; i < H; i += kThreads) sb1[i] = __ldg(gb1 + i);
     for (int i = t; i < C; i += kThreads) sb2[i] = __ldg(gb2 + i);
     for (int i = t; i < E; i += kThreads) {
         sgamma[i] = __ldg(ggamma + i);
         sbeta[i] = __ldg(gbeta + i);
     }
     for (int i = t; i < kDensFloats; i += kThreads) sdens[i] = __ldg(gdens + i);
-    for (int i = t; i < H; i += kThreads) sb1[i] = __ldg(gb1 + i);
-    // first-layer weights: one hidden unit per lane keeps its row in registers; with two units per lane (C = 128) that
-    // would push the token phase past 128 registers, so the rows are read from a transposed (conflict-free) smem copy
-    constexpr int W1R = HPL == 1 ? 12 : 1;
-    float w1[W1R];
-    if constexpr (HPL == 1) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) w1[i] = __ldg(gW1 + lane * 12 + i);
-    } else {
-        w1[0] = 0.f;
-    }
-    for (int i = t; i < 12 * H; i += kThreads) sW1t[i] = __ldg(gW1 + (i % H) * 12 + i / H);
 
-    // ---- phase 1: ordered ball scan, thread per centre
+    // ---- phase 1: ordered ball scan, lane = centre, every warp scans its slice of the cloud
     const int j = j0 + lane;
     const bool active = j < p.m;
     float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -151,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
     float *obase = p.out + ((size_t)scene * p.m + j0) * ns * E;
     const float *gbase = p.glob + ((size_t)scene * p.m + j0) * C;
     float *srppe = srppe_all + warp * 32 * 12;
-    float *sh = sh_all + warp * 16 * H;
+    float *spos = spos_all + warp * 8 * PP;
 
     for (int pass = warp; pass < npass; pass += kWarps) {
         // lane = token: geometry, density scale, encoding
@@ -190,130 +217,148 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
         __syncwarp();
 
 #pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            // lane = hidden unit(s): first layer of the position MLP for 16 tokens
-#pragma unroll 4
-            for (int tk = 0; tk < 16; tk++) {
-                const float4 *r = reinterpret_cast<const float4 *>(srppe + (half * 16 + tk) * 12);
-                const float4 r0 = r[0], r1 = r[1], r2 = r[2];
-                const float rv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+        for (int mt = 0; mt < 2; mt++) {                       // 16 tokens = one m-tile, inside one neighbourhood (16 | ns)
+            const int tok0 = pass * 32 + 16 * mt;
+            if (tok0 >= ntok) break;                           // warp-uniform
+            // ---- layer 1: h1 = relu(W1 . rppe + b1), 12 (padded to 16) -> H, TF32 with the 3x compensation
+            float h1[H / 8][4];
 #pragma unroll
-                for (int u = 0; u < HPL; u++) {
-                    float a = sb1[lane + 32 * u];
-#pragma unroll
-                    for (int i = 0; i < 12; i++)
-                        a = fmaf(HPL == 1 ? w1[i % W1R] : sW1t[i * H + lane + 32 * u], rv[i], a);
-                    sh[tk * H + lane + 32 * u] = fmaxf(a, 0.f);
-                }
+            for (int nt = 0; nt < H / 8; nt++) {
+                const float b0 = sb1[nt * 8 + 2 * t4], b1 = sb1[nt * 8 + 2 * t4 + 1];
+                h1[nt][0] = b0, h1[nt][1] = b1, h1[nt][2] = b0, h1[nt][3] = b1;
             }
-            __syncwarp();
-
-#pragma unroll 1
-            for (int tb = 0; tb < 16 / TB; tb++) {
-                const int tbase = half * 16 + tb * TB;           // first token (lane index) of this block of TB
-                const int tok0 = pass * 32 + tbase;
-                if (tok0 >= ntok) break;                         // warp-uniform: blocks of TB never straddle ntok
-                // the TB neighbours' feature rows and the centre's global row: in flight during the second layer
-                float feat[TB][CPL], gl[CPL];
 #pragma unroll
-                for (int q = 0; q < TB; q++) {
-                    const int kq = __shfl_sync(0xffffffffu, k, tbase + q);
-                    vldg<CPL>(feat[q], features_t + (size_t)kq * C + CPL * lane);
+            for (int ks = 0; ks < 2; ks++) {
+                const float *r0 = srppe + (16 * mt + g) * 12 + 8 * ks + t4, *r1 = r0 + 8 * 12;
+                unsigned ah[4], al[4];
+                split_tf32(r0[0], ah[0], al[0]);                                   // (row g,     k = t)
+                split_tf32(r1[0], ah[1], al[1]);                                   // (row g + 8, k = t)
+                split_tf32(ks == 0 ? r0[4] : 0.f, ah[2], al[2]);                   // (row g,     k = t + 4): inputs 12..15 are padding
+                split_tf32(ks == 0 ? r1[4] : 0.f, ah[3], al[3]);
+                unsigned bh[H / 8][2], bl[H / 8][2];
+#pragma unroll
+                for (int nt = 0; nt < H / 8; nt++) {
+                    const float *w = sW1 + (nt * 8 + g) * kW1Pitch + 8 * ks + t4;
+                    split_tf32(w[0], bh[nt][0], bl[nt][0]);
+                    split_tf32(w[4], bh[nt][1], bl[nt][1]);
                 }
-                vldg<CPL>(gl, gbase + (size_t)(tok0 / ns) * C + CPL * lane);
-                float acc[TB][CPL];
-                {
-                    float b[CPL];
-                    vload<CPL>(b, sb2 + CPL * lane);
 #pragma unroll
-                    for (int q = 0; q < TB; q++)
+                for (int ps = 0; ps < 3; ps++)                                       // small terms first, tiles interleaved
 #pragma unroll
-                        for (int e = 0; e < CPL; e++) acc[q][e] = b[e];
-                }
+                    for (int nt = 0; nt < H / 8; nt++)
+                        mma_tf32(h1[nt], ps == 1 ? al : ah, ps == 0 ? bl[nt][0] : bh[nt][0], ps == 0 ? bl[nt][1] : bh[nt][1]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < H / 8; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) h1[nt][e] = fmaxf(h1[nt][e], 0.f);
+            // ---- layer 2: pos = relu(W2 . h1 + b2), H -> C, bf16 m16n8k16 split products; A = packed C fragments of layer 1
+            float pos[C / 8][4];
+#pragma unroll
+            for (int nt = 0; nt < C / 8; nt++) {
+                const float b0 = sb2[nt * 8 + 2 * t4], b1 = sb2[nt * 8 + 2 * t4 + 1];
+                pos[nt][0] = b0, pos[nt][1] = b1, pos[nt][2] = b0, pos[nt][3] = b1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < H / 16; ks++) {
+                unsigned ah[4], al[4];
+                split_bf16x2(h1[2 * ks][0], h1[2 * ks][1], ah[0], al[0]);
+                split_bf16x2(h1[2 * ks][2], h1[2 * ks][3], ah[1], al[1]);
+                split_bf16x2(h1[2 * ks + 1][0], h1[2 * ks + 1][1], ah[2], al[2]);
+                split_bf16x2(h1[2 * ks + 1][2], h1[2 * ks + 1][3], ah[3], al[3]);
+#pragma unroll
+                for (int ps = 0; ps < 3; ps++)
+#pragma unroll
+                    for (int nt = 0; nt < C / 8; nt++) {
+                        const int w = (nt * 8 + g) * P2 + ks * 8 + t4;
+                        const unsigned *sw = ps == 0 ? sW2l : sW2h;
+                        mma_bf16(pos[nt], ps == 1 ? al : ah, sw[w], sw[w + 4]);
+                    }
+            }
+            // ---- rows: the position block goes through this warp's smem tile, 8 tokens (rows g, then rows g + 8) at a time, into
+            // the row layout: lane = CPL consecutive channels of each of the four parts [pos | feat * scale | feat | glob], so a
+            // row is four coalesced 16-byte accesses per lane; LayerNorm (two-pass, like torch.nn.LayerNorm) = two warp sums.
+            float gl[CPL];
+            vldg<CPL>(gl, gbase + (size_t)(tok0 / ns) * C + CPL * lane);
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                __syncwarp();  // the previous half has been read
+#pragma unroll
+                for (int nt = 0; nt < C / 8; nt++)
+                    *reinterpret_cast<float2 *>(spos + g * PP + 8 * nt + 2 * t4) =
+                        make_float2(fmaxf(pos[nt][2 * r], 0.f), fmaxf(pos[nt][2 * r + 1], 0.f));
+                __syncwarp();
 #pragma unroll 1
-                for (int in0 = 0; in0 < H; in0 += 4) {
-                    float wv[4][CPL];
+                for (int qb = 0; qb < 8; qb += 4) {            // 4 token rows at a time: their shuffle sums interleave
+                    float pv[4][CPL], fv[4][CPL], scq[4], mean[4], rstd[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) vload<CPL>(wv[i], sW2t + (in0 + i) * C + CPL * lane);
+                    for (int q = 0; q < 4; q++) {
+                        const int tl = 16 * mt + 8 * r + qb + q;                    // the row's token, as a lane of stage A
+                        const int kq = __shfl_sync(0xffffffffu, k, tl);
+                        scq[q] = __shfl_sync(0xffffffffu, sc, tl);
+                        vldg<CPL>(fv[q], features_t + (size_t)kq * C + CPL * lane);
+                        vload<CPL>(pv[q], spos + (qb + q) * PP + CPL * lane);
+                    }
 #pragma unroll
-                    for (int q = 0; q < TB; q++) {
-                        const float4 hv = *reinterpret_cast<const float4 *>(sh + (tb * TB + q) * H + in0);
+                    for (int q = 0; q < 4; q++) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int e = 0; e < CPL; e++) sum += pv[q][e] + fv[q][e] * scq[q] + fv[q][e] + gl[e];
+                        mean[q] = sum;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) mean[q] += __shfl_xor_sync(0xffffffffu, mean[q], off);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        mean[q] *= 1.0f / E;
+                        float sq = 0.f;
 #pragma unroll
                         for (int e = 0; e < CPL; e++) {
-                            acc[q][e] = fmaf(wv[0][e], hv.x, acc[q][e]);
-                            acc[q][e] = fmaf(wv[1][e], hv.y, acc[q][e]);
-                            acc[q][e] = fmaf(wv[2][e], hv.z, acc[q][e]);
-                            acc[q][e] = fmaf(wv[3][e], hv.w, acc[q][e]);
+                            const float a = pv[q][e] - mean[q], b = fv[q][e] * scq[q] - mean[q], c = fv[q][e] - mean[q],
+                                        d = gl[e] - mean[q];
+                            sq += (a * a + b * b) + (c * c + d * d);
+                        }
+                        rstd[q] = sq;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) rstd[q] += __shfl_xor_sync(0xffffffffu, rstd[q], off);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) rstd[q] = rsqrtf(rstd[q] * (1.0f / E) + p.eps);
+                    float *rows = obase + (size_t)(tok0 + 8 * r + qb) * E + CPL * lane;
+#pragma unroll
+                    for (int part = 0; part < 4; part++) {
+                        float gm[CPL], bt[CPL];
+                        vload<CPL>(gm, sgamma + part * C + CPL * lane);
+                        vload<CPL>(bt, sbeta + part * C + CPL * lane);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            float y[CPL];
+#pragma unroll
+                            for (int e = 0; e < CPL; e++) {
+                                const float v = part == 0 ? pv[q][e] : part == 1 ? fv[q][e] * scq[q] : part == 2 ? fv[q][e] : gl[e];
+                                y[e] = (v - mean[q]) * rstd[q] * gm[e] + bt[e];
+                            }
+                            vstore<CPL>(rows + (size_t)q * E + part * C, y);
                         }
                     }
                 }
-                // rows: [pos | feat * scale | feat | glob], LayerNorm (two-pass, like torch.nn.LayerNorm), store
-                float scq[TB], mean[TB], rstd[TB];
-#pragma unroll
-                for (int q = 0; q < TB; q++) {
-                    scq[q] = __shfl_sync(0xffffffffu, sc, tbase + q);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int e = 0; e < CPL; e++) {
-                        acc[q][e] = fmaxf(acc[q][e], 0.f);
-                        sum += acc[q][e] + feat[q][e] * scq[q] + feat[q][e] + gl[e];
-                    }
-                    mean[q] = sum;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                    for (int q = 0; q < TB; q++) mean[q] += __shfl_xor_sync(0xffffffffu, mean[q], off);
-#pragma unroll
-                for (int q = 0; q < TB; q++) {
-                    mean[q] *= 1.0f / E;
-                    float sq = 0.f;
-#pragma unroll
-                    for (int e = 0; e < CPL; e++) {
-                        const float a = acc[q][e] - mean[q], b = feat[q][e] * scq[q] - mean[q],
-                                    c = feat[q][e] - mean[q], d = gl[e] - mean[q];
-                        sq += (a * a + b * b) + (c * c + d * d);
-                    }
-                    rstd[q] = sq;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                    for (int q = 0; q < TB; q++) rstd[q] += __shfl_xor_sync(0xffffffffu, rstd[q], off);
-#pragma unroll
-                for (int q = 0; q < TB; q++) rstd[q] = rsqrtf(rstd[q] * (1.0f / E) + p.eps);
-                float *rows = obase + (size_t)tok0 * E + CPL * lane;
-#pragma unroll
-                for (int part = 0; part < 4; part++) {
-                    float g[CPL], bt[CPL];
-                    vload<CPL>(g, sgamma + part * C + CPL * lane);
-                    vload<CPL>(bt, sbeta + part * C + CPL * lane);
-#pragma unroll
-                    for (int q = 0; q < TB; q++) {
-                        float y[CPL];
-#pragma unroll
-                        for (int e = 0; e < CPL; e++) {
-                            const float v = part == 0 ? acc[q][e] : part == 1 ? feat[q][e] * scq[q]
-                                          : part == 2 ? feat[q][e] : gl[e];
-                            y[e] = (v - mean[q]) * rstd[q] * g[e] + bt[e];
-                        }
-                        vstore<CPL>(rows + (size_t)q * E + part * C, y);
-                    }
-                }
             }
-            __syncwarp();  // sh is rewritten by the next half / pass
         }
+        __syncwarp();  // srppe is rewritten by the next pass
     }
 }
 
 template <int C>
 size_t enc_smem(int nsample) {
-    constexpr int H = C / 2, E = 4 * C, CTR = 32;
-    const size_t phase2 = sizeof(float) * (kWarps * 32 * 12 + kWarps * 16 * H);
-    const size_t phase1 = sizeof(int) * ((size_t)kWarps * nsample * 33 + kWarps * 32);
-    return sizeof(float4) * kWarps * pdab::kSplitTile +
-           sizeof(float) * ((size_t)H * C + C + 2 * E + kDensFloats + H + 12 * H + 3 * CTR) +
-           sizeof(int) * (size_t)nsample * (CTR + 1) + (phase1 > phase2 ? phase1 : phase2);
+    constexpr int H = C / 2, E = 4 * C, CTR = 32, PP = C + 8;
+    const size_t phase1 = sizeof(float4) * kWarps * pdab::kSplitTile + sizeof(int) * ((size_t)kWarps * nsample * 33 + kWarps * 32);
+    const size_t phase2 = sizeof(float) * (kWarps * 32 * 12 + kWarps * 8 * PP);
+    return sizeof(float) * ((size_t)2 * C * p16(H) + H * kW1Pitch + H + C + 2 * E + kDensFloats + 3 * CTR) +
+           sizeof(int) * (((size_t)nsample * (CTR + 1) + 3) & ~(size_t)3) + (phase1 > phase2 ? phase1 : phase2);
 }
 
 template <int C>
