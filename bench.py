@@ -34,7 +34,7 @@ UNIT = "scenes/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pdab", choices=["pdab", "reference"])
     ap.add_argument("--config", default="kitti", choices=["kitti", "once"])
