@@ -10,7 +10,7 @@
 // Exactness: the fp32 test is sqdist3(centre, point) < radius*radius with the
 // reference's compiled op order (common.cuh); hit order = point index order;
 // unfilled slots repeat the first hit; an empty ball leaves its row untouched.
-#include "common.cuh"
+#include "ball_scan.cuh"
 
 namespace {
 
@@ -106,7 +106,60 @@ int launch(int b, int n, int m, float r_hi, float r_lo, int nsample, const float
     return 0;
 }
 
+// Same result from the scene's hashed cell list (ball_scan.cuh): a centre tests the points of the 27 cells around it and keeps
+// the nsample smallest indices among the hits = the first nsample hits of the in-order scan.  Thread per centre; the lists
+// live in shared memory (slot-major, one column per thread) and leave through one coalesced sweep.
+constexpr int kGridStride = kThreads + 1;
+__global__ void __launch_bounds__(kThreads)
+ball_query_grid_kernel(int n, int m, float r2, float inv_edge, int nsample, const float *__restrict__ new_xyz,
+                       const unsigned char *__restrict__ ws, int *__restrict__ idx) {
+    extern __shared__ int slist[];                       // nsample x kGridStride
+    const int scene = blockIdx.y, t = threadIdx.x;
+    const int j0 = blockIdx.x * kThreads, j = j0 + t;
+    const unsigned char *wscene = ws + (size_t)scene * pdab::grid_scene_bytes(n);
+    const int *start = reinterpret_cast<const int *>(wscene);
+    const float4 *sorted = reinterpret_cast<const float4 *>(wscene + pdab::grid_scene_ints() * sizeof(int));
+    int cnt = 0;
+    if (j < m) {
+        const float *c = new_xyz + ((size_t)scene * m + j) * 3;
+        cnt = pdab::grid_scan_column<kGridStride>(start, sorted, inv_edge, c[0], c[1], c[2], r2, nsample, slist, t);
+        const int first = cnt > 0 ? slist[t] : 0;
+        for (int l = cnt; l < nsample; l++) slist[l * kGridStride + t] = first;
+    }
+    // an empty ball leaves its row untouched (the caller pre-zeroes idx, PB/pointnet2_utils.py:246): mark it with -1
+    if (j < m && cnt == 0) slist[t] = -1;
+    __syncthreads();
+    const int nctr = min(kThreads, m - j0);
+    int *out = idx + ((size_t)scene * m + j0) * nsample;
+    for (int e = t; e < nctr * nsample; e += kThreads) {
+        const int jl = e / nsample, l = e - jl * nsample;
+        if (slist[jl] >= 0) out[e] = slist[l * kGridStride + jl];
+    }
+}
+
 }  // namespace
+
+extern "C" int pdab_ball_query_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                                    int *idx, void *workspace, pdab_stream_t stream) {
+    if (b < 0 || n < 0 || m < 0 || nsample < 1 || !new_xyz || !xyz || !idx || !workspace || !(radius > 0.f)) return PDAB_EINVAL;
+    if (b == 0 || m == 0 || n == 0) return 0;
+    if (b > 65535 || nsample > 256) return PDAB_EUNSUPPORTED;
+    cudaStream_t s = pdab::to_stream(stream);
+    const float inv_edge = 1.0f / (pdab::kCellSlack * radius);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    pdab::grid_build_kernel<<<b, pdab::kBuildThreads, 0, s>>>(n, inv_edge, xyz, ws);
+    PDAB_LAUNCH_CHECK();
+    const size_t smem = sizeof(int) * (size_t)nsample * kGridStride;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PDAB_CUDA(cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(pdab::div_up(m, kThreads), b);
+    ball_query_grid_kernel<<<grid, kThreads, smem, s>>>(n, m, radius * radius, inv_edge, nsample, new_xyz, ws, idx);
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int pdab_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
                                int *idx, pdab_stream_t stream) {

@@ -432,70 +432,6 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     }
 }
 
-// One CTA per scene builds the scene's cell list: bucket counts (global atomics), exclusive scan, scatter of
-// (x, y, z, index) into bucket order.  ~20 us for 16 x 16384 points; the order inside a bucket is arbitrary (the query
-// keeps hits sorted by index).
-constexpr int kBuildThreads = 1024;
-__global__ void __launch_bounds__(kBuildThreads)
-grid_build_kernel(int n, float inv_edge, const float *__restrict__ xyz_all, unsigned char *__restrict__ ws) {
-    constexpr int NB = pdab::kGridBuckets, PER = NB / kBuildThreads;
-    __shared__ int warp_sums[kBuildThreads / 32];
-    const int scene = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const float *xyz = xyz_all + (size_t)scene * n * 3;
-    unsigned char *wscene = ws + (size_t)scene * pdab::grid_scene_bytes(n);
-    int *start = reinterpret_cast<int *>(wscene);
-    int *cursor = start + NB + 4;
-    float4 *sorted = reinterpret_cast<float4 *>(wscene + pdab::grid_scene_ints() * sizeof(int));
-    for (int i = t; i < NB; i += kBuildThreads) cursor[i] = 0;
-    __syncthreads();
-    for (int k = t; k < n; k += kBuildThreads) {
-        const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
-        atomicAdd(cursor + pdab::grid_hash(pdab::grid_cell(x, inv_edge), pdab::grid_cell(y, inv_edge),
-                                           pdab::grid_cell(z, inv_edge)), 1);
-    }
-    __syncthreads();
-    // exclusive scan of the NB counts: PER consecutive buckets per thread, then warp / CTA prefix
-    int local[PER], sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; i++) {
-        local[i] = cursor[t * PER + i];
-        sum += local[i];
-    }
-    int incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_sums[lane];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, w, off);
-            if (lane >= off) w += v;
-        }
-        warp_sums[lane] = w;  // inclusive
-    }
-    __syncthreads();
-    int run = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0);
-#pragma unroll
-    for (int i = 0; i < PER; i++) {
-        start[t * PER + i] = run;
-        cursor[t * PER + i] = run;
-        run += local[i];
-    }
-    if (t == kBuildThreads - 1) start[NB] = run;
-    __syncthreads();
-    for (int k = t; k < n; k += kBuildThreads) {
-        const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
-        const int pos = atomicAdd(cursor + pdab::grid_hash(pdab::grid_cell(x, inv_edge), pdab::grid_cell(y, inv_edge),
-                                                           pdab::grid_cell(z, inv_edge)), 1);
-        sorted[pos] = make_float4(x, y, z, __int_as_float(k));
-    }
-}
-
 template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3>
 int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns_b, const float *xyz,
                 const float *new_xyz, const float *features, const float *const *W, const float *const *B, float *out,
@@ -509,7 +445,7 @@ int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns
     if (workspace) {
         const float inv_edge = 1.0f / (pdab::kCellSlack * fmaxf(ra, rb));
         unsigned char *ws = static_cast<unsigned char *>(workspace);
-        grid_build_kernel<<<b, kBuildThreads, 0, stream>>>(n, inv_edge, xyz, ws);
+        pdab::grid_build_kernel<<<b, pdab::kBuildThreads, 0, stream>>>(n, inv_edge, xyz, ws);
         PDAB_LAUNCH_CHECK();
         auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, true>;
         PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -170,6 +170,30 @@ def test_ball_query_bit_exact_vs_reference_kernel(ops, ref_pointnet2, tag, B, N,
     assert torch.equal(got, want)
 
 
+def test_ball_query_cell_list_equals_scan(ops):
+    """pdab_ball_query_grid (hashed cell list, the nsample smallest indices among the hits of 27 cells) == pdab_ball_query (the
+    in-order scan with early exit), bit for bit: sparse and overflowing balls, duplicates, negative coordinates, a squeezed cloud
+    whose every point falls into a handful of cells, an empty ball, nsample up to 64."""
+    from pdanet_b200 import pointnet2_batch_cuda as shim
+    for seed, B, N, M, r, ns, shift, scale, kw in [
+            (1, 2, 16384, 4096, 0.2, 16, 0.0, 1.0, {}), (2, 2, 16384, 4096, 0.8, 32, -50.0, 1.0, dict(duplicate_frac=0.1)),
+            (3, 1, 16384, 1000, 4.8, 64, 0.0, 1.0, {}), (4, 2, 8192, 777, 0.8, 32, 3.0, 0.02, {}),
+            (5, 1, 65536, 16384, 0.8, 32, 0.0, 1.0, {}), (6, 1, 5000, 300, 1.0, 5, 0.0, 1.0, dict(quantize=1.0))]:
+        xyz = (scene_xyz(seed, B, N, **kw) * scale + shift).contiguous()
+        new_xyz = xyz[:, :M].clone()
+        new_xyz[:, -1] = 1e4  # one empty ball per scene: its row stays zero
+        outs = []
+        for min_points in (None, 1):
+            saved = shim.CELL_LIST_MIN_POINTS
+            shim.CELL_LIST_MIN_POINTS = min_points
+            try:
+                outs.append(ops.ball_query(r, ns, dev(xyz), dev(new_xyz)).cpu())
+            finally:
+                shim.CELL_LIST_MIN_POINTS = saved
+        assert torch.equal(outs[0], outs[1]), (seed, N, M, r, ns)
+        assert (outs[1][:, -1] == 0).all()
+
+
 def test_ball_query_dilated_bit_exact(ops):
     xyz = scene_xyz(21, 2, 1200, quantize=0.5)
     new_xyz = xyz[:, :100].contiguous()
