@@ -81,8 +81,10 @@ int pdab_ball_query_dilated(int b, int n, int m, float max_radius, float min_rad
 
 /* pdab_ball_query through a hashed cell list: the call first buckets every scene's points by cell (edge = radius + 0.1 %), the
  * centres then test the 27 cells around them and keep the nsample smallest indices among the hits — the same idx, bit for bit,
- * at ~N / 30 of the distance tests when the balls are small against the cloud.  workspace: pdab_sa_grid_workspace_bytes(b, n)
- * bytes on the device, 16-byte aligned.  nsample <= 256. */
+ * at ~N / 30 of the distance tests when the balls are small against the cloud.  Centres whose 27 cells hold many more points
+ * than slots (dense balls) are handed to the in-order scan kernel, which stops at nsample hits.
+ * workspace: pdab_ball_query_grid_workspace_bytes(b, n, m) bytes on the device, 16-byte aligned.  nsample <= 256. */
+size_t pdab_ball_query_grid_workspace_bytes(int b, int n, int m);
 int pdab_ball_query_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx,
                          void *workspace, pdab_stream_t stream);
 

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "pdab_gather_points": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pdab_gather_points_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pdab_ball_query": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "pdab_ball_query_grid_workspace_bytes": (_sz, [_i, _i, _i]),
     "pdab_ball_query_grid": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_ball_query_dilated": (_i, [_i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "pdab_group_points": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -108,7 +109,7 @@ def check(fn: str, code: int) -> int:
 
 
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches` count)
-KERNELS_PER_CALL = {"pdab_nms_device": 2, "pdab_nms_batched": 2, "pdab_nms_host": 2, "pdab_sa_fused_pair": 2, "pdab_ball_query_grid": 2}
+KERNELS_PER_CALL = {"pdab_nms_device": 2, "pdab_nms_batched": 2, "pdab_nms_host": 2, "pdab_sa_fused_pair": 2, "pdab_ball_query_grid": 3}
 
 launch_counts: dict = {}      # entry point -> number of kernels launched through `call`
 _timing = None                # when enabled: entry point -> list of (start_event, end_event)

@@ -585,25 +585,6 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
             const long long m0 = row0_of(item);
             const int k = ka * BKE + chunk * 4 * V;       // first fp32 column this thread converts
             if (ALOAD == A_ROWS) {
-                // The group has ONE k-atom of loads in flight (registers are the landing zone); under a write-heavy epilogue
-                // stream their DRAM latency is what the producers wait for (ncu: ~50 % of their samples on the loads'
-                // scoreboard).  Pull the k-atom this group converts kPrefetch turns from now towards L2: one prefetch per
-                // 128-byte line (the lanes holding the first 16-byte chunk of a line).
-                constexpr int kPrefetch = 2;
-                const long long pstep = step + (long long)kPrefetch * G;
-                if (pstep < total && (chunk & (NPASS == 2 ? 3 : 7)) == 0) {
-                    const long long pli = pstep / steps_per_item;
-                    const int pka = (int)(pstep - pli * steps_per_item) % KA;
-                    const long long pm0 = row0_of(item0 + pli * item_step);
-                    const int pk = pka * BKE + chunk * 4 * V;
-                    if (pk < p.K) {
-#pragma unroll
-                        for (int i = 0; i < R; i++) {
-                            const long long t = pm0 + r0 + RSTEP * i;
-                            if (t < p.T) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.A + t * p.lda + pk));
-                        }
-                    }
-                }
 #pragma unroll
                 for (int i = 0; i < R; i++) {
                     const long long t = m0 + r0 + RSTEP * i;

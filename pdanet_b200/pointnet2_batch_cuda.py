@@ -87,8 +87,9 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, gr
 
 
 # Clouds of at least this many points are searched through a hashed cell list (pdab_ball_query_grid: 27 cells per centre instead of
-# the whole cloud, the same idx bit for bit); smaller ones are scanned in order with early exit.  None disables the cell list.
-CELL_LIST_MIN_POINTS = 4096
+# the whole cloud, dense balls fall back to the in-order scan inside the kernel; the same idx bit for bit); smaller ones are scanned
+# in order with early exit (building the list costs more than it saves).  None disables the cell list.
+CELL_LIST_MIN_POINTS = 8192
 
 
 def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
@@ -98,7 +99,8 @@ def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx
     pi = _chk(idx_tensor, "idx", torch.int32, (b, m, nsample))
     with _same_device(new_xyz_tensor, xyz_tensor, idx_tensor):
         if CELL_LIST_MIN_POINTS is not None and n >= CELL_LIST_MIN_POINTS and nsample <= 256 and radius > 0 and b > 0 and m > 0:
-            ws = torch.empty(_lib.lib().pdab_sa_grid_workspace_bytes(b, n), dtype=torch.uint8, device=xyz_tensor.device)
+            ws = torch.empty(_lib.lib().pdab_ball_query_grid_workspace_bytes(b, n, m), dtype=torch.uint8,
+                             device=xyz_tensor.device)
             _lib.call("pdab_ball_query_grid", b, n, m, float(radius), nsample, pn, px, pi, ws.data_ptr(), _stream(xyz_tensor))
         else:
             _lib.call("pdab_ball_query", b, n, m, float(radius), nsample, pn, px, pi, _stream(xyz_tensor))
