@@ -30,8 +30,9 @@ class PackedLinear:
             raise RuntimeError("PackedLinear needs CUDA weights (pdanet_b200 has no CPU path)")
         w = weight.detach().float().contiguous()
         self.nout, self.k = int(w.shape[0]), int(w.shape[1])
-        if npass == 2 and self.k % 8:
+        if npass == 2 and self.k % 8 and not (xyz_last == 3 and (self.k - 3) % 8 == 0):
             npass = 3   # split-bf16 packs 8 inputs per 16-byte chunk; odd widths (K = 12 position MLP) use 3xTF32
+                        # (the SA gather prologue builds its [features (C % 8 == 0), xyz (3)] rows itself: C + 3 is fine there)
         self.npass = npass
         self.bn = bn if bn is not None else (256 if self.nout > 128 else 128)
         self.xyz_last = xyz_last
