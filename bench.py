@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight per GPU (ScenePipeline slots)")
+    ap.add_argument("--depth", type=int, default=8, help="batches in flight per GPU (ScenePipeline slots)")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs the persistent tensor-core grid leaves free for the other batches' FPS kernels (default: batch)")
     ap.add_argument("--kernels", type=int, default=12, help="how many per-kernel rows to keep in the JSON line")
