@@ -77,9 +77,9 @@ class ScenePipeline:
 
     Why: distance-FPS is a serial latency chain that occupies one SM per scene for milliseconds (hard
     part 1); run back to back it idles ~130 SMs.  With several batches in flight the FPS of batch k+1 runs on its 16 SMs
-    while the tensor-core / gather kernels of batch k use the others, and the tails of small kernels overlap (measured:
-    depth 2 -> 1200, depth 4 -> 1280 scenes/s); the graph removes the host launch cost of the
-    ~350 kernels of a step.  The persistent tensor-core kernels are told to leave one SM per in-flight scene free
+    while the tensor-core / gather kernels of batch k use the others, and the tails of small kernels overlap (measured at the
+    end of round 1: depth 2 -> 1380, 4 -> 1450, 6 -> 1650, 8 -> 1690, 12 -> 1710 scenes/s); the graph removes the host launch
+    cost of the ~270 kernels of a step.  The persistent tensor-core kernels are told to leave one SM per in-flight scene free
     (`pdab_set_persistent_ctas`) so their grid never queues behind an FPS CTA.
 
     Results are identical to `SceneRunner.infer` (same kernels, same order per batch); tests check it.
