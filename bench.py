@@ -47,9 +47,10 @@ def parse():
                     help="SMs the persistent tensor-core grid leaves free for the other batches' FPS kernels (default: batch)")
     ap.add_argument("--kernels", type=int, default=12, help="how many per-kernel rows to keep in the JSON line")
     ap.add_argument("--no-graphs", action="store_true", help="do not capture the forward in CUDA graphs")
-    ap.add_argument("--tc-passes", type=int, default=None, choices=[1, 2, 3],
-                    help="tensor-core product mode of our GEMM kernels: 3 = 3xTF32 (fp32-level), 2 = split-bf16 (2^-16), "
-                         "1 = TF32; default = the modules' default")
+    ap.add_argument("--tc-passes", type=int, default=None, choices=[1, 2, 3, 4],
+                    help="tensor-core product mode of our GEMM kernels: 4 = fp16 single pass, fp16 activations between kernels, "
+                         "(hi, lo) fp16 residual streams; 3 = 3xTF32 (fp32-level); 2 = split-bf16 (2^-16); 1 = TF32; "
+                         "default = the modules' default")
     ap.add_argument("--matmul", default="ieee", choices=["ieee", "tf32"],
                     help="fp32 matmul mode of the unchanged PyTorch layers (PDA transformer); our kernels are fp32 either way")
     return ap.parse_args()
@@ -187,12 +188,34 @@ def algorithmic_bytes(key: str, batch: int):
         out_cols = nout // 3 if epi == 5 else nout             # attention epilogue: only ctx (rows, E) is written
         resid = rows * nout * 4 if epi in (2, 3) else 0
         return rows * k * 4 + out_rows * out_cols * 4 + resid + nout * k * 4 * (2 if npass == 3 else 1)
+    if name == "pdab_tc_linear_h":     # fp16 single pass; key ints: rows, k, nout, bn, epilogue, lda (pointers are filtered out)
+        rows, k, nout, bn, epi = a[:5]
+        # A read once as fp16 (an fp32 A, converted in the kernel, is counted at 2 B too: the smaller, algorithmic figure);
+        # residual = (hi, lo) fp16 planes = 4 B; outputs: pooled fp32, LayerNorm (hi, lo) planes 4 B, everything else fp16
+        out_rows = rows if epi not in (3, 4) else rows // 16
+        out_cols = nout // 3 if epi == 5 else nout
+        out_b = 4 if epi in (2, 3, 4) else 2
+        resid = rows * nout * 4 if epi in (2, 3) else 0
+        return rows * k * 2 + out_rows * out_cols * out_b + resid + nout * k * 2
     if name == "pdab_tc_sa_gather_linear":
         b, c, n, m, ns, nout = a[:6]
         return b * (4 * c * n + 12 * n + 12 * m + 4 * m * ns) + b * m * ns * nout * 4
+    if name == "pdab_tc_sa_gather_linear_h":
+        b, c, n, m, ns, nout = a[:6]
+        return b * (4 * c * n + 12 * n + 12 * m + 4 * m * ns) + b * m * ns * nout * 2
+    if name in ("pdab_pda_encode_ln", "pdab_pda_encode_ln_h"):
+        b, c, n, m = a[:4]
+        ns = a[4] if len(a) > 4 else 16     # (radius is a float and not in the key; nsample is)
+        return b * (12 * n + 4 * c * n + 12 * m + 4 * c * m + 16 * c * m * ns)   # output (tokens, 4c) at 4 B dominates
+    if name == "pdab_sa_fused_pair":
+        b, c, n, m = a[:4]
+        return b * (12 * n + 4 * c * n + 12 * m + 4 * 96 * m)   # both scales: 32 + 64 output channels per centre
     if name == "pdab_group_attention":
         groups, ns, heads, hd = a[:4]
         return groups * ns * heads * hd * 4 * 4          # q, k, v read + ctx written
+    if name == "pdab_group_attention_h":
+        groups, ns, heads, hd = a[:4]
+        return groups * ns * heads * hd * 4 * 2          # the same in fp16
     if name == "pdab_nms_batched":
         s, stride = a[:2]
         return s * (28 * stride + 8 * stride * ((stride + 63) // 64) + 8 * stride)
@@ -201,7 +224,7 @@ def algorithmic_bytes(key: str, batch: int):
 
 # tensor-pipe work per algorithmic flop, in bf16-MMA flops: split-bf16 ("bf16x3") issues 3 bf16 MMAs per product, 3xTF32
 # issues 3 TF32 MMAs (a TF32 MMA occupies the pipe like 2 bf16 MMAs), plain TF32 one
-MMA_COST = {2: 3.0, 3: 6.0, 1: 2.0}
+MMA_COST = {2: 3.0, 3: 6.0, 1: 2.0, 4: 1.0}
 
 
 def algorithmic_flops(key: str):
@@ -212,10 +235,23 @@ def algorithmic_flops(key: str):
         rows, k, nout, npass = a[:4]
         f = 2.0 * rows * k * nout
         return f, f * MMA_COST[npass]
+    if name == "pdab_tc_linear_h":
+        rows, k, nout = a[:3]
+        f = 2.0 * rows * k * nout
+        return f, f * MMA_COST[4]
     if name == "pdab_tc_sa_gather_linear":
         b, c, n, m, ns, nout, npass = a[:7]
         f = 2.0 * b * m * ns * (c + 3) * nout
         return f, f * MMA_COST[npass]
+    if name == "pdab_tc_sa_gather_linear_h":
+        b, c, n, m, ns, nout = a[:6]
+        f = 2.0 * b * m * ns * (c + 3) * nout
+        return f, f * MMA_COST[4]
+    if name == "pdab_sa_fused_pair":       # L0: (4 -> 16 -> 16 -> 32) x ns_a + (4 -> 32 -> 32 -> 64) x ns_b rows per centre
+        b, c, n, m = a[:4]
+        ns_a, ns_b = 16, 32
+        f = 2.0 * b * m * (ns_a * ((3 + c) * 16 + 16 * 16 + 16 * 32) + ns_b * ((3 + c) * 32 + 32 * 32 + 32 * 64))
+        return f, f * 3.0
     return None
 
 
@@ -353,7 +389,10 @@ def run_gpu_arm(args, cfg, n_points, batch):
                 "pdab_pda_group": "group", "pdab_pda_group_tokens": "group", "pdab_pda_encode_ln": "group_encode_pda",
                 "pdab_pda_assemble_ln_split": "group_encode_pda", "pdab_sa_fused": "fused_group_mlp_maxpool",
                 "pdab_sa_fused_pair": "fused_group_mlp_maxpool", "pdab_tc_sa_gather_linear": "fused_group_mlp_maxpool",
-                "pdab_tc_linear": "mlp_gemm", "pdab_group_attention": "attention", "pdab_nms_batched": "nms"}
+                "pdab_tc_linear": "mlp_gemm", "pdab_group_attention": "attention", "pdab_nms_batched": "nms",
+                "pdab_tc_linear_h": "mlp_gemm", "pdab_tc_sa_gather_linear_h": "fused_group_mlp_maxpool",
+                "pdab_pda_encode_ln_h": "group_encode_pda", "pdab_group_attention_h": "attention",
+                "pdab_ball_query_grid": "group"}
     stages = {}
     for name, g in groups.items():
         st = stage_of.get(name, "other")

@@ -14,7 +14,10 @@
  *   - fp32 data, int32 indices, int64 NMS keep lists;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *     the reference always launches on the legacy default stream;
- *   - nothing allocates, synchronises or touches global state unless stated;
+ *   - nothing allocates, synchronises or touches process-wide state unless stated.  The three launch-policy setters
+ *     (pdab_set_persistent_ctas, pdab_set_fps_max_cluster, pdab_set_cta_pairs) are THREAD-LOCAL: they change how the calling
+ *     host thread's later launches are shaped (never the results), two pipelines driven from two threads do not see each
+ *     other's settings, and a CUDA graph keeps the shape it was captured with;
  *   - return value: 0 on success, a positive cudaError_t value on a CUDA error,
  *     a negative PDAB_E* code on a bad argument.  The library never aborts the
  *     process (the reference calls exit(-1) on launch failure,
@@ -162,6 +165,11 @@ size_t pdab_pda_encode_param_floats(int c);
 int pdab_pda_encode_ln(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
                        const float *features_t, const float *glob, const float *params, float eps, float *out,
                        pdab_stream_t stream);
+/* Same, written as a (hi, lo) pair of fp16 planes (b*m*nsample, 4c) each: row = hi + lo to ~2^-22 — hi is the TMA operand
+ * of pdab_tc_linear_h, hi + lo the residual stream. */
+int pdab_pda_encode_ln_h(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                         const float *features_t, const float *glob, const float *params, float eps, void *out_hi,
+                         void *out_lo, pdab_stream_t stream);
 
 /* Row-wise kernels of the PDA block, each fused with the hi/lo split (hi = top 19 bits, exactly representable in
  * TF32; lo = value - hi) that feeds error-compensated 3xTF32 tensor-core projections.  `tokens` rows of e = 4c
@@ -192,6 +200,11 @@ int pdab_add_maxpool(long long groups, int nsample, int e, const float *a_hi, co
  * m16n8k16 (hi / lo bf16 pairs, ~2^-17 per product, the class of the split-bf16 GEMMs; half the instructions). */
 int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, int npass, const float *qkv, float *ctx,
                          pdab_stream_t stream);
+
+/* fp16 form (the fp16 single-pass mode of pdab_tc_linear_h): qkv (groups*nsample, 3E) and ctx (groups*nsample, E) are fp16;
+ * both contractions are fp16 m16n8k16 MMAs with fp32 accumulation, the softmax is fp32.  replaces: the same lines. */
+int pdab_group_attention_h(long long groups, int nsample, int heads, int head_dim, const void *qkv, void *ctx,
+                           pdab_stream_t stream);
 
 /* Fused plain set-abstraction scale: ball query -> group (xyz centred) -> shared MLP
  * (1x1 conv with eval-mode BatchNorm folded in, ReLU) x nlayers -> max over nsample.
@@ -253,25 +266,47 @@ int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn, int epilo
                    const float *w_packed, const float *bias, const float *residual, int ldr, const float *gamma,
                    const float *beta, float eps, int nsample, float *out, int ldo, pdab_stream_t stream);
 
-/* Largest thread-block cluster (CTAs per scene) the n > 16384 FPS path may use beyond the minimum that holds the scene
+/* Launch policy of the CALLING THREAD (thread-local; results never change, only how launches are shaped).
+ * Largest thread-block cluster (CTAs per scene) the n > 16384 FPS path may use beyond the minimum that holds the scene
  * (default 16: shortest chain).  A caller that pipelines batches lowers it so one batch's FPS chain occupies few SMs and runs
- * beside the other batches' kernels; results do not change.  Process-wide; 1 <= n <= 16. */
+ * beside the other batches' kernels.  1 <= n <= 16. */
 int pdab_set_fps_max_cluster(int n);
 
-/* Grid size of the persistent tensor-core kernels (default 148 = one CTA per SM).  A caller that pipelines batches on
- * several streams lowers it (e.g. 148 - scenes per batch) so the persistent grid never queues behind the one-CTA-per-
- * scene FPS kernels of another batch.  Process-wide; 1 <= n <= 148. */
+/* Grid size of the persistent tensor-core kernels launched by the calling thread: 0 (default) = one CTA per SM of the
+ * current device (cudaDevAttrMultiProcessorCount).  A caller that pipelines batches on several streams lowers it (e.g.
+ * SMs - scenes per batch) so the persistent grid never queues behind the one-CTA-per-scene FPS kernels of another batch. */
 int pdab_set_persistent_ctas(int n);
 
-/* 1 (default): the tensor-core kernels run as cta_group::2 CTA pairs (thread-block clusters of 2, M = 256) when the problem
- * is large enough; 0: single CTAs only.  Same results either way (the pairing is a schedule, not arithmetic). */
+/* 1 (default): the calling thread's tensor-core kernels run as cta_group::2 CTA pairs (thread-block clusters of 2, M = 256)
+ * when the problem is large enough; 0: single CTAs only.  Same results either way (a schedule, not arithmetic). */
 int pdab_set_cta_pairs(int on);
+
+/* fp16 single-pass form of pdab_tc_linear (tcgen05.mma kind::f16, fp16 x fp16 products, fp32 accumulation in TMEM; 11-bit
+ * significands = the TF32 precision class at a third of the MMAs of the split modes), with 16-bit activations BETWEEN
+ * kernels:
+ *   a        a_fp16 = 1: fp16 (rows, lda) row-major, 16-byte aligned, lda % 8 == 0 — loaded by the TMA engine
+ *            (cp.async.bulk.tensor through a SWIZZLE_128B tensor map: no producer warps, no register round trip);
+ *            a_fp16 = 0: fp32 (rows, lda), converted to fp16 by the kernel's producer warps.
+ *   w_packed pdab_tc_pack_weights(npass = 4): one fp16 plane.
+ *   residual res_lo == NULL: fp32 (rows, ldr) in res_hi; otherwise a (hi, lo) pair of fp16 planes, residual = hi + lo
+ *            (22 significand bits: the residual stream of the transformer keeps fp32-level precision — it, not the
+ *            products, sets the output error of the block).
+ *   out      out_fmt 0: fp32 (.., ldo); 1: fp16; 2 (ADD_LN only): (hi, lo) fp16 planes in out / out_lo — the next
+ *            GEMM's TMA operand is the hi plane, the next residual is hi + lo.  *_MAXPOOL outputs are fp32.
+ *   nsample  additionally 64 for PDAB_EPI_RELU_MAXPOOL (out is zeroed first: a memset node on `stream`).
+ *   k % 8 == 0.  Everything else as pdab_tc_linear.
+ * replaces: the same reference lines as pdab_tc_linear. */
+int pdab_tc_linear_h(long long rows, int k, int nout, int bn, int epilogue, const void *a, int lda, int a_fp16,
+                     const float *w_packed, const float *bias, const void *res_hi, const void *res_lo, int ldr,
+                     const float *gamma, const float *beta, float eps, int nsample, void *out, void *out_lo, int ldo,
+                     int out_fmt, pdab_stream_t stream);
 
 /* Number of floats pdab_tc_pack_weights writes for a (nout, k) weight matrix. */
 size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn);
 /* Packs W (nout, k) row-major (device) into the shared-memory image the tensor-core kernels stream:
  * [column chunk of bn][k-atom of 32][hi | lo][bn rows x 128 B, K-major, 128-byte swizzle], zero padded.
- * npass = 3 writes the (hi, lo) TF32 split, npass = 1 the round-to-nearest TF32 value.  If xyz_last > 0 the first
+ * npass = 3 writes the (hi, lo) TF32 split, npass = 1 the round-to-nearest TF32 value, npass = 2 the (hi, lo) bf16 split
+ * (k-atoms of 64), npass = 4 one fp16 plane (k-atoms of 64; pdab_tc_linear_h).  If xyz_last > 0 the first
  * xyz_last input columns of W are moved behind the others (the gather prologue of pdab_tc_sa_gather_linear feeds
  * [features, centred xyz] while the reference's Conv2d expects [xyz, features], PB/pointnet2_utils.py:692-699). */
 int pdab_tc_pack_weights(int nout, int k, int npass, int bn, int xyz_last, const float *w, float *packed,
@@ -287,6 +322,12 @@ int pdab_tc_pack_weights(int nout, int k, int npass, int bn, int xyz_last, const
 int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
                              const float *features_t, const float *xyz, const float *new_xyz, const float *w_packed,
                              const float *bias, float *out, int ldo, pdab_stream_t stream);
+
+/* fp16 single-pass form of pdab_tc_sa_gather_linear (w_packed: npass = 4); out fp32 or, out_fp16 != 0, fp16 (the TMA
+ * operand of the next pdab_tc_linear_h layer).  replaces: the same reference lines. */
+int pdab_tc_sa_gather_linear_h(int b, int c, int n, int m, int nsample, int nout, const int *idx,
+                               const float *features_t, const float *xyz, const float *new_xyz, const float *w_packed,
+                               const float *bias, void *out, int ldo, int out_fp16, pdab_stream_t stream);
 
 /* ---- iou3d_nms_cuda -------------------------------------------------------- */
 

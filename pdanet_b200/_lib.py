@@ -44,10 +44,15 @@ _SIGNATURES = {
     "pdab_relu_split": (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
     "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_group_attention": (_i, [C.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdab_group_attention_h": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_fused_pair": (_i, [_i, _i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_grid_workspace_bytes": (_sz, [_i, _i]),
     "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
+    "pdab_tc_linear_h": (_i, [C.c_longlong, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i,
+                               _i, _vp]),
+    "pdab_tc_sa_gather_linear_h": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "pdab_pda_encode_ln_h": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "pdab_set_persistent_ctas": (_i, [_i]),
     "pdab_set_fps_max_cluster": (_i, [_i]),
     "pdab_set_cta_pairs": (_i, [_i]),

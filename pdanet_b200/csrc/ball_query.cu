@@ -190,11 +190,8 @@ extern "C" int pdab_ball_query_grid(int b, int n, int m, float radius, int nsamp
     pdab::grid_build_kernel<<<b, pdab::kBuildThreads, 0, s>>>(n, inv_edge, xyz, ws);
     PDAB_LAUNCH_CHECK();
     const size_t smem = sizeof(int) * (size_t)nsample * kGridStride;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PDAB_CUDA(cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int dense_above = 2 * nsample + 32;
     dim3 grid(pdab::div_up(m, kThreads), b);
     ball_query_grid_kernel<<<grid, kThreads, smem, s>>>(n, m, radius * radius, inv_edge, nsample, dense_above, new_xyz, ws, todo,

@@ -33,7 +33,7 @@ constexpr int kMaxCluster = 16;
 // Largest cluster (CTAs per scene) the N > 16384 path may grow to.  Default 16: as many SMs per scene as fit, shortest chain.
 // A caller that pipelines batches lowers it (pdab_set_fps_max_cluster) so that the FPS chain of one batch occupies few SMs
 // and runs beside the other batches' kernels instead of taking the whole GPU.
-int g_max_cluster = kMaxCluster;
+thread_local int g_max_cluster = kMaxCluster;   // launch policy of the calling thread (pdab_set_fps_max_cluster)
 
 struct __align__(16) Candidate {
     unsigned long long key;  // [dist bits | ~tiekey]; 0 = no candidate
@@ -234,12 +234,9 @@ template <int P, bool MATRIX>
 int launch(int b, int n, int m, const float *src, float *temp, int *idx, int L, int CL, cudaStream_t stream) {
     const size_t smem = MATRIX ? 0 : (size_t)3 * P * kThreads * sizeof(float);
     auto kern = fps_kernel<P, MATRIX>;
-    static bool configured = false;  // benign race: the attribute calls are idempotent
-    if (!configured) {
-        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        configured = true;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(b * CL);
     cfg.blockDim = dim3(kThreads);

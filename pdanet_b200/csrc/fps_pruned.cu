@@ -23,7 +23,6 @@
 // The argmax key [dist bits | ~tiekey(k)] is the one fps.cu uses, on ORIGINAL point indices, so
 // the reference's tie rule (argmin (bitrev_L(k mod BS), k) over maxima) is preserved under the
 // permutation.  Preconditions: finite coordinates, temp >= 0 (the caller fills 1e10).
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -465,25 +464,13 @@ int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int
     if (CL < 1 || CL > kMaxCluster || n < 1) return PDAB_EUNSUPPORTED;
     const int per_cta = (n + CL - 1) / CL;
     if (per_cta > 16384) return PDAB_EUNSUPPORTED;
-    static const int variant = getenv("PDAB_FPS_VARIANT") ? atoi(getenv("PDAB_FPS_VARIANT")) : 0;  // tuning aid
+    // 16 warps, 64-point buckets; buckets per warp grow with the slice (the other warp / bucket shapes were measured slower,
+    // profiles/r01_microbench.txt)
     const int sz = per_cta <= 2048 ? 0 : per_cta <= 4096 ? 1 : per_cta <= 8192 ? 2 : 3;
-#define PDAB_FPS_CASE(V, W, B0, B1, B2, B3, P)                                        \
-    if (variant == V) {                                                                \
-        if (sz == 0) return launch<W, B0, P>(b, n, m, xyz, temp, idx, L, CL, stream);      \
-        if (sz == 1) return launch<W, B1, P>(b, n, m, xyz, temp, idx, L, CL, stream);      \
-        if (sz == 2) return launch<W, B2, P>(b, n, m, xyz, temp, idx, L, CL, stream);      \
-        return launch<W, B3, P>(b, n, m, xyz, temp, idx, L, CL, stream);                   \
-    }
-    PDAB_FPS_CASE(1, 32, 2, 4, 8, 16, 1)   // 32 warps, 32-point buckets
-    PDAB_FPS_CASE(2, 16, 2, 4, 8, 16, 2)   // 16 warps, 64-point buckets
-    PDAB_FPS_CASE(3, 8, 2, 4, 8, 16, 4)    // 8 warps, 128-point buckets
-    PDAB_FPS_CASE(4, 8, 1, 2, 4, 8, 8)     // 8 warps, 256-point buckets
-    PDAB_FPS_CASE(6, 16, 1, 1, 2, 4, 8)    // 16 warps, 256-point buckets
-    PDAB_FPS_CASE(7, 32, 1, 1, 2, 4, 4)    // 32 warps, 128-point buckets
-    PDAB_FPS_CASE(5, 16, 1, 2, 4, 8, 4)    // 16 warps, 128-point buckets
-    PDAB_FPS_CASE(0, 16, 2, 4, 8, 16, 2)   // default
-#undef PDAB_FPS_CASE
-    return PDAB_EUNSUPPORTED;
+    if (sz == 0) return launch<16, 2, 2>(b, n, m, xyz, temp, idx, L, CL, stream);
+    if (sz == 1) return launch<16, 4, 2>(b, n, m, xyz, temp, idx, L, CL, stream);
+    if (sz == 2) return launch<16, 8, 2>(b, n, m, xyz, temp, idx, L, CL, stream);
+    return launch<16, 16, 2>(b, n, m, xyz, temp, idx, L, CL, stream);
 }
 
 }  // namespace pdab

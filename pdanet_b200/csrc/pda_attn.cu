@@ -256,11 +256,8 @@ template <int NS, int HD, bool BF>
 int launch(long long groups, int heads, const float *qkv, float *ctx, cudaStream_t s) {
     using SM = AttnSmem<NS, HD, BF>;
     auto kern = group_attention_kernel<NS, HD, BF>;
-    static bool configured = false;
-    if (!configured) {
-        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
-        configured = true;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
     const long long blocks = groups * heads;
     if (blocks > 2147483647LL) return PDAB_EUNSUPPORTED;
     kern<<<(unsigned)blocks, kThreads, SM::BYTES, s>>>(groups, heads, qkv, ctx);
@@ -268,7 +265,163 @@ int launch(long long groups, int heads, const float *qkv, float *ctx, cudaStream
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// fp16 form (the fp16 single-pass GEMM mode, tc_gemm.cu NPASS = 4): qkv and ctx are fp16 matrices — half the bytes of a
+// kernel that is HBM-bound — and both contractions run as ONE fp16 m16n8k16 MMA per k-step (fp32 accumulation, fp32
+// softmax).  Fragments come straight out of shared memory as packed half pairs: A / B of Q K^T by 4-byte loads (row pitch
+// HD + 8 halves: bank = 4 g + t), B of P V by ldmatrix.trans (V is stored [key][channel]; its transpose is the col-major
+// operand).  A warp owns one 16-row m-tile and a slice of the output channels; its scores and probabilities never leave
+// registers (the C fragments of Q K^T are the A fragments of P V).
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_half, float hi_half) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+    return r;
+}
+
+template <int NS, int HD>
+__global__ void __launch_bounds__(kThreads) group_attention_h_kernel(long long groups, int heads,
+                                                                     const unsigned short *__restrict__ qkv,
+                                                                     unsigned short *__restrict__ ctx) {
+    constexpr int P = HD + 8;               // row pitch in halves (272 B / 144 B: 16-byte aligned, conflict-free fragments)
+    constexpr int MT = NS / 16;             // m-tiles
+    constexpr int NW = 4 / MT;              // warps sharing an m-tile, each owning HD / NW output channels
+    constexpr int O_NT = HD / 8 / NW;       // output n-tiles per warp
+    constexpr int S_NT = NS / 8;            // score n-tiles (all keys) per warp
+    __shared__ __align__(16) unsigned short sQ[NS * P], sK[NS * P], sV[NS * P];
+
+    const long long gh = blockIdx.x;
+    const long long grp = gh / heads;
+    const int h = (int)(gh - grp * heads);
+    const int E = heads * HD;
+    const unsigned short *base = qkv + grp * NS * 3LL * E + h * HD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    constexpr int C8 = HD / 8;              // 16-byte chunks per row
+#pragma unroll 4
+    for (int i = tid; i < 3 * NS * C8; i += kThreads) {
+        const int part = i / (NS * C8);
+        const int rem = i - part * (NS * C8);
+        const int r = rem / C8, c8 = rem - r * C8;
+        const unsigned short *src = base + (long long)r * 3 * E + part * E + c8 * 8;
+        unsigned short *dst = (part == 0 ? sQ : part == 1 ? sK : sV) + r * P + c8 * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int mt = warp % MT, nw = warp / MT;
+    const int m0 = mt * 16;
+    constexpr float scaling = HD == 64 ? 0.125f : 0.08838834764831845f;
+
+    // ---- S = Q K^T for this warp's 16 rows, all NS keys (the NW warps of an m-tile repeat it: 16 x NS x HD, cheap)
+    float sc[S_NT][4];
+#pragma unroll
+    for (int n = 0; n < S_NT; n++) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+#pragma unroll 4
+    for (int k0 = 0; k0 < HD; k0 += 16) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t *>(sQ + (m0 + g) * P + k0 + 2 * t);
+        a[1] = *reinterpret_cast<const uint32_t *>(sQ + (m0 + g + 8) * P + k0 + 2 * t);
+        a[2] = *reinterpret_cast<const uint32_t *>(sQ + (m0 + g) * P + k0 + 8 + 2 * t);
+        a[3] = *reinterpret_cast<const uint32_t *>(sQ + (m0 + g + 8) * P + k0 + 8 + 2 * t);
+#pragma unroll
+        for (int n = 0; n < S_NT; n++) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(sK + (8 * n + g) * P + k0 + 2 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(sK + (8 * n + g) * P + k0 + 8 + 2 * t);
+            mma_f16(sc[n], a, b0, b1);
+        }
+    }
+    // ---- softmax over the keys of rows g (values [.][0..1]) and g + 8 ([.][2..3]); a row lives in one quad of lanes
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int n = 0; n < S_NT; n++) {
+            sc[n][2 * r] *= scaling;
+            sc[n][2 * r + 1] *= scaling;
+            mx = fmaxf(mx, fmaxf(sc[n][2 * r], sc[n][2 * r + 1]));
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int n = 0; n < S_NT; n++) {
+            sc[n][2 * r] = expf(sc[n][2 * r] - mx);
+            sc[n][2 * r + 1] = expf(sc[n][2 * r + 1] - mx);
+            sum += sc[n][2 * r] + sc[n][2 * r + 1];
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int n = 0; n < S_NT; n++) {
+            sc[n][2 * r] *= inv;
+            sc[n][2 * r + 1] *= inv;
+        }
+    }
+    // ---- O = P V for this warp's channel slice: keys 16 s .. 16 s + 15 per k-step
+    float o[O_NT][4];
+#pragma unroll
+    for (int n = 0; n < O_NT; n++) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int s16 = 0; s16 < NS / 16; s16++) {
+        uint32_t a[4];
+        a[0] = pack_f16x2(sc[2 * s16][0], sc[2 * s16][1]);
+        a[1] = pack_f16x2(sc[2 * s16][2], sc[2 * s16][3]);
+        a[2] = pack_f16x2(sc[2 * s16 + 1][0], sc[2 * s16 + 1][1]);
+        a[3] = pack_f16x2(sc[2 * s16 + 1][2], sc[2 * s16 + 1][3]);
+#pragma unroll
+        for (int n = 0; n < O_NT; n++) {
+            const int n0 = (nw * O_NT + n) * 8;
+            // ldmatrix.x2.trans: lanes 0-15 address the 16 key rows of the (16 keys x 8 channels) block
+            const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sV + (16 * s16 + (lane & 15)) * P + n0);
+            uint32_t b0, b1;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+            mma_f16(o[n], a, b0, b1);
+        }
+    }
+    unsigned short *orow0 = ctx + (grp * NS + m0 + g) * (long long)E + h * HD;
+    unsigned short *orow1 = orow0 + 8LL * E;
+#pragma unroll
+    for (int n = 0; n < O_NT; n++) {
+        const int n0 = (nw * O_NT + n) * 8;
+        *reinterpret_cast<uint32_t *>(orow0 + n0 + 2 * t) = pack_f16x2(o[n][0], o[n][1]);
+        *reinterpret_cast<uint32_t *>(orow1 + n0 + 2 * t) = pack_f16x2(o[n][2], o[n][3]);
+    }
+}
+
+template <int NS, int HD>
+int launch_h(long long groups, int heads, const void *qkv, void *ctx, cudaStream_t s) {
+    const long long blocks = groups * heads;
+    if (blocks > 2147483647LL) return PDAB_EUNSUPPORTED;
+    group_attention_h_kernel<NS, HD><<<(unsigned)blocks, kThreads, 0, s>>>(
+        groups, heads, reinterpret_cast<const unsigned short *>(qkv), reinterpret_cast<unsigned short *>(ctx));
+    PDAB_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace
+
+extern "C" int pdab_group_attention_h(long long groups, int nsample, int heads, int head_dim, const void *qkv, void *ctx,
+                                      pdab_stream_t stream) {
+    if (groups < 0 || heads < 1 || !qkv || !ctx) return PDAB_EINVAL;
+    if (groups == 0) return 0;
+    cudaStream_t s = pdab::to_stream(stream);
+    if (nsample == 16 && head_dim == 64) return launch_h<16, 64>(groups, heads, qkv, ctx, s);
+    if (nsample == 32 && head_dim == 64) return launch_h<32, 64>(groups, heads, qkv, ctx, s);
+    if (nsample == 16 && head_dim == 128) return launch_h<16, 128>(groups, heads, qkv, ctx, s);
+    if (nsample == 32 && head_dim == 128) return launch_h<32, 128>(groups, heads, qkv, ctx, s);
+    return PDAB_EUNSUPPORTED;
+}
 
 extern "C" int pdab_group_attention(long long groups, int nsample, int heads, int head_dim, int npass, const float *qkv,
                                     float *ctx, pdab_stream_t stream) {

@@ -25,6 +25,8 @@
 //                             bytes of a row): LayerNorm statistics are two shuffles inside the quad, the row is written as
 //                             full 32-byte sectors.
 // The encoding itself (density, direction, DensityNet, LayerNorm) stays on CUDA cores (north_star); all accumulation in fp32.
+#include <cuda_fp16.h>
+
 #include "ball_scan.cuh"
 
 namespace {
@@ -69,6 +71,24 @@ __device__ __forceinline__ void vstore(float *p, const float (&d)[CPL]) {
     if constexpr (CPL == 4) *reinterpret_cast<float4 *>(p) = make_float4(d[0], d[1], d[2], d[3]);
     else *reinterpret_cast<float2 *>(p) = make_float2(d[0], d[1]);
 }
+// d -> fp16 hi plane and the fp16 remainders (lo plane): d = hi + lo to ~2^-22 relative
+template <int CPL>
+__device__ __forceinline__ void vstore_split16(__half *hi, __half *lo, const float (&d)[CPL]) {
+    __half2 h[CPL / 2], l[CPL / 2];
+#pragma unroll
+    for (int i = 0; i < CPL / 2; i++) {
+        h[i] = __floats2half2_rn(d[2 * i], d[2 * i + 1]);
+        const float2 b = __half22float2(h[i]);
+        l[i] = __floats2half2_rn(d[2 * i] - b.x, d[2 * i + 1] - b.y);
+    }
+    if constexpr (CPL == 4) {
+        *reinterpret_cast<uint2 *>(hi) = make_uint2(*reinterpret_cast<unsigned *>(&h[0]), *reinterpret_cast<unsigned *>(&h[1]));
+        *reinterpret_cast<uint2 *>(lo) = make_uint2(*reinterpret_cast<unsigned *>(&l[0]), *reinterpret_cast<unsigned *>(&l[1]));
+    } else {
+        *reinterpret_cast<__half2 *>(hi) = h[0];
+        *reinterpret_cast<__half2 *>(lo) = l[0];
+    }
+}
 
 __host__ __device__ constexpr int p16(int K) { return K / 2 + 4; }   // packed-pair row pitch (words): 4 * odd -> conflict-free
 constexpr int kW1Pitch = 20;                                         // layer-1 weights: 12 inputs padded to 16, + 4
@@ -98,6 +118,9 @@ struct EncParams {
     float radius, r2, two_r2, dens_norm, eps;
     const float *xyz, *new_xyz, *features_t, *glob, *params;
     float *out;
+    // fp16 (hi, lo) plane output (the fp16 single-pass transformer path): out_hi feeds the in_proj GEMM through TMA, hi + lo
+    // is the fp32-level residual stream; out == nullptr then
+    __half *out_hi, *out_lo;
 };
 
 // params (floats): W1 [H][12] | b1 [H] | W2t [H][C] | b2 [C] | dens (kDensFloats) | gamma [4C] | beta [4C],  H = C / 2
@@ -175,7 +198,8 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
     const int nctr = min(CTR, p.m - j0);
     const int ntok = nctr * ns;
     const int npass = (ntok + 31) >> 5;
-    float *obase = p.out + ((size_t)scene * p.m + j0) * ns * E;
+    const size_t obase_off = ((size_t)scene * p.m + j0) * ns * E;
+    float *obase = p.out + obase_off;
     const float *gbase = p.glob + ((size_t)scene * p.m + j0) * C;
     float *srppe = srppe_all + warp * 32 * 12;
     float *spos = spos_all + warp * 8 * PP;
@@ -328,7 +352,8 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
                         for (int q = 0; q < 4; q++) rstd[q] += __shfl_xor_sync(0xffffffffu, rstd[q], off);
 #pragma unroll
                     for (int q = 0; q < 4; q++) rstd[q] = rsqrtf(rstd[q] * (1.0f / E) + p.eps);
-                    float *rows = obase + (size_t)(tok0 + 8 * r + qb) * E + CPL * lane;
+                    const size_t row_off = (size_t)(tok0 + 8 * r + qb) * E + CPL * lane;
+                    float *rows = obase + row_off;
 #pragma unroll
                     for (int part = 0; part < 4; part++) {
                         float gm[CPL], bt[CPL];
@@ -342,7 +367,11 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
                                 const float v = part == 0 ? pv[q][e] : part == 1 ? fv[q][e] * scq[q] : part == 2 ? fv[q][e] : gl[e];
                                 y[e] = (v - mean[q]) * rstd[q] * gm[e] + bt[e];
                             }
-                            vstore<CPL>(rows + (size_t)q * E + part * C, y);
+                            if (p.out_hi)
+                                vstore_split16<CPL>(p.out_hi + obase_off + row_off + (size_t)q * E + part * C,
+                                                    p.out_lo + obase_off + row_off + (size_t)q * E + part * C, y);
+                            else
+                                vstore<CPL>(rows + (size_t)q * E + part * C, y);
                         }
                     }
                 }
@@ -365,11 +394,8 @@ template <int C>
 int enc_launch(int b, const EncParams &p, cudaStream_t s) {
     const size_t smem = enc_smem<C>(p.nsample);
     auto kern = pda_encode_ln_kernel<C>;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(pdab::div_up(p.m, 32), b);
     kern<<<grid, kThreads, smem, s>>>(p);
     PDAB_LAUNCH_CHECK();
@@ -384,10 +410,11 @@ extern "C" size_t pdab_pda_encode_param_floats(int c) {
     return h * 12 + h + h * c + c + kDensFloats + 8 * (size_t)c;
 }
 
-extern "C" int pdab_pda_encode_ln(int b, int c, int n, int m, float radius, int nsample, const float *xyz,
-                                  const float *new_xyz, const float *features_t, const float *glob,
-                                  const float *params, float eps, float *out, pdab_stream_t stream) {
-    if (b < 0 || n < 1 || m < 0 || nsample < 1 || !xyz || !new_xyz || !features_t || !glob || !params || !out)
+static int encode_ln(int b, int c, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                     const float *features_t, const float *glob, const float *params, float eps, float *out,
+                     void *out_hi, void *out_lo, pdab_stream_t stream) {
+    if (b < 0 || n < 1 || m < 0 || nsample < 1 || !xyz || !new_xyz || !features_t || !glob || !params ||
+        (!out && !(out_hi && out_lo)))
         return PDAB_EINVAL;
     if (b == 0 || m == 0) return 0;
     if ((c != 64 && c != 128) || (nsample != 16 && nsample != 32) || b > 65535) return PDAB_EUNSUPPORTED;
@@ -407,6 +434,22 @@ extern "C" int pdab_pda_encode_ln(int b, int c, int n, int m, float radius, int 
     p.glob = glob;
     p.params = params;
     p.out = out;
+    p.out_hi = reinterpret_cast<__half *>(out_hi);
+    p.out_lo = reinterpret_cast<__half *>(out_lo);
     cudaStream_t s = pdab::to_stream(stream);
     return c == 64 ? enc_launch<64>(b, p, s) : enc_launch<128>(b, p, s);
+}
+
+extern "C" int pdab_pda_encode_ln(int b, int c, int n, int m, float radius, int nsample, const float *xyz,
+                                  const float *new_xyz, const float *features_t, const float *glob,
+                                  const float *params, float eps, float *out, pdab_stream_t stream) {
+    if (!out) return PDAB_EINVAL;
+    return encode_ln(b, c, n, m, radius, nsample, xyz, new_xyz, features_t, glob, params, eps, out, nullptr, nullptr, stream);
+}
+
+extern "C" int pdab_pda_encode_ln_h(int b, int c, int n, int m, float radius, int nsample, const float *xyz,
+                                    const float *new_xyz, const float *features_t, const float *glob,
+                                    const float *params, float eps, void *out_hi, void *out_lo, pdab_stream_t stream) {
+    if (!out_hi || !out_lo) return PDAB_EINVAL;
+    return encode_ln(b, c, n, m, radius, nsample, xyz, new_xyz, features_t, glob, params, eps, nullptr, out_hi, out_lo, stream);
 }

@@ -218,11 +218,8 @@ extern "C" int pdab_pda_group(int b, int c, int n, int m, float radius, int nsam
     if (nsample > 128 || b > 65535) return PDAB_EUNSUPPORTED;
     const size_t smem = sizeof(float4) * (pdab::kScanTile + 8) + sizeof(float) * 3 * kThreads +
                         sizeof(int) * (size_t)nsample * kStride;
-    static int configured_smem = 0;
-    if ((int)smem > configured_smem) {
-        PDAB_CUDA(cudaFuncSetAttribute(pda_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_smem = (int)smem;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(pda_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // Python-double scalars are rounded to fp32 once, as torch does for tensor-scalar ops
     // (PB/pointnet2_utils.py:593).
     const float two_r2 = (float)(2.0 * (double)radius * (double)radius);

@@ -14,6 +14,16 @@
 //   NPASS = 3 : error-compensated "3xTF32": x = x_hi + x_lo, w = w_hi + w_lo with the hi parts exactly representable
 //               in TF32 (top 19 bits), acc += x_hi w_lo + x_lo w_hi + x_hi w_hi.  The dropped x_lo w_lo term is
 //               O(2^-22) relative: fp32-level results (what nn.Linear computes in the reference) at 3 MMAs / k-step.
+//   NPASS = 2 : the same compensation with bf16 halves (kind::f16, K = 16 per MMA): ~1e-5 relative, 3 MMAs / k-step.
+//   NPASS = 4 : fp16 x fp16 single pass (kind::f16, fp32 accumulation): 11-bit significands, the TF32 precision class at
+//               one MMA per k-step.  In this mode activations travel BETWEEN kernels as fp16 (half the HBM bytes) and the
+//               residual streams of the transformer as (hi, lo) fp16 plane pairs (fp32-level, 22 bits): measured, the
+//               residual stream is what sets the block's output error (5e-4 with rounded residuals, 8e-5 with exact
+//               ones), the single-pass products contribute 4e-5 (tools/precision_study.py).
+//               A operand: fp32 rows converted by the producer warps (A_ROWS / A_GATHER), or — A_TMA — an fp16 row-major
+//               matrix loaded by the TMA engine: cp.async.bulk.tensor.2d (UTMALDG) boxes of 128 rows x 64 columns through a
+//               SWIZZLE_128B tensor map land as the canonical K-major tile the UMMA descriptor expects; no producer warps,
+//               no register round trip, no shared-memory stores from the LSU.
 //
 // Mapping to the SM.  One CTA per SM, persistent over (row tile, column group) work items.  Large problems run as
 // CTA PAIRS (cta_group::2, thread-block clusters of 2): one tcgen05.mma covers M = 256 rows across the two SMs, each SM
@@ -32,7 +42,9 @@
 // row for the LayerNorm epilogue) so the epilogue of item i overlaps the main loop of item i+1.
 // Weights are packed once (host side, pdanet_b200/tc_pack.py) into the exact smem image of each (column chunk, k-atom)
 // tile — canonical K-major SWIZZLE_128B layout — so a stage's weights are ONE contiguous bulk copy.
-#include <cstdlib>
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -45,11 +57,14 @@ using u64 = uint64_t;
 constexpr int BM = 128;            // rows per tile (TMEM lanes)
 constexpr int BK = 32;             // fp32 / tf32 elements per k-atom (128 B swizzle row); bf16 mode: 64 elements
 constexpr int A_TILE_BYTES = BM * 128;     // 16 KB: 128 rows x one 128-byte swizzle row
-__host__ __device__ constexpr int bk_of(int npass) { return npass == 2 ? 64 : 32; }
+__host__ __device__ constexpr bool BK_IS_64(int npass) { return npass == 2 || npass == 4; }
+__host__ __device__ constexpr int bk_of(int npass) { return (npass == 2 || npass == 4) ? 64 : 32; }
+// operand planes per k-atom: the split modes stage (hi, lo), TF32 / fp16 single-pass one plane
+__host__ __device__ constexpr int parts_of(int npass) { return (npass == 2 || npass == 3) ? 2 : 1; }
 constexpr int kTmemCols = 512;
 constexpr int kStgPitch = 36;       // floats per row of an epilogue staging tile (32 + 4: 16-byte aligned, conflict-free)
 
-enum ALoad { A_ROWS = 0, A_GATHER = 1 };
+enum ALoad { A_ROWS = 0, A_GATHER = 1, A_TMA = 2 };
 enum Epi { E_STORE = 0, E_RELU = 1, E_ADD_LN = 2, E_ADD_MAXPOOL = 3, E_RELU_MAXPOOL = 4, E_ATTN = 5 };
 constexpr int kAttnVP = 68;         // floats per row of the attention epilogue's V staging tile (64 + 4: conflict-free B fragments)
 
@@ -80,7 +95,19 @@ struct GemmParams {
     const float *gamma, *beta;
     float eps;
     long long n_items;
-    long long store_rows;  // rows of the output actually written: T, or 0 with PDAB_TC_NOSTORE=1 (timing aid: main loop only)
+    // NPASS = 4 i/o formats.  out16: 0 = fp32 `out`; 1 = fp16 `out`; 2 = (hi, lo) fp16 planes `out` / `out_lo`
+    // (E_ADD_LN: the next residual stream).  res16: 0 = fp32 residual R; 1 = R / R_lo are fp16 (hi, lo) planes.
+    // Pooled outputs (E_*_MAXPOOL) are always fp32.
+    int out16, res16;
+    void *out_lo;
+    const void *R_lo;
+    int persistent_ctas;   // grid cap of this launch (<= SM count)
+    // A_TMA: fp16 (T, lda) row-major A, box = 64 columns x 128 rows, SWIZZLE_128B, out-of-range elements read as zero
+    alignas(64) CUtensorMap tmA;
+    // the residual's (hi, lo) fp16 planes, same box shape (res_tma != 0: the epilogue reads the residual from a smem ring)
+    alignas(64) CUtensorMap tmRh;
+    alignas(64) CUtensorMap tmRl;
+    int res_tma;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -148,6 +175,18 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+
+// TMA tensor load (UTMALDG): box (c0 = first column, c1 = first row) of a 2-D tensor map -> shared memory of this CTA,
+// completing `bytes` on this CTA's mbarrier.  The map lives in the kernel's parameter space (__grid_constant__).
+__device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap *map, int c0, int c1, u32 bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 // CG = 1: one SM; CG = 2: CTA pair (both CTAs' allocating warps execute the instruction, same smem slot offset)
@@ -311,6 +350,25 @@ __device__ __forceinline__ void bf16_split8(const float4 &a, const float4 &b, ui
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// 8 fp32 -> 8 fp16 (round to nearest even) packed in a uint4
+__device__ __forceinline__ u32 f16x2(float lo_half, float hi_half) {
+    u32 r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+    return r;
+}
+__device__ __forceinline__ uint4 f16_pack8(const float4 &a, const float4 &b) {
+    return make_uint4(f16x2(a.x, a.y), f16x2(a.z, a.w), f16x2(b.x, b.y), f16x2(b.z, b.w));
+}
+__device__ __forceinline__ float2 f16x2_to_float2(u32 h) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&h));
+}
+// (a, b) -> fp16 pair `hi` and the fp16 pair of the remainders `lo`: a = hi.x + lo.x to ~2^-22 relative
+__device__ __forceinline__ void f16_split2(float a, float b, u32 &hi, u32 &lo) {
+    hi = f16x2(a, b);
+    const float2 h = f16x2_to_float2(hi);
+    lo = f16x2(a - h.x, b - h.y);
+}
+
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_rna(float v) {
     u32 r;
@@ -328,6 +386,7 @@ __device__ __forceinline__ float tf32_rna(float v) {
 // setmaxnreg: the two warpgroups that hold the loader / MMA / A-producer warps grow to kProdRegs, the two epilogue
 // warpgroups shrink to kEpiRegs (128 * 2 * 152 + 128 * 2 * 104 = 65536).
 constexpr int kProdRegs = 152, kEpiRegs = 104;
+__host__ __device__ constexpr bool epi_has_res(int epi) { return epi == 2 || epi == 3; }   // E_ADD_LN, E_ADD_MAXPOOL
 template <int EPI, int CG>
 struct EpiWarps {
     // (tried for the residual + max-pool epilogues too: slower — they wait for residual tiles, not for issue slots, and
@@ -335,23 +394,47 @@ struct EpiWarps {
     static constexpr int value = (CG == 2 && EPI == 5) ? 8 : 4;
 };
 
-template <int NPASS, int BN, int CG, int EW = 4>
+// RES: the epilogue adds a residual (E_ADD_LN, E_ADD_MAXPOOL).  With the TMA-fed fp16 mode (A_TMA) the residual is staged
+// too: a ring of kResStages x {hi, lo} fp16 boxes of 128 rows x 64 columns (SWIZZLE_128B), filled by a dedicated warp while the
+// main loop of the same item still runs, so the epilogue reads it from shared memory at shared-memory latency.
+constexpr int kMaxSmem = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+constexpr int kResStages = 2;
+constexpr int kResStageBytes = 2 * A_TILE_BYTES;     // hi + lo box: 128 rows x 64 fp16 columns each
+constexpr int kBarBytes = 512;
+template <int NPASS, int BN, int CG, int EW = 4, int ALOAD = A_ROWS, bool RES = false>
 struct Cfg {
+    static constexpr int PARTS = parts_of(NPASS);
     static constexpr int W_TILE_BYTES = BN * 128 / CG;                     // one of {hi, lo}, per CTA
-    static constexpr int STAGE_BYTES = (NPASS >= 2 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
-    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + W_TILE_BYTES);
+    static constexpr bool RES_TMA = RES && ALOAD == A_TMA;
+    static constexpr int RES_BYTES = RES_TMA ? kResStages * kResStageBytes : 0;
+    // BN = 192 is the attention epilogue (one head of [Q | K | V], head_dim 64, per chunk): + a V staging tile per warp
+    static constexpr int ATTN_BYTES = BN == 192 ? 4 * 32 * kAttnVP * 4 : 0;
+    static constexpr int MISC_BYTES = 1024 /*align slack*/ + kBarBytes + 4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/;
+    // rings get 200 KB (A_TMA: minus the residual ring and the attention tile, which the producer-fed modes fit on top)
+    static constexpr int STAGES_RAW = ALOAD == A_TMA ? (200 * 1024 - ATTN_BYTES - RES_BYTES) / STAGE_BYTES
+                                                     : (200 * 1024) / STAGE_BYTES;
     // A-producer groups: group g owns k-atom steps g, g+G, ...  G must divide STAGES so that every smem stage belongs
     // to ONE group, which then sees every phase of that stage's `empty` barrier (a parity wait can only tell two
     // consecutive phases apart).
-    static constexpr int STAGES = CG == 2 ? (STAGES_RAW >= 6 ? 6 : 3) : (STAGES_RAW >= 4 ? 4 : 2);
+    // (A_TMA has no producer groups: any depth from 2 to 6 works)
+    static constexpr int STAGES = ALOAD == A_TMA ? (STAGES_RAW >= 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW))
+                                  : CG == 2      ? (STAGES_RAW >= 6 ? 6 : 3)
+                                                 : (STAGES_RAW >= 4 ? 4 : 2);
     static constexpr int GROUPS = CG == 2 ? 3 : STAGES;
-    static constexpr int PRODUCER_WARPS = CG == 2 ? 6 : 8;
+    static constexpr int PRODUCER_WARPS = ALOAD == A_TMA ? 0 : (CG == 2 ? 6 : 8);   // A_TMA: the TMA engine is the producer
     static constexpr int EPI_WARPS = EW;
-    static constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + EW);
-    // BN = 192 is the attention epilogue (one head of [Q | K | V], head_dim 64, per chunk): + a V staging tile per warp
-    static constexpr int ATTN_BYTES = BN == 192 ? 4 * 32 * kAttnVP * 4 : 0;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/ + ATTN_BYTES;
+    // warps before the epilogue warps: loader, MMA, producers; A_TMA: loader, MMA, residual loader, one idle warp (so that
+    // epilogue warp e sits in TMEM lane quadrant e % 4)
+    static constexpr int FIRST_EPI_WARP = ALOAD == A_TMA ? 4 : 2 + PRODUCER_WARPS;
+    static constexpr int THREADS = 32 * (FIRST_EPI_WARP + EW);
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = RING_BYTES + RES_BYTES;                 // residual ring right behind the main ring (1024-aligned)
+    static constexpr int PARAM_OFF = BAR_OFF + kBarBytes;
+    static constexpr int SMEM_BYTES = RING_BYTES + RES_BYTES + MISC_BYTES + ATTN_BYTES;
+    static_assert(SMEM_BYTES <= kMaxSmem, "shared memory budget");
+    static_assert((4 * STAGES + 4 + 2 * kResStages) * 8 + 8 <= kBarBytes, "barrier block");
+    static_assert(STAGE_BYTES % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
 };
 
 struct Pipe {
@@ -367,8 +450,10 @@ struct Pipe {
 };
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
-__global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::THREADS, 1) tc_gemm_kernel(const GemmParams p) {
-    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>;
+__global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, ALOAD, epi_has_res(EPI)>::THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ GemmParams p) {
+    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, ALOAD, epi_has_res(EPI)>;
+    static_assert(ALOAD != A_TMA || NPASS == 4, "the TMA-fed A operand is the fp16 single-pass mode");
     constexpr int EW = C::EPI_WARPS;
     constexpr int S = C::STAGES;
     constexpr int kThreads = C::THREADS, kProducerWarps = C::PRODUCER_WARPS;
@@ -388,7 +473,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
     extern __shared__ uint8_t smem_raw[];
     const u32 smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const u32 bar_base = smem_base + S * C::STAGE_BYTES;
+    const u32 bar_base = smem_base + C::BAR_OFF;
     // barriers (8 B each): full_w[S], full_a[S], empty[S], acc_full[2], acc_empty[2], peer_w[S]; then the TMEM base address.
     // CTA pair: full_a / acc_empty / peer_w of the LEADER also receive the peer's arrivals (remote mbarrier.arrive);
     // empty / acc_full are signalled in both CTAs by the leader's multicast tcgen05.commit.
@@ -398,12 +483,16 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
     auto acc_full = [&](int a) { return bar_base + 8u * (3 * S + a); };
     auto acc_empty = [&](int a) { return bar_base + 8u * (3 * S + 2 + a); };
     auto peer_w = [&](int s) { return bar_base + 8u * (3 * S + 4 + s); };
-    const u32 tmem_slot = bar_base + 8u * (4 * S + 4);
-    volatile u32 *tmem_slot_ptr = reinterpret_cast<volatile u32 *>(smem + S * C::STAGE_BYTES + 8 * (4 * S + 4));
+    auto r_full = [&](int s) { return bar_base + 8u * (4 * S + 4 + s); };               // residual ring (RES_TMA)
+    auto r_empty = [&](int s) { return bar_base + 8u * (4 * S + 4 + kResStages + s); };
+    const u32 tmem_slot = bar_base + 8u * (4 * S + 4 + 2 * kResStages);
+    volatile u32 *tmem_slot_ptr = reinterpret_cast<volatile u32 *>(smem + C::BAR_OFF + 8 * (4 * S + 4 + 2 * kResStages));
+    // the residual ring is used when the host built the residual tensor maps (fp16 plane pair, nout % 64 == 0)
+    const bool res_tma = C::RES_TMA && p.res_tma != 0;
 
     auto a_hi = [&](int s) { return smem_base + (u32)s * C::STAGE_BYTES; };
-    auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };                       // NPASS >= 2 only
-    auto w_hi = [&](int s) { return a_hi(s) + (NPASS >= 2 ? 2 : 1) * A_TILE_BYTES; };
+    auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };                       // split modes only
+    auto w_hi = [&](int s) { return a_hi(s) + C::PARTS * A_TILE_BYTES; };
     auto w_lo = [&](int s) { return w_hi(s) + C::W_TILE_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,7 +500,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(full_w(s), 1);
-            mbar_init(full_a(s), CG * (kProducerWarps / C::GROUPS));
+            mbar_init(full_a(s), ALOAD == A_TMA ? 1 : CG * (kProducerWarps / C::GROUPS));   // (unused with A_TMA)
             mbar_init(empty(s), 1);
             mbar_init(peer_w(s), 1);
         }
@@ -419,12 +508,16 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
             mbar_init(acc_full(a), 1);
             mbar_init(acc_empty(a), EW * CG);
         }
+        for (int r = 0; r < kResStages; r++) {
+            mbar_init(r_full(r), 1);
+            mbar_init(r_empty(r), EW);
+        }
         fence_barrier_init();
     }
     if (CG == 2) cluster_sync_all();  // both CTAs of the pair resident, barriers initialised before any remote arrive
     if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
     if (EPI == E_ADD_LN) {  // LayerNorm scale / shift -> smem once (Nout = NCH * BN <= 512 columns)
-        float *sg = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512;
+        float *sg = reinterpret_cast<float *>(smem + C::PARAM_OFF) + 4 * 512;
         for (int i = threadIdx.x; i < NCH * BN; i += kThreads) {
             sg[i] = __ldg(p.gamma + i);
             sg[512 + i] = __ldg(p.beta + i);
@@ -440,27 +533,31 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
     // EW = 8: warps 0-7 (loader, MMA, 6 producers) and warps 8-15 (epilogue) are two pairs of warpgroups; each side
     // re-sizes its registers INSIDE its own branch, so that the setmaxnreg dominates the code it governs (ptxas bounds
     // the registers of a region by the setmaxnreg that dominates it) and a warpgroup executes one and the same instruction.
-    if (warp < 2 + kProducerWarps) {
-    if constexpr (EW == 8) {
-        static_assert(EW != 8 || C::PRODUCER_WARPS == 6, "register re-division assumes 4 warpgroups");
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
-    }
+    // (A_TMA has no producer warps: 2 + EW warps, nothing to re-divide)
+    constexpr bool kSetMaxNReg = EW == 8 && C::PRODUCER_WARPS == 6;
+    static_assert(EW != 8 || C::PRODUCER_WARPS == 6 || C::PRODUCER_WARPS == 0, "register re-division assumes 4 warpgroups");
+    if (warp < C::FIRST_EPI_WARP) {
+    if constexpr (kSetMaxNReg) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProdRegs));
     if (warp == 0) {
         // ===================================================================== W loader
         if (lane == 0) {
             Pipe pipe;
-            constexpr int PARTS = NPASS >= 2 ? 2 : 1;
-            constexpr u32 BYTES = PARTS * C::W_TILE_BYTES;          // bytes this CTA receives per stage
+            constexpr int PARTS = C::PARTS;
+            // bytes this CTA receives per stage (A_TMA: + its own 128-row A tile, on the same barrier)
+            constexpr u32 BYTES = PARTS * C::W_TILE_BYTES + (ALOAD == A_TMA ? A_TILE_BYTES : 0);
             constexpr size_t TILE = (size_t)PARTS * BN * 128;        // packed bytes of one (chunk, k-atom) tile
+            if (ALOAD == A_TMA) tma_prefetch_desc(&p.tmA);
             constexpr u32 PIECE = C::W_TILE_BYTES < 8192 ? C::W_TILE_BYTES : (C::W_TILE_BYTES % 8192 ? 4096 : 8192);
             for (long long item = item0; item < n_items; item += item_step) {
                 const int n_group = (int)(item % p.n_groups);
+                const int arow0 = (int)row0_of(item);
                 for (int c = 0; c < NCH; c++) {
                     const int chunk = n_group * NCH + c;
                     const uint8_t *src = reinterpret_cast<const uint8_t *>(p.Wp) + (size_t)chunk * KA * TILE;
                     for (int ka = 0; ka < KA; ka++) {
                         mbar_wait(empty(pipe.stage), pipe.phase ^ 1);
                         mbar_arrive_expect_tx(full_w(pipe.stage), BYTES);
+                        if (ALOAD == A_TMA) tma_load_2d(a_hi(pipe.stage), &p.tmA, ka * 64, arow0, full_w(pipe.stage));
                         // several smaller bulk copies: more requests in flight per SM than one big copy.  CTA pair:
                         // this CTA takes rows [rank * BN/2, +BN/2) of the hi and of the lo image.
 #pragma unroll
@@ -493,8 +590,8 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
             Pipe pipe;
             int as = 0;
             u32 aphase = 0;
-            constexpr u32 idesc = umma_idesc<BN, NPASS == 2 ? 1 : 2, CG>();
-            constexpr int BKE = bk_of(NPASS), KSTEP = NPASS == 2 ? 16 : 8;   // elements per k-atom / per MMA
+            constexpr u32 idesc = umma_idesc<BN, NPASS == 2 ? 1 : (NPASS == 4 ? 0 : 2), CG>();   // bf16 / fp16 / tf32 operands
+            constexpr int BKE = bk_of(NPASS), KSTEP = BKE / 4;               // elements per k-atom / per MMA (32 bytes of K)
             for (long long item = item0; item < n_items; item += item_step) {
                 if (!CHUNKED) {
                     if (CG == 2) mbar_wait_cluster(acc_empty(as), aphase ^ 1);
@@ -508,11 +605,11 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     }
                     const u32 d = tmem_base + (u32)(as * ACC_COLS + c * BN);
                     for (int ka = 0; ka < KA; ka++) {
-                        mbar_wait(full_w(pipe.stage), pipe.phase);
+                        mbar_wait(full_w(pipe.stage), pipe.phase);   // (A_TMA: this CTA's A tile arrives on it too)
                         if (CG == 2) {
-                            mbar_wait_cluster(full_a(pipe.stage), pipe.phase);   // both CTAs' A tiles
-                            mbar_wait_cluster(peer_w(pipe.stage), pipe.phase);   // the peer's W half
-                        } else {
+                            if (ALOAD != A_TMA) mbar_wait_cluster(full_a(pipe.stage), pipe.phase);   // both CTAs' A tiles
+                            mbar_wait_cluster(peer_w(pipe.stage), pipe.phase);   // the peer's W half (A_TMA: and A tile)
+                        } else if (ALOAD != A_TMA) {
                             mbar_wait(full_a(pipe.stage), pipe.phase);
                         }
                         tc_fence_after();
@@ -534,6 +631,8 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                 umma_bf16<CG>(d, ah, wl, idesc, acc);
                                 umma_bf16<CG>(d, al, wh, idesc, 1u);
                                 umma_bf16<CG>(d, ah, wh, idesc, 1u);
+                            } else if (NPASS == 4) {
+                                umma_bf16<CG>(d, ah, wh, idesc, acc);    // kind::f16, fp16 operands (idesc)
                             } else {
                                 umma_tf32<CG>(d, ah, wh, idesc, acc);
                             }
@@ -552,6 +651,29 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                 }
             }
         }
+    } else if constexpr (ALOAD == A_TMA) {
+        // ===================================================================== residual loader (warp 2; warp 3 idles)
+        // Runs ahead of the epilogue by the depth of the ring: the first boxes of an item land while its MMAs are still
+        // being issued.  Consumption order = the epilogue's: 64-column blocks of the item, left to right.
+        if constexpr (C::RES_TMA) {
+            if (warp == 2 && lane == 0 && res_tma) {
+                tma_prefetch_desc(&p.tmRh);
+                tma_prefetch_desc(&p.tmRl);
+                Pipe rp;
+                for (long long item = item0; item < n_items; item += item_step) {
+                    const int rrow0 = (int)row0_of(item);
+                    const int col0 = (int)(item % p.n_groups) * NCH * BN;
+                    for (int cb = 0; cb < NCH * BN / 64; cb++) {
+                        mbar_wait(r_empty(rp.stage), rp.phase ^ 1);
+                        mbar_arrive_expect_tx(r_full(rp.stage), (u32)kResStageBytes);
+                        const u32 dst = smem_base + C::RING_BYTES + (u32)rp.stage * kResStageBytes;
+                        tma_load_2d(dst, &p.tmRh, col0 + 64 * cb, rrow0, r_full(rp.stage));
+                        tma_load_2d(dst + A_TILE_BYTES, &p.tmRl, col0 + 64 * cb, rrow0, r_full(rp.stage));
+                        rp.advance<kResStages>();
+                    }
+                }
+            }
+        }
     } else {
         // ===================================================================== A producers (G groups of 8/G warps)
         // Group g owns k-atom steps g, g+G, g+2G, ... of this CTA's flattened (item, chunk pass, k-atom) sequence and
@@ -564,7 +686,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
         constexpr int WPG = kProducerWarps / G;           // warps per group
         constexpr int RSTEP = 4 * WPG;                    // rows covered by one group-wide access
         constexpr int R = BM / RSTEP;                     // rows per thread
-        constexpr int V = NPASS == 2 ? 2 : 1;             // float4 loads per row: bf16 mode packs 8 fp32 -> one 16 B chunk
+        constexpr int V = BK_IS_64(NPASS) ? 2 : 1;        // float4 loads per row: 16-bit modes pack 8 fp32 -> one 16 B chunk
         constexpr int BKE = bk_of(NPASS);                 // elements per k-atom
         const int pw = warp - 2;
         const int g = pw / WPG, h = pw % WPG;
@@ -647,6 +769,8 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     bf16_split8(v[i][0], v[i][V - 1], hi, lo);
                     *reinterpret_cast<uint4 *>(ah + off) = hi;
                     *reinterpret_cast<uint4 *>(ah + A_TILE_BYTES + off) = lo;
+                } else if (NPASS == 4) {
+                    *reinterpret_cast<uint4 *>(ah + off) = f16_pack8(v[i][0], v[i][V - 1]);
                 } else {
                     const float4 x = v[i][0];
                     *reinterpret_cast<float4 *>(ah + off) =
@@ -662,7 +786,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
         }
     }
     } else {
-        if constexpr (EW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+        if constexpr (kSetMaxNReg) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
         // ===================================================================== epilogue (128 threads)
         // The accumulator is read with the 16x256b TMEM load shape, which hands out an MMA-C-fragment layout: for a
         // 32-row x 32-column block, lane (fr = lane / 4, fc = 2 * (lane % 4)) holds rows 16 h + 8 j + fr (h, j in {0,1})
@@ -672,12 +796,12 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
         // version used the 32x32b shape — thread = row — and staged every block through shared memory twice; it was
         // instruction- and latency-bound: profiles/r01_ncu_tc_gemm_*.)
         const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-        const int ew = warp - (2 + kProducerWarps);   // 0..EW-1 (EW = 8: ew & 3 == q, ew >> 2 = the warp's m-tile)
+        const int ew = warp - C::FIRST_EPI_WARP;      // 0..EW-1 (EW = 8: ew >> 2 = the warp's m-tile)
         const int fr = lane >> 2, fc = (lane & 3) * 2;
         // Per-column parameters live in shared memory: with ~200 KB of it carved out the L1 is a few KB and thrashed by
         // the A stream, so an __ldg of bias / gamma / beta inside the block loop was an L2 round trip on the critical path.
-        float *sbias = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + ew * (2048 / EW);
-        const float *sgamma = reinterpret_cast<const float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512;
+        float *sbias = reinterpret_cast<float *>(smem + C::PARAM_OFF) + ew * (2048 / EW);
+        const float *sgamma = reinterpret_cast<const float *>(smem + C::PARAM_OFF) + 4 * 512;
         const float *sbeta = sgamma + 512;
         int as = 0;
         u32 aphase = 0;
@@ -707,7 +831,11 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     }
             }
         };
-        // global rows [grow0, grow0+32) x columns [n0, n0+32) in the fragment layout; zeros outside the matrix
+        // global rows [grow0, grow0+32) x columns [n0, n0+32) in the fragment layout; zeros outside the matrix.
+        // res16 (NPASS = 4): the residual is a (hi, lo) pair of fp16 planes; a tile register then carries the two packed
+        // half2 words (.x = hi pair, .y = lo pair) and add_tile adds hi + lo — the same 8 bytes per element pair in flight.
+        const bool res16 = NPASS == 4 && p.res16 != 0;
+        const int out16 = NPASS == 4 ? p.out16 : 0;
         auto issue_tile = [&](float2 (&t)[2][8], const float *base, int ld, long long grow0, long long nrows, int n0) {
 #pragma unroll
             for (int h = 0; h < 2; h++)
@@ -718,8 +846,16 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     for (int k = 0; k < 4; k++) {
                         const int col = n0 + 8 * k + fc;
                         t[h][k * 2 + j] = make_float2(0.f, 0.f);
-                        if (r < nrows && col < p.Nout)
-                            t[h][k * 2 + j] = __ldg(reinterpret_cast<const float2 *>(base + r * ld + col));
+                        if (r < nrows && col < p.Nout) {
+                            if (res16) {
+                                const size_t o = (size_t)r * ld + col;
+                                t[h][k * 2 + j] = make_float2(
+                                    __uint_as_float(__ldg(reinterpret_cast<const u32 *>(reinterpret_cast<const __half *>(base) + o))),
+                                    __uint_as_float(__ldg(reinterpret_cast<const u32 *>(reinterpret_cast<const __half *>(p.R_lo) + o))));
+                            } else {
+                                t[h][k * 2 + j] = __ldg(reinterpret_cast<const float2 *>(base + r * ld + col));
+                            }
+                        }
                     }
                 }
         };
@@ -730,10 +866,16 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                 for (int j = 0; j < 2; j++)
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        v[h][k * 4 + j * 2] += t[h][k * 2 + j].x;
-                        v[h][k * 4 + j * 2 + 1] += t[h][k * 2 + j].y;
+                        float2 r = t[h][k * 2 + j];
+                        if (res16) {
+                            const float2 a = f16x2_to_float2(__float_as_uint(r.x)), b = f16x2_to_float2(__float_as_uint(r.y));
+                            r = make_float2(a.x + b.x, a.y + b.y);
+                        }
+                        v[h][k * 4 + j * 2] += r.x;
+                        v[h][k * 4 + j * 2 + 1] += r.y;
                     }
         };
+        // out16 = 1: fp16 rows; 2: (hi, lo) fp16 planes (p.out, p.out_lo); 0: fp32 rows
         auto store_tile = [&](const float (&v)[2][16], float *base, int ld, long long grow0, long long nrows, int n0) {
 #pragma unroll
             for (int h = 0; h < 2; h++)
@@ -743,11 +885,52 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const int col = n0 + 8 * k + fc;
-                        if (r < nrows && col < p.Nout)
-                            *reinterpret_cast<float2 *>(base + r * ld + col) =
-                                make_float2(v[h][k * 4 + j * 2], v[h][k * 4 + j * 2 + 1]);
+                        if (r < nrows && col < p.Nout) {
+                            const float a = v[h][k * 4 + j * 2], b = v[h][k * 4 + j * 2 + 1];
+                            if (out16 == 0) {
+                                *reinterpret_cast<float2 *>(base + r * ld + col) = make_float2(a, b);
+                            } else {
+                                const size_t o = (size_t)r * ld + col;
+                                if (out16 == 1) {
+                                    *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(base) + o) = f16x2(a, b);
+                                } else {
+                                    u32 hi, lo;
+                                    f16_split2(a, b, hi, lo);
+                                    *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(base) + o) = hi;
+                                    *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(p.out_lo) + o) = lo;
+                                }
+                            }
+                        }
                     }
                 }
+        };
+        // Staged residual (RES_TMA): the (hi, lo) fp16 boxes of the current 64-column block sit in ring stage rp.stage as
+        // SWIZZLE_128B tiles (row pitch 128 B, 16-byte chunk c of row r at slot c ^ (r & 7)); the 8 rows x 4 lanes of a warp-wide
+        // 4-byte read then cover all 32 banks.  `sub` = which 32-column half of the box.  The first read of a box waits for
+        // its TMA, the second half's read releases the stage to the loader warp.
+        Pipe rp;
+        auto add_res_smem = [&](float (&v)[2][16], int sub) {
+            if (sub == 0) mbar_wait(r_full(rp.stage), rp.phase);
+            const uint8_t *rs = smem + C::RING_BYTES + (size_t)rp.stage * kResStageBytes + (size_t)(q * 32) * 128;
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const uint8_t *rowp = rs + (16 * h + 8 * j + fr) * 128 + fc * 2;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int off = ((sub * 4 + k) ^ fr) << 4;
+                        const float2 a = f16x2_to_float2(*reinterpret_cast<const u32 *>(rowp + off));
+                        const float2 b = f16x2_to_float2(*reinterpret_cast<const u32 *>(rowp + A_TILE_BYTES + off));
+                        v[h][k * 4 + j * 2] += a.x + b.x;
+                        v[h][k * 4 + j * 2 + 1] += a.y + b.y;
+                    }
+                }
+            if (sub == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(r_empty(rp.stage));
+                rp.advance<kResStages>();
+            }
         };
         // max over the ns (16 or 32) consecutive rows of each neighbourhood -> out[group, n0 + ...]
         auto pool_store = [&](const float (&v)[2][16], long long grow0, int n0, int ns) {
@@ -769,7 +952,15 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                 for (int k = 0; k < 4; k++) {
                     const int col = n0 + 8 * k + fc;
                     if (col >= p.Nout) continue;
-                    if (ns == 32) {
+                    if (ns == 64) {
+                        // a neighbourhood spans two quadrants (two warps): combine through atomicMax on the bit patterns —
+                        // E_RELU_MAXPOOL only (values >= 0 order like their int bits), `out` zeroed by the host wrapper
+                        if (grow0 < p.T) {
+                            int *o = reinterpret_cast<int *>(p.out + (grow0 / 64) * p.ldo + col);
+                            atomicMax(o, __float_as_int(fmaxf(m[0][k * 2], m[1][k * 2])));
+                            atomicMax(o + 1, __float_as_int(fmaxf(m[0][k * 2 + 1], m[1][k * 2 + 1])));
+                        }
+                    } else if (ns == 32) {
                         if (grow0 < p.T)
                             *reinterpret_cast<float2 *>(p.out + (grow0 / 32) * p.ldo + col) =
                                 make_float2(fmaxf(m[0][k * 2], m[1][k * 2]), fmaxf(m[0][k * 2 + 1], m[1][k * 2 + 1]));
@@ -801,15 +992,26 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
             constexpr int NW = EW / 4;                       // warps per quadrant
             const int half = EW == 8 ? (ew >> 2) : 0;        // which of them this warp is
             float2 ra[2][8], rb[2][8];
-            if (EPI == E_ADD_MAXPOOL || EPI == E_ADD_LN) {
+            if ((EPI == E_ADD_MAXPOOL || EPI == E_ADD_LN) && !res_tma) {
                 const int nb0 = n_group * NCH * BN;
                 // pull this warp's whole residual slab (32 rows x NCH * BN columns) towards L2 while the MMAs still run:
                 // the register tiles below are then fed at L2 latency, not DRAM latency
                 if (wrow0 + lane < p.T) {
-                    const float *rrow = p.R + (wrow0 + lane) * p.ldr + nb0;
+                    if (res16) {   // two fp16 planes: 128 B = 64 columns of each
+                        const __half *rh = reinterpret_cast<const __half *>(p.R) + (wrow0 + lane) * p.ldr + nb0;
+                        const __half *rl = reinterpret_cast<const __half *>(p.R_lo) + (wrow0 + lane) * p.ldr + nb0;
 #pragma unroll
-                    for (int c = 0; c < NCH * BN; c += 32)
-                        if (nb0 + c < p.Nout) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
+                        for (int c = 0; c < NCH * BN; c += 64)
+                            if (nb0 + c < p.Nout) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rh + c));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rl + c));
+                            }
+                    } else {
+                        const float *rrow = p.R + (wrow0 + lane) * p.ldr + nb0;
+#pragma unroll
+                        for (int c = 0; c < NCH * BN; c += 32)
+                            if (nb0 + c < p.Nout) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
+                    }
                 }
                 issue_tile(ra, p.R, p.ldr, wrow0, p.T, nb0 + 32 * half);
                 if (NW == 1) issue_tile(rb, p.R, p.ldr, wrow0, p.T, nb0 + 32);
@@ -835,7 +1037,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                 v[1][e] = fmaxf(v[1][e], 0.f);
                             }
                         }
-                        store_tile(v, p.out, p.ldo, wrow0, p.store_rows, n0);
+                        store_tile(v, p.out, p.ldo, wrow0, p.T, n0);
                     }
                 }
             } else if (EPI == E_ADD_MAXPOOL || EPI == E_RELU_MAXPOOL) {
@@ -850,8 +1052,12 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     frag_ld(tacc + (b / (BN / 32)) * BN + (b % (BN / 32)) * 32, v);
                     add_bias(v, b * 32);
                     if (EPI == E_ADD_MAXPOOL) {
-                        add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
-                        if (b + 2 < nblk) issue_tile(r, p.R, p.ldr, wrow0, p.T, n0_of(b + 2));
+                        if (res_tma) {
+                            add_res_smem(v, b & 1);
+                        } else {
+                            add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
+                            if (b + 2 < nblk) issue_tile(r, p.R, p.ldr, wrow0, p.T, n0_of(b + 2));
+                        }
                     }
                     if (EPI == E_RELU_MAXPOOL) {
 #pragma unroll
@@ -882,8 +1088,12 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     float v[2][16];
                     frag_ld(tacc + j0, v);
                     add_bias(v, j0);
-                    add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
-                    if (j0 + 64 < E) issue_tile(r, p.R, p.ldr, wrow0, p.T, j0 + 64);
+                    if (res_tma) {
+                        add_res_smem(v, (j0 >> 5) & 1);
+                    } else {
+                        add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
+                        if (j0 + 64 < E) issue_tile(r, p.R, p.ldr, wrow0, p.T, j0 + 64);
+                    }
 #pragma unroll
                     for (int h = 0; h < 2; h++)
 #pragma unroll
@@ -975,7 +1185,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                 const int mt0 = EW == 8 ? (ew >> 2) : 0;         // first m-tile of this warp
                 const int ns = p.ns;
                 const int g = fr, t2 = fc;  // fragment coordinates: row g, column pair t2 = 2 (lane % 4)
-                float *sV = reinterpret_cast<float *>(smem + S * C::STAGE_BYTES + 256) + 4 * 512 + 2 * 512 + q * 32 * kAttnVP;
+                float *sV = reinterpret_cast<float *>(smem + C::PARAM_OFF) + 4 * 512 + 2 * 512 + q * 32 * kAttnVP;
                 auto split = [](float x, u32 &hi, u32 &lo) {
                     hi = __float_as_uint(x) & 0xffffe000u;
                     lo = __float_as_uint(x - __uint_as_float(hi));
@@ -991,17 +1201,31 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                 // pipe with the tcgen05 MMAs of the next item and does not overlap with them (measured: the kernel takes
                 // main loop + ~18 cycles per HMMA), so the instruction count is what the epilogue costs.  A 16x256b
                 // fragment pair (column blocks 2s, 2s + 1) IS the k16 A / B fragment, no permutation needed.
-                constexpr bool BF = NPASS == 2;
-                auto split2 = [](float x0, float x1, u32 &hi, u32 &lo) {   // (x0, x1) -> packed bf16 pairs, x0 in the low half
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-                    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+                // NPASS = 4 (fp16 single-pass GEMM): fp16 m16n8k16, ONE MMA per k-step — a third of the instructions again.
+                constexpr bool BF = NPASS == 2 || NPASS == 4;
+                constexpr bool H1 = NPASS == 4;
+                constexpr int PASS0 = H1 ? 2 : 0;     // pass 2 = (a_hi, b_hi); passes 0, 1 = the compensation terms
+                auto split2 = [](float x0, float x1, u32 &hi, u32 &lo) {   // (x0, x1) -> packed 16-bit pairs, x0 in the low half
+                    if constexpr (H1) {
+                        hi = f16x2(x0, x1);
+                        lo = 0u;
+                    } else {
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+                        const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+                    }
                 };
                 auto mma16 = [](float (&d)[4], const u32 (&a)[4], const u32 (&b)[2]) {
-                    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-                        "{%0,%1,%2,%3};"
-                        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+                    if constexpr (H1)
+                        asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                            "{%0,%1,%2,%3};"
+                            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+                    else
+                        asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                            "{%0,%1,%2,%3};"
+                            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
                 };
                 auto pair_sync = [&]() {  // the two warps of a quadrant (EW = 8)
                     if (EW == 8) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
@@ -1054,7 +1278,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                         split2(kf[kh][4 * k + 4 + 2 * e], kf[kh][4 * k + 5 + 2 * e], bh[kh][e][1], bl[kh][e][1]);
                                     }
 #pragma unroll
-                                for (int pass = 0; pass < 3; pass++)
+                                for (int pass = PASS0; pass < 3; pass++)
 #pragma unroll
                                     for (int ni = 0; ni < NTW; ni++)
 #pragma unroll
@@ -1164,7 +1388,6 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                     if (FULL) pair_sync();  // all 32 rows of V staged (two 16-row neighbourhoods read only their own rows)
                     else __syncwarp();
                     // ---- ctx = P V + bias_v : contraction over the keys; 32 output channels at a time
-                    float *obase = p.out + (size_t)n_group * HD;
 #pragma unroll
                     for (int nb = 0; nb < HD / 32; nb++) {   // (unrolled: the two channel halves are independent chains)
                         float o[MTW][4][4];
@@ -1209,7 +1432,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
 #pragma unroll
                                     for (int mi = 0; mi < MTW; mi++) afrag16(sc[mi][2 * s16], sc[mi][2 * s16 + 1], ah[mi], al[mi]);
 #pragma unroll
-                                    for (int pass = 0; pass < 3; pass++)
+                                    for (int pass = PASS0; pass < 3; pass++)
 #pragma unroll
                                         for (int n4 = 0; n4 < 4; n4++)
 #pragma unroll
@@ -1223,7 +1446,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
                                     bfrag16(mt0 + mi, bh, bl);
                                     afrag16(sc[mi][0], sc[mi][1], ah, al);
 #pragma unroll
-                                    for (int pass = 0; pass < 3; pass++)
+                                    for (int pass = PASS0; pass < 3; pass++)
 #pragma unroll
                                         for (int n4 = 0; n4 < 4; n4++)
                                             mma16(o[mi][n4], pass == 1 ? al : ah, pass == 0 ? bl[n4] : bh[n4]);
@@ -1264,12 +1487,14 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
 #pragma unroll
                             for (int r = 0; r < 2; r++) {
                                 const long long row = wrow0 + 16 * (mt0 + mi) + 8 * r + g;
-                                if (row < p.store_rows) {
+                                if (row < p.T) {
 #pragma unroll
                                     for (int n4 = 0; n4 < 4; n4++) {
                                         const float2 bv = *reinterpret_cast<const float2 *>(sbias + 2 * HD + 32 * nb + 8 * n4 + t2);
-                                        *reinterpret_cast<float2 *>(obase + row * p.ldo + 32 * nb + 8 * n4 + t2) =
-                                            make_float2(o[mi][n4][2 * r] + bv.x, o[mi][n4][2 * r + 1] + bv.y);
+                                        const float oa = o[mi][n4][2 * r] + bv.x, ob = o[mi][n4][2 * r + 1] + bv.y;
+                                        const size_t oo = (size_t)n_group * HD + (size_t)row * p.ldo + 32 * nb + 8 * n4 + t2;
+                                        if (out16) *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(p.out) + oo) = f16x2(oa, ob);
+                                        else *reinterpret_cast<float2 *>(p.out + oo) = make_float2(oa, ob);
                                     }
                                 }
                             }
@@ -1306,25 +1531,29 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>::
     }
 }
 
-// CTAs of the persistent grid.  148 = every SM; a pipelined caller that overlaps this kernel with SM-filling latency
-// chains of another batch (FPS: one 192 KB-smem CTA per scene) lowers it so that no CTA of the grid waits for an SM.
-int g_persistent_ctas = pdab::kNumSMs;
+// Launch policy of the calling thread (pdab_set_persistent_ctas / pdab_set_cta_pairs): thread-local, so two pipelines
+// driven from two host threads do not see each other's settings, and baked into a CUDA graph at capture time.
+// persistent CTAs: 0 = every SM of the current device; a pipelined caller that overlaps these kernels with SM-filling
+// latency chains of another batch (FPS: one 192 KB-smem CTA per scene) lowers it so that no CTA of the grid waits for an SM.
+thread_local int g_persistent_ctas = 0;
 // 1: cta_group::2 CTA pairs (M = 256 per pair) whenever the problem has at least one full pair tile per pair; 0: single CTAs.
-int g_cta_pairs = 1;
+thread_local int g_cta_pairs = 1;
+
+int persistent_ctas() {
+    if (g_persistent_ctas > 0) return g_persistent_ctas;
+    int dev = 0, sms = pdab::kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
 int launch_cg(GemmParams p, cudaStream_t s) {
-    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value>;
+    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, ALOAD>;
     auto kern = tc_gemm_kernel<NPASS, BN, NCH, ALOAD, EPI, CG>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     p.n_items = ((p.T + BM * CG - 1) / (BM * CG)) * p.n_groups;
-    static const bool nostore = getenv("PDAB_TC_NOSTORE") != nullptr;
-    p.store_rows = nostore ? 0 : p.T;
-    long long grid = p.n_items * CG < g_persistent_ctas ? p.n_items * CG : g_persistent_ctas;
+    long long grid = p.n_items * CG < p.persistent_ctas ? p.n_items * CG : p.persistent_ctas;
     if (CG == 2) grid &= ~1LL;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -1344,9 +1573,10 @@ int launch_cg(GemmParams p, cudaStream_t s) {
 }
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI>
-int launch(const GemmParams &p, cudaStream_t s) {
+int launch(GemmParams &p, cudaStream_t s) {
+    p.persistent_ctas = persistent_ctas();
     // CTA pairs pay off once every pair has whole 256-row tiles to chew on; tiny problems stay on single CTAs
-    if (g_cta_pairs && g_persistent_ctas >= 2 && p.T >= 2 * BM * 8)
+    if (g_cta_pairs && p.persistent_ctas >= 2 && p.T >= 2 * BM * 8)
         return launch_cg<NPASS, BN, NCH, ALOAD, EPI, 2>(p, s);
     return launch_cg<NPASS, BN, NCH, ALOAD, EPI, 1>(p, s);
 }
@@ -1356,20 +1586,23 @@ int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
     const int chunks = (p.Nout + bn - 1) / bn;
     auto items = [&](int nch) { p.n_groups = chunks / nch; };
     if (epi == E_ADD_LN) {
-        if (ALOAD != A_ROWS || bn != 256 || p.Nout % 256 || chunks > 2) return PDAB_EUNSUPPORTED;
+        if (ALOAD == A_GATHER || bn != 256 || p.Nout % 256 || chunks > 2) return PDAB_EUNSUPPORTED;
+        constexpr int AL = ALOAD == A_GATHER ? A_ROWS : ALOAD;
         if (chunks == 1) {
             items(1);
-            return launch<NPASS, 256, 1, A_ROWS, E_ADD_LN>(p, s);
+            return launch<NPASS, 256, 1, AL, E_ADD_LN>(p, s);
         }
         items(2);
-        return launch<NPASS, 256, 2, A_ROWS, E_ADD_LN>(p, s);
+        return launch<NPASS, 256, 2, AL, E_ADD_LN>(p, s);
     }
     items(1);
     if (epi == E_ATTN) {
-        if (ALOAD != A_ROWS || bn != 192 || p.Nout % 192) return PDAB_EUNSUPPORTED;
-        return launch<NPASS, 192, 1, A_ROWS, E_ATTN>(p, s);
+        if (ALOAD == A_GATHER || bn != 192 || p.Nout % 192) return PDAB_EUNSUPPORTED;
+        constexpr int AL = ALOAD == A_GATHER ? A_ROWS : ALOAD;
+        return launch<NPASS, 192, 1, AL, E_ATTN>(p, s);
     }
-    if (bn == 192 && epi == E_STORE && ALOAD == A_ROWS) return launch<NPASS, 192, 1, A_ROWS, E_STORE>(p, s);
+    if constexpr (ALOAD != A_GATHER)
+        if (bn == 192 && epi == E_STORE) return launch<NPASS, 192, 1, ALOAD, E_STORE>(p, s);
     if (bn == 256) {
         switch (epi) {
             case E_STORE: return launch<NPASS, 256, 1, ALOAD, E_STORE>(p, s);
@@ -1388,10 +1621,40 @@ int dispatch(GemmParams &p, int epi, int bn, cudaStream_t s) {
     return PDAB_EUNSUPPORTED;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// fp16 (rows, ld) row-major matrix -> boxes of 64 columns x 128 rows, SWIZZLE_128B (the K-major UMMA tile), zero fill
+int make_a_map(CUtensorMap *map, const void *a, long long rows, int k, int ld) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return PDAB_EUNSUPPORTED;
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(a), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PDAB_EINVAL;
+}
+
 }  // namespace
 
 extern "C" int pdab_set_persistent_ctas(int n) {
-    if (n < 1 || n > pdab::kNumSMs) return PDAB_EINVAL;
+    if (n < 0 || n > 1024) return PDAB_EINVAL;
     g_persistent_ctas = n;
     return 0;
 }
@@ -1440,15 +1703,74 @@ extern "C" int pdab_tc_linear(long long rows, int k, int nout, int npass, int bn
            : npass == 2 ? dispatch<2, A_ROWS>(p, epilogue, bn, s) : dispatch<1, A_ROWS>(p, epilogue, bn, s);
 }
 
-extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
-                                        const float *features_t, const float *xyz, const float *new_xyz,
-                                        const float *w_packed, const float *bias, float *out, int ldo,
-                                        pdab_stream_t stream) {
+// fp16 single-pass form (NPASS = 4); see include/pdab.h.
+extern "C" int pdab_tc_linear_h(long long rows, int k, int nout, int bn, int epilogue, const void *a, int lda, int a_fp16,
+                                const float *w_packed, const float *bias, const void *res_hi, const void *res_lo, int ldr,
+                                const float *gamma, const float *beta, float eps, int nsample, void *out, void *out_lo,
+                                int ldo, int out_fmt, pdab_stream_t stream) {
+    if (rows < 0 || k < 1 || nout < 1 || !a || !w_packed || !out) return PDAB_EINVAL;
+    if (rows == 0) return 0;
+    if ((k & 7) || (lda & 7) || (ldo & 3) || (nout & 3) || lda < k || rows > 0x7fffffffLL) return PDAB_EINVAL;
+    if (out_fmt < 0 || out_fmt > 2 || (out_fmt == 2 && !out_lo)) return PDAB_EINVAL;
+    if (bn != 128 && bn != 256 && !(bn == 192 && (epilogue == E_ATTN || epilogue == E_STORE))) return PDAB_EINVAL;
+    if (epilogue == E_ATTN && (bn != 192 || nout % 192 || (nsample != 16 && nsample != 32) || rows % nsample || out_fmt == 2))
+        return PDAB_EUNSUPPORTED;
+    if ((epilogue == E_ADD_LN || epilogue == E_ADD_MAXPOOL) && (!res_hi || (ldr & 3))) return PDAB_EINVAL;
+    if (epilogue == E_ADD_LN && (!gamma || !beta)) return PDAB_EINVAL;
+    if (epilogue != E_ADD_LN && out_fmt == 2) return PDAB_EUNSUPPORTED;
+    if ((epilogue == E_ADD_MAXPOOL || epilogue == E_RELU_MAXPOOL) &&
+        ((nsample != 16 && nsample != 32 && !(nsample == 64 && epilogue == E_RELU_MAXPOOL)) || rows % nsample || out_fmt != 0))
+        return PDAB_EUNSUPPORTED;
+    GemmParams p{};
+    p.A = reinterpret_cast<const float *>(a);
+    p.lda = lda;
+    p.T = rows;
+    p.K = k;
+    p.KA = (k + 63) / 64;
+    p.Wp = w_packed;
+    p.bias = bias;
+    p.Nout = nout;
+    p.out = reinterpret_cast<float *>(out);
+    p.out_lo = out_lo;
+    p.out16 = out_fmt;
+    p.ldo = ldo;
+    p.R = reinterpret_cast<const float *>(res_hi);
+    p.R_lo = res_lo;
+    p.res16 = res_lo != nullptr;
+    p.ldr = ldr;
+    p.gamma = gamma;
+    p.beta = beta;
+    p.eps = eps;
+    p.ns = nsample;
+    cudaStream_t s = pdab::to_stream(stream);
+    if (nsample == 64 && epilogue == E_RELU_MAXPOOL)   // the two half-neighbourhood maxima meet through atomicMax
+        PDAB_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)nout * sizeof(float), (size_t)(rows / 64), s));
+    if (a_fp16) {
+        if (reinterpret_cast<uintptr_t>(a) & 15) return PDAB_EINVAL;
+        int rc = make_a_map(&p.tmA, a, rows, k, lda);
+        if (rc) return rc;
+        // residual as a (hi, lo) fp16 plane pair covering whole accumulator chunks: staged through shared memory by TMA
+        if (res_lo && (epilogue == E_ADD_LN || epilogue == E_ADD_MAXPOOL) && nout % bn == 0 && !(ldr & 7) &&
+            !((reinterpret_cast<uintptr_t>(res_hi) | reinterpret_cast<uintptr_t>(res_lo)) & 15)) {
+            rc = make_a_map(&p.tmRh, res_hi, rows, nout, ldr);
+            if (!rc) rc = make_a_map(&p.tmRl, res_lo, rows, nout, ldr);
+            if (rc) return rc;
+            p.res_tma = 1;
+        }
+        return dispatch<4, A_TMA>(p, epilogue, bn, s);
+    }
+    return dispatch<4, A_ROWS>(p, epilogue, bn, s);
+}
+
+static int sa_gather(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
+                     const float *features_t, const float *xyz, const float *new_xyz, const float *w_packed,
+                     const float *bias, void *out, int ldo, int out_fp16, pdab_stream_t stream) {
     if (b < 0 || c < 0 || n < 1 || m < 1 || nsample < 1 || nout < 1 || !idx || !xyz || !new_xyz || !w_packed || !out)
         return PDAB_EINVAL;
     if (b == 0) return 0;
     if ((c & 3) || (c > 0 && !features_t) || (ldo & 3) || (nout & 3)) return PDAB_EINVAL;
-    if (npass < 1 || npass > 3 || (npass == 2 && (c & 7))) return PDAB_EINVAL;
+    if (npass < 1 || npass > 4 || (BK_IS_64(npass) && (c & 7))) return PDAB_EINVAL;
+    if (out_fp16 && npass != 4) return PDAB_EINVAL;
     GemmParams p{};
     p.T = (long long)b * m * nsample;
     p.K = c + 3;
@@ -1464,9 +1786,26 @@ extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample,
     p.Wp = w_packed;
     p.bias = bias;
     p.Nout = nout;
-    p.out = out;
+    p.out = reinterpret_cast<float *>(out);
+    p.out16 = out_fp16 ? 1 : 0;
     p.ldo = ldo;
     cudaStream_t s = pdab::to_stream(stream);
-    return npass == 3 ? dispatch<3, A_GATHER>(p, E_RELU, 256, s)
+    return npass == 4   ? dispatch<4, A_GATHER>(p, E_RELU, 256, s)
+           : npass == 3 ? dispatch<3, A_GATHER>(p, E_RELU, 256, s)
            : npass == 2 ? dispatch<2, A_GATHER>(p, E_RELU, 256, s) : dispatch<1, A_GATHER>(p, E_RELU, 256, s);
+}
+
+extern "C" int pdab_tc_sa_gather_linear(int b, int c, int n, int m, int nsample, int nout, int npass, const int *idx,
+                                        const float *features_t, const float *xyz, const float *new_xyz,
+                                        const float *w_packed, const float *bias, float *out, int ldo,
+                                        pdab_stream_t stream) {
+    if (npass == 4) return PDAB_EINVAL;   // the fp16 mode is pdab_tc_sa_gather_linear_h
+    return sa_gather(b, c, n, m, nsample, nout, npass, idx, features_t, xyz, new_xyz, w_packed, bias, out, ldo, 0, stream);
+}
+
+extern "C" int pdab_tc_sa_gather_linear_h(int b, int c, int n, int m, int nsample, int nout, const int *idx,
+                                          const float *features_t, const float *xyz, const float *new_xyz,
+                                          const float *w_packed, const float *bias, void *out, int ldo, int out_fp16,
+                                          pdab_stream_t stream) {
+    return sa_gather(b, c, n, m, nsample, nout, 4, idx, features_t, xyz, new_xyz, w_packed, bias, out, ldo, out_fp16, stream);
 }

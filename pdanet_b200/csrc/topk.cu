@@ -116,12 +116,9 @@ extern "C" int pdab_topk_ctr(int b, int n, int c, int npoint, const float *cls, 
     int P2 = 1;
     while (P2 < npoint) P2 <<= 1;
     const size_t smem = (size_t)P2 * sizeof(unsigned long long);
-    static bool configured = false;
-    if (!configured) {
-        PDAB_CUDA(cudaFuncSetAttribute(topk_ctr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kMaxSelect * sizeof(unsigned long long))));
-        configured = true;
-    }
+    // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
+    PDAB_CUDA(cudaFuncSetAttribute(topk_ctr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kMaxSelect * sizeof(unsigned long long))));
     topk_ctr_kernel<<<b, kThreads, smem, pdab::to_stream(stream)>>>(n, c, npoint, cls, idx);
     PDAB_LAUNCH_CHECK();
     return 0;

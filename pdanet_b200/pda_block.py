@@ -25,7 +25,8 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from .tc_linear import (EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_ATTN, EPI_RELU, EPI_STORE, PackedLinear, attn_in_proj)
+from .tc_linear import (EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_ATTN, EPI_RELU, EPI_STORE, OUT_F16, OUT_SPLIT, PackedLinear,
+                        SplitHalf, attn_in_proj)
 
 
 class LinearExact:
@@ -91,6 +92,10 @@ class PDAScalePlan:
                 self._enc_params = ops.pda_encode_params(w1, b1, w2, b2, dens_layers, self.norm1.weight, self.norm1.bias)
             glob = torch.cat([new_xyz.reshape(G, 3), centre_feature_t.reshape(G, C)], dim=1)
             glob = F.relu_(self.global_[1](F.relu_(self.global_[0](glob))))
+            if self.in_proj.npass == 4:   # fp16 single-pass path: tokens leave the encoder as (hi, lo) fp16 planes
+                y = ops.pda_encode_ln(self.radius, ns, xyz, new_xyz, features_t, glob, self._enc_params, self.norm1.eps,
+                                      split_half=True)
+                return self._transformer_h(ops, y, B, M, ns)
             y = ops.pda_encode_ln(self.radius, ns, xyz, new_xyz, features_t, glob, self._enc_params, self.norm1.eps)
             return self._transformer(ops, y, B, M, ns)
 
@@ -114,6 +119,8 @@ class PDAScalePlan:
 
         # token assembly + LayerNorm 1 in one pass (csrc/pda_elem.cu)
         y = ops.pda_assemble_ln(pos, X, scale.reshape(T), glob, ns, self.norm1)
+        if self.in_proj.npass == 4:
+            return self._transformer_h(ops, SplitHalf.from_float(y), B, M, ns)
         return self._transformer(ops, y, B, M, ns)
 
     def _transformer(self, ops, y, B, M, ns):
@@ -127,4 +134,19 @@ class PDAScalePlan:
         h = self.lin1(z, EPI_RELU)
         pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)          # max_s (z + ffn), (:931)
         out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU)              # (G, C_out)
+        return out.view(B, M, -1).permute(0, 2, 1)
+
+    def _transformer_h(self, ops, y: SplitHalf, B, M, ns):
+        """The same block in the fp16 single-pass mode (tc_linear npass = 4): every GEMM operand is an fp16 matrix loaded
+        by TMA, one tcgen05 MMA per k-step; the two residual streams (y, z) are (hi, lo) fp16 plane pairs, i.e. keep
+        fp32-level precision — they, not the products, set the block's output error (tools/precision_study.py)."""
+        if self.fused_attention:
+            ctx = self.in_proj_attn(y.hi, EPI_ATTN, nsample=ns, out_fmt=OUT_F16)          # (T, E) fp16; qkv never exists
+        else:
+            qkv = self.in_proj(y.hi, EPI_STORE, out_fmt=OUT_F16)                         # (T, 3E) fp16
+            ctx = ops.group_attention_h(qkv, ns, self.heads)                             # (T, E) fp16
+        z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2, out_fmt=OUT_SPLIT)   # LN2(y + attn) as (hi, lo)
+        h = self.lin1(z.hi, EPI_RELU, out_fmt=OUT_F16)
+        pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)                   # max_s (z + ffn), fp32 (G, E)
+        out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU)                       # (G, C_out)
         return out.view(B, M, -1).permute(0, 2, 1)

@@ -118,6 +118,39 @@ class _SamplingSABase(nn.Module):
         self.dilated_group = dilated_group
         self.ops = ops if ops is not None else _cuda_ops
 
+    # ---- derived parameter caches (BN-folded weights, packed tensor-core images, encoder parameter blocks)
+    # They are built lazily in eval mode and must die with the parameters they were derived from: `.train()`,
+    # `load_state_dict`, `.to(device)` / `.half()` (`_apply`) and in-place updates (optimizer steps bump `_version`)
+    # all invalidate them.  A CUDA graph captured by `ScenePipeline` bakes the cached buffers in: rebuild the pipeline
+    # after any weight change.
+    def _drop_caches(self):
+        raise NotImplementedError
+
+    def _fingerprint(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _caches_fresh(self):
+        """Call at the top of an eval forward: drops the caches if any parameter / buffer changed since they were built."""
+        fp = self._fingerprint()
+        if fp != getattr(self, "_cache_fp", None):
+            self._drop_caches()
+            self._cache_fp = fp
+
+    def train(self, mode: bool = True):
+        self._drop_caches()
+        self._cache_fp = None
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._drop_caches()
+        self._cache_fp = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._drop_caches()
+        self._cache_fp = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _make_heads(self, out_channels, aggregation_mlp, confidence_mlp, num_class, have_scales):
         if aggregation_mlp and have_scales:
             layers, out_channels = _conv_bn_relu_1d(out_channels, aggregation_mlp)
@@ -221,10 +254,9 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         # 1e-6); 1 = plain TF32 (5e-4, the reference's own default class)
         self.tc_passes = 2
 
-    def train(self, mode: bool = True):
+    def _drop_caches(self):
         self._folded = None
         self._wide = {}
-        return super().train(mode)
 
     def _folded_params(self, i):
         if self._folded is None:
@@ -240,7 +272,8 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         seq = self.mlps[i]
         widths = [seq[3 * k].out_channels for k in range(len(seq) // 3)]
         return (features is not None and features.shape[1] % 4 == 0 and features.shape[1] >= 32 and len(widths) == 3
-                and all(w % 4 == 0 for w in widths) and self.nsamples[i] in (16, 32)
+                and all(w % 4 == 0 for w in widths)
+                and (self.nsamples[i] in (16, 32) or (self.nsamples[i] == 64 and self.tc_passes == 4))
                 and hasattr(self.ops, "ball_query") and features.is_cuda)
 
     def _scale_wide(self, i, xyz, new_xyz, features_t):
@@ -254,8 +287,13 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         ns = self.nsamples[i]
         B, M, _ = new_xyz.shape
         idx = self.ops.ball_query(self.radii[i], ns, xyz, new_xyz)          # (B, M, ns) int32
-        h = l1.sa_gather(idx, features_t, xyz, new_xyz)                     # (B*M*ns, c1): grouped tensor never exists
-        h = l2(h, EPI_RELU)
+        if l1.npass == 4 and l2.npass == 4 and l3.npass == 4:               # fp16 single pass, fp16 activations between layers
+            from .tc_linear import OUT_F16
+            h = l1.sa_gather(idx, features_t, xyz, new_xyz, out_fmt=OUT_F16)
+            h = l2(h, EPI_RELU, out_fmt=OUT_F16)
+        else:
+            h = l1.sa_gather(idx, features_t, xyz, new_xyz)                 # (B*M*ns, c1): grouped tensor never exists
+            h = l2(h, EPI_RELU)
         pooled = l3(h, EPI_RELU_MAXPOOL, nsample=ns)                        # (B*M, c3)
         return pooled.view(B, M, -1).permute(0, 2, 1)
 
@@ -303,6 +341,8 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         """xyz (B,N,3), features (B,C,N), cls_features (B,N,num_class) ->
         (new_xyz (B,npoint,3), new_features (B,C',npoint), cls_features (B,npoint,num_class) | None, sampled_idx)."""
         ops = self.ops
+        if not self.training:
+            self._caches_fresh()
         sampled_idx = []
         if ctr_xyz is None:
             sampled_idx = self._sample(xyz, features, cls_features)
@@ -383,9 +423,8 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
         self.tc_passes = 2      # tensor-core product mode of the fast path: 2 = split-bf16 (1e-5), 3 = 3xTF32 (1e-6), 1 = TF32
         self._plans = {}
 
-    def train(self, mode: bool = True):
+    def _drop_caches(self):
         self._plans = {}
-        return super().train(mode)
 
     def _fast_path_ok(self, features):
         return (self.fast_eval and not self.training and not torch.is_grad_enabled()
@@ -424,6 +463,8 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
     def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, cls_features: torch.Tensor = None,
                 new_xyz=None, ctr_xyz=None):
         ops = self.ops
+        if not self.training:
+            self._caches_fresh()
         sampled_idx = []
         centre_feature = None
         if ctr_xyz is None:

@@ -287,9 +287,10 @@ def pda_encode_params(w1, b1, w2, b2, dens, gamma, beta) -> torch.Tensor:
 
 
 def pda_encode_ln(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, features_t: torch.Tensor,
-                  glob: torch.Tensor, params: torch.Tensor, eps: float) -> torch.Tensor:
+                  glob: torch.Tensor, params: torch.Tensor, eps: float, split_half: bool = False):
     """Fused PDA token encoder (forward only): LayerNorm(cat[pos, feat*scale, feat, glob]) per (centre, neighbour)
-    token, (B*M*nsample, 4C); see include/pdab.h `pdab_pda_encode_ln`."""
+    token, (B*M*nsample, 4C); see include/pdab.h `pdab_pda_encode_ln`.  split_half: the rows are returned as a
+    `tc_linear.SplitHalf` — a (hi, lo) pair of fp16 planes, hi + lo = the fp32 row to ~2^-22 (`pdab_pda_encode_ln_h`)."""
     for t in (xyz, new_xyz, features_t, glob, params):
         if not t.is_cuda:
             raise RuntimeError("pda_encode_ln needs CUDA tensors")
@@ -298,6 +299,14 @@ def pda_encode_ln(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch
     M = new_xyz.shape[1]
     C = features_t.shape[2]
     assert glob.shape == (B * M, C)
+    if split_half:
+        from .tc_linear import SplitHalf
+        y = SplitHalf.empty(B * M * nsample, 4 * C, xyz.device)
+        with torch.cuda.device(xyz.device):
+            _lib.call("pdab_pda_encode_ln_h", B, C, N, M, float(radius), nsample, xyz.data_ptr(), new_xyz.data_ptr(),
+                      features_t.data_ptr(), glob.data_ptr(), params.data_ptr(), float(eps), y.hi.data_ptr(),
+                      y.lo.data_ptr(), torch.cuda.current_stream(xyz.device).cuda_stream)
+        return y
     y = torch.empty(B * M * nsample, 4 * C, dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         _lib.call("pdab_pda_encode_ln", B, C, N, M, float(radius), nsample, xyz.data_ptr(), new_xyz.data_ptr(),
@@ -347,6 +356,20 @@ def group_attention(qkv, nsample, heads, npass: int = 3):
     with torch.cuda.device(qkv.device):
         _lib.call("pdab_group_attention", T // nsample, nsample, heads, E // heads, int(npass), qkv.data_ptr(),
                   ctx.data_ptr(), _stream_of(qkv))
+    return ctx
+
+
+def group_attention_h(qkv, nsample, heads):
+    """fp16 form of `group_attention`: qkv (T, 3E) fp16 -> ctx (T, E) fp16 (fp16 MMAs, fp32 accumulation and softmax)."""
+    if not qkv.is_cuda:
+        raise RuntimeError("group_attention_h needs CUDA tensors")
+    T, E3 = qkv.shape
+    E = E3 // 3
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous() and T % nsample == 0 and E % heads == 0
+    ctx = torch.empty(T, E, dtype=torch.float16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.call("pdab_group_attention_h", T // nsample, nsample, heads, E // heads, qkv.data_ptr(), ctx.data_ptr(),
+                  _stream_of(qkv))
     return ctx
 
 

@@ -97,20 +97,21 @@ class ScenePipeline:
         # N > 16384: a scene's FPS runs on a cluster of CTAs; pipelined, the smallest cluster that holds the scene (16384
         # points per CTA) keeps the chain on few SMs beside the other batches' kernels instead of taking the whole GPU
         fps_ctas = -(-N // 16384)
+        self._fps_cluster = 16
         if depth > 1 and fps_ctas > 1:
             cl = 1
             while cl < fps_ctas:
                 cl *= 2
             fps_ctas = cl
-            _lib.check("pdab_set_fps_max_cluster", _lib.lib().pdab_set_fps_max_cluster(min(16, cl)))
+            self._fps_cluster = min(16, cl)
         if reserve_sms is None:  # one SM per FPS CTA of ONE in-flight FPS kernel (deeper pipelines rarely overlap two)
             reserve_sms = B * fps_ctas if depth > 1 and B * fps_ctas < 100 else 0
         self.reserve_sms = reserve_sms
-        _lib.check("pdab_set_persistent_ctas", _lib.lib().pdab_set_persistent_ctas(148 - reserve_sms))
+        self._ctas = torch.cuda.get_device_properties(dev).multi_processor_count - reserve_sms
         if warm_points is None:
             warm_points = make_batch(B, N, runner.cfg.POINT_CLOUD_RANGE)["points"]
         self.slots = []
-        with torch.cuda.device(dev), torch.no_grad():
+        with torch.cuda.device(dev), torch.no_grad(), self._launch_policy():
             for _ in range(depth):
                 s = SimpleNamespace(stream=torch.cuda.Stream(dev), inp=torch.empty(B * N, 5, device=dev),
                                     pinned_in=torch.empty(B * N, 5).pin_memory(), graph=None, out=None,
@@ -132,6 +133,25 @@ class ScenePipeline:
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.slots[0].pinned_out.values())
         self.h2d_bytes = B * N * 5 * 4
 
+    def _launch_policy(self):
+        """The library's thread-local launch policy for THIS pipeline's launches (grid of the persistent tensor-core kernels,
+        FPS cluster cap), restored to the defaults on exit: other runners / direct op calls of the process are not affected,
+        and a captured CUDA graph keeps the shapes it was captured with."""
+        import contextlib
+        from . import _lib
+
+        @contextlib.contextmanager
+        def scope():
+            lib = _lib.lib()
+            _lib.check("pdab_set_persistent_ctas", lib.pdab_set_persistent_ctas(self._ctas))
+            _lib.check("pdab_set_fps_max_cluster", lib.pdab_set_fps_max_cluster(self._fps_cluster))
+            try:
+                yield
+            finally:
+                lib.pdab_set_persistent_ctas(0)
+                lib.pdab_set_fps_max_cluster(16)
+        return scope()
+
     def _forward(self, points_dev):
         prev = self.model.output_padded
         self.model.output_padded = True
@@ -147,7 +167,8 @@ class ScenePipeline:
             if self.graphs:
                 s.graph.replay()
             else:
-                s.out = self._forward(s.inp)
+                with self._launch_policy():
+                    s.out = self._forward(s.inp)
             if to_host:
                 for k, v in s.out.items():
                     s.pinned_out[k].copy_(v, non_blocking=True)

@@ -148,12 +148,16 @@ def test_cuda_backbone_matches_reference_modules_golden():
     replay_reference_backbone_golden(pointnet2_utils, "cuda", rtol=RTOL)
 
 
-def test_pda_fast_path_equals_reference_statement_order(models):
-    """pda_block.py (token-major, folded BN, 3xTF32 projections) vs the module's reference-order forward, same inputs."""
+@pytest.mark.parametrize("tc_passes,tol", [(2, 1e-4), (4, 6e-4)])
+def test_pda_fast_path_equals_reference_statement_order(models, tc_passes, tol):
+    """pda_block.py (token-major, folded BN, tensor-core projections) vs the module's reference-order forward (fp32 torch),
+    same inputs.  tc_passes = 2: split-bf16 products; 4: fp16 single pass with fp16 activations between the kernels and
+    (hi, lo) fp16 residual streams — both far inside the 1e-3 feature bar."""
     cfg, gpu, _ = models
     g = torch.Generator().manual_seed(11)
     for layer, (N, C) in ((1, (4096, 64)), (2, (1024, 128))):
         mod = gpu.backbone_3d.SA_modules[layer]
+        prev_passes, mod.tc_passes, mod._plans = mod.tc_passes, tc_passes, {}
         xyz = (torch.rand(2, N, 3, generator=g) * torch.tensor([30.0, 30.0, 2.0])).cuda()
         feats = torch.randn(2, C, N, generator=g).cuda()
         cls = torch.randn(2, N, 3, generator=g).cuda()
@@ -163,10 +167,11 @@ def test_pda_fast_path_equals_reference_statement_order(models):
             mod.fast_eval = False
             slow = mod(xyz, feats, cls)
             mod.fast_eval = True
+        mod.tc_passes, mod._plans = prev_passes, {}
         assert torch.equal(fast[3], slow[3])
         scale = slow[1].abs().max().item()
-        assert (fast[1] - slow[1]).abs().max().item() <= 1e-4 * scale
-        assert (fast[2] - slow[2]).abs().max().item() <= 1e-4 * slow[2].abs().max().item()
+        assert (fast[1] - slow[1]).abs().max().item() <= tol * scale
+        assert (fast[2] - slow[2]).abs().max().item() <= tol * slow[2].abs().max().item()
 
 
 def test_pda_group_tokens_matches_channel_major_grouper():
@@ -239,12 +244,9 @@ def test_pipelined_runner_equals_sequential_runner(graphs):
     runner = SceneRunner(cfg, device="cuda:0", batch_size=B, num_points=N, seed=0)
     batches = [make_batch(B, N, cfg.POINT_CLOUD_RANGE, first_scene=10 * k)["points"] for k in range(5)]
     want = [runner.infer(b) for b in batches]
-    try:
-        pipe = ScenePipeline(runner, depth=2, graphs=graphs, warm_points=batches[0])
-        got = pipe.run(batches)
-        got2 = pipe.run(batches[::-1])[::-1]       # slots reused in another order: no state leaks between replays
-    finally:
-        _lib.lib().pdab_set_persistent_ctas(148)
+    pipe = ScenePipeline(runner, depth=2, graphs=graphs, warm_points=batches[0])
+    got = pipe.run(batches)
+    got2 = pipe.run(batches[::-1])[::-1]       # slots reused in another order: no state leaks between replays
     if graphs:
         assert pipe.launches_per_step > 20
     for res in (got, got2):

@@ -144,3 +144,42 @@ def replay_reference_backbone_golden(ops_base, device, rtol):
 
 def test_backbone_matches_reference_modules_golden():
     replay_reference_backbone_golden(torch_ops, "cpu", rtol=1e-5)
+
+
+def test_derived_weight_caches_die_with_the_weights():
+    """BN-folded / packed weight caches of the SA modules are rebuilt after load_state_dict, an in-place parameter update,
+    .to() / .float() and .train() — a stale cache would silently compute with the old weights."""
+    from pdanet_b200.config import load_config
+    from pdanet_b200.iassd import build_model
+    from oracle import torch_ops
+    cfg = load_config("kitti")
+    torch.manual_seed(0)
+    model = build_model(cfg, ops=torch_ops, nms_utils=torch_ops.nms_utils, batched_post_processing=False).eval()
+    plain, pda = model.backbone_3d.SA_modules[0], model.backbone_3d.SA_modules[1]
+
+    def poison():
+        plain._caches_fresh(), pda._caches_fresh()
+        plain._folded, plain._wide, pda._plans = {"stale": 1}, {"stale": 1}, {"stale": 1}
+
+    def clean():
+        plain._caches_fresh(), pda._caches_fresh()
+        return plain._folded is None and plain._wide == {} and pda._plans == {}
+
+    poison()
+    plain._caches_fresh(), pda._caches_fresh()
+    assert plain._folded == {"stale": 1} and pda._plans == {"stale": 1}      # nothing changed: caches kept
+    model.load_state_dict(model.state_dict())
+    assert clean()
+    poison()
+    with torch.no_grad():
+        next(plain.parameters()).mul_(1.0)                                   # in-place update bumps _version
+        next(pda.parameters()).add_(0.0)
+    assert clean()
+    poison()
+    model.double()
+    assert clean()
+    model.float()
+    poison()
+    model.train()
+    assert plain._folded is None and pda._plans == {}
+    model.eval()
