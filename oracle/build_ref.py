@@ -15,6 +15,11 @@ into this repo), for sm_100a:
       (nms_gpu, nms_normal_gpu, boxes_overlap_bev_gpu, boxes_iou_bev_gpu,
       boxes_iou_bev_cpu).
 
+  oracle/_ref/pyref/pcdet/...
+      byte-for-byte copies of the reference PYTHON files of the path (PB/pointnet2_utils.py, pointnet2_modules.py,
+      PointFormer.py, backbones_3d/IASSD_backbone.py, iou3d_nms/iou3d_nms_utils.py, model_utils/model_nms_utils.py), so
+      that a GPU test can run the UNMODIFIED reference modules on libpdab.so (tests/test_gpu_reference_python.py).
+
 oracle/_ref/ is git-ignored but NOT gpurun-ignored: the built .so files travel
 to the GPU box, where /root/reference does not exist.  Nothing here runs the
 reference's own build system (setup.py); it is plain nvcc / g++ on the files.
@@ -56,6 +61,29 @@ def _run(cmd):
     subprocess.check_call([str(c) for c in cmd])
 
 
+PY_FILES = [
+    "pcdet/ops/pointnet2/pointnet2_batch/pointnet2_utils.py",
+    "pcdet/ops/pointnet2/pointnet2_batch/pointnet2_modules.py",
+    "pcdet/ops/pointnet2/pointnet2_batch/PointFormer.py",
+    "pcdet/models/backbones_3d/IASSD_backbone.py",
+    "pcdet/ops/iou3d_nms/iou3d_nms_utils.py",
+    "pcdet/models/model_utils/model_nms_utils.py",
+]
+
+
+def stage_python() -> bool:
+    """Copies the reference's Python files of the path into oracle/_ref/pyref (git-ignored; travels to the GPU box)."""
+    import shutil
+    dst_root = OUT / "pyref"
+    if not all((REF / f).exists() for f in PY_FILES):
+        return all((dst_root / f).exists() for f in PY_FILES)
+    for f in PY_FILES:
+        dst = dst_root / f
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copyfile(REF / f, dst)
+    return True
+
+
 def reference_available() -> bool:
     return (PB / "sampling_gpu.cu").exists() and (IOU / "iou3d_nms_kernel.cu").exists()
 
@@ -64,6 +92,8 @@ def build(force: bool = False) -> bool:
     """Returns True when oracle/_ref holds both libraries (built now or before)."""
     lib_pn = OUT / "libpdanet_ref_pointnet2.so"
     lib_iou = OUT / "iou3d_nms_cuda.so"
+    OUT.mkdir(exist_ok=True)
+    stage_python()
     if lib_pn.exists() and lib_iou.exists() and not force:
         return True
     if not reference_available():

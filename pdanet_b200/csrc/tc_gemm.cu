@@ -185,6 +185,10 @@ __device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap *map, int
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// the same box pulled into L2 only (no shared memory, no barrier): hides DRAM latency behind a short smem ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -387,11 +391,14 @@ __device__ __forceinline__ float tf32_rna(float v) {
 // warpgroups shrink to kEpiRegs (128 * 2 * 152 + 128 * 2 * 104 = 65536).
 constexpr int kProdRegs = 152, kEpiRegs = 104;
 __host__ __device__ constexpr bool epi_has_res(int epi) { return epi == 2 || epi == 3; }   // E_ADD_LN, E_ADD_MAXPOOL
-template <int EPI, int CG>
+template <int EPI, int CG, int ALOAD = A_ROWS>
 struct EpiWarps {
-    // (tried for the residual + max-pool epilogues too: slower — they wait for residual tiles, not for issue slots, and
-    // 104 registers leave one tile in flight per warp instead of two)
-    static constexpr int value = (CG == 2 && EPI == 5) ? 8 : 4;
+    // (tried for the residual + max-pool epilogues of the producer-fed modes too: slower — they wait for residual tiles, not
+    // for issue slots, and 104 registers leave one tile in flight per warp instead of two.)
+    // A_TMA has no producer warps and its residual comes from shared memory: the epilogue is then a dependent chain of
+    // TMEM load -> arithmetic -> store per 32-column block with ONE warp per scheduler and nothing to hide its latency
+    // behind (measured: 14 k cycles per 128 x 256 tile against 1 k cycles of MMAs), so it always runs two warps per quadrant.
+    static constexpr int value = (ALOAD == A_TMA || (CG == 2 && EPI == 5)) ? 8 : 4;
 };
 
 // RES: the epilogue adds a residual (E_ADD_LN, E_ADD_MAXPOOL).  With the TMA-fed fp16 mode (A_TMA) the residual is staged
@@ -410,7 +417,9 @@ struct Cfg {
     static constexpr int RES_BYTES = RES_TMA ? kResStages * kResStageBytes : 0;
     // BN = 192 is the attention epilogue (one head of [Q | K | V], head_dim 64, per chunk): + a V staging tile per warp
     static constexpr int ATTN_BYTES = BN == 192 ? 4 * 32 * kAttnVP * 4 : 0;
-    static constexpr int MISC_BYTES = 1024 /*align slack*/ + kBarBytes + 4 * 512 * 4 /*per-warp bias*/ + 2 * 512 * 4 /*gamma, beta*/;
+    static constexpr int BIAS_BYTES = EW * 512 * 4;     // per-warp bias staging (an item has at most 512 columns)
+    static constexpr int MISC_BYTES = 1024 /*align slack*/ + kBarBytes + BIAS_BYTES + 2 * 512 * 4 /*gamma, beta*/ +
+                                      2 * 256 * 4 /*LayerNorm partial sums of the two warps of a quadrant*/;
     // rings get 200 KB (A_TMA: minus the residual ring and the attention tile, which the producer-fed modes fit on top)
     static constexpr int STAGES_RAW = ALOAD == A_TMA ? (200 * 1024 - ATTN_BYTES - RES_BYTES) / STAGE_BYTES
                                                      : (200 * 1024) / STAGE_BYTES;
@@ -450,9 +459,9 @@ struct Pipe {
 };
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
-__global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, ALOAD, epi_has_res(EPI)>::THREADS, 1)
+__global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::value, ALOAD, epi_has_res(EPI)>::THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, ALOAD, epi_has_res(EPI)>;
+    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::value, ALOAD, epi_has_res(EPI)>;
     static_assert(ALOAD != A_TMA || NPASS == 4, "the TMA-fed A operand is the fp16 single-pass mode");
     constexpr int EW = C::EPI_WARPS;
     constexpr int S = C::STAGES;
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
     if (CG == 2) cluster_sync_all();  // both CTAs of the pair resident, barriers initialised before any remote arrive
     if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
     if (EPI == E_ADD_LN) {  // LayerNorm scale / shift -> smem once (Nout = NCH * BN <= 512 columns)
-        float *sg = reinterpret_cast<float *>(smem + C::PARAM_OFF) + 4 * 512;
+        float *sg = reinterpret_cast<float *>(smem + C::PARAM_OFF) + EW * 512;
         for (int i = threadIdx.x; i < NCH * BN; i += kThreads) {
             sg[i] = __ldg(p.gamma + i);
             sg[512 + i] = __ldg(p.beta + i);
@@ -660,9 +669,22 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                 tma_prefetch_desc(&p.tmRh);
                 tma_prefetch_desc(&p.tmRl);
                 Pipe rp;
+                // The ring holds kResStages 64-column blocks; the rest of an item's residual slab (and the next item's) is pulled
+                // into L2 ahead of time, so a ring refill costs an L2 round trip, not a DRAM one.
+                auto prefetch_item = [&](long long item) {
+                    if (item >= n_items) return;
+                    const int r0 = (int)row0_of(item), c0 = (int)(item % p.n_groups) * NCH * BN;
+                    if (r0 >= p.T) return;
+                    for (int cb = 0; cb < NCH * BN / 64; cb++) {
+                        tma_prefetch_2d(&p.tmRh, c0 + 64 * cb, r0);
+                        tma_prefetch_2d(&p.tmRl, c0 + 64 * cb, r0);
+                    }
+                };
+                prefetch_item(item0);
                 for (long long item = item0; item < n_items; item += item_step) {
                     const int rrow0 = (int)row0_of(item);
                     const int col0 = (int)(item % p.n_groups) * NCH * BN;
+                    prefetch_item(item + item_step);
                     for (int cb = 0; cb < NCH * BN / 64; cb++) {
                         mbar_wait(r_empty(rp.stage), rp.phase ^ 1);
                         mbar_arrive_expect_tx(r_full(rp.stage), (u32)kResStageBytes);
@@ -800,9 +822,10 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
         const int fr = lane >> 2, fc = (lane & 3) * 2;
         // Per-column parameters live in shared memory: with ~200 KB of it carved out the L1 is a few KB and thrashed by
         // the A stream, so an __ldg of bias / gamma / beta inside the block loop was an L2 round trip on the critical path.
-        float *sbias = reinterpret_cast<float *>(smem + C::PARAM_OFF) + ew * (2048 / EW);
-        const float *sgamma = reinterpret_cast<const float *>(smem + C::PARAM_OFF) + 4 * 512;
+        float *sbias = reinterpret_cast<float *>(smem + C::PARAM_OFF) + ew * 512;
+        const float *sgamma = reinterpret_cast<const float *>(smem + C::PARAM_OFF) + EW * 512;
         const float *sbeta = sgamma + 512;
+        float *sstat = const_cast<float *>(sbeta) + 512;   // [2 exchanges][4 quadrants][2 halves][32 rows]
         int as = 0;
         u32 aphase = 0;
 
@@ -910,7 +933,9 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
         // its TMA, the second half's read releases the stage to the loader warp.
         Pipe rp;
         auto add_res_smem = [&](float (&v)[2][16], int sub) {
-            if (sub == 0) mbar_wait(r_full(rp.stage), rp.phase);
+            // one warp per quadrant walks both halves of a box; with two warps per quadrant each owns one half
+            constexpr bool kBothHalves = EW == 4;
+            if (!kBothHalves || sub == 0) mbar_wait(r_full(rp.stage), rp.phase);
             const uint8_t *rs = smem + C::RING_BYTES + (size_t)rp.stage * kResStageBytes + (size_t)(q * 32) * 128;
 #pragma unroll
             for (int h = 0; h < 2; h++)
@@ -926,7 +951,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                         v[h][k * 4 + j * 2 + 1] += a.y + b.y;
                     }
                 }
-            if (sub == 1) {
+            if (!kBothHalves || sub == 1) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(r_empty(rp.stage));
                 rp.advance<kResStages>();
@@ -1024,7 +1049,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
 
             if (EPI == E_STORE || EPI == E_RELU) {
                 for (int c = 0; c < NCH; c++) {
-                    for (int j = 0; j < BN; j += 32) {
+                    for (int j = 32 * half; j < BN; j += 32 * NW) {
                         const int n0 = (n_group * NCH + c) * BN + j;
                         if (n0 >= p.Nout) break;
                         float v[2][16];
@@ -1083,6 +1108,26 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                 // (Software-pipelining the passes over two fragment buffers — TMEM load of block b + 1 in flight while
                 // block b is processed — was measured slower: the extra 32 registers spill.)
                 constexpr int E = NCH * BN;
+                // NW = 2: the two warps of a quadrant take alternate 32-column blocks (= the two halves of a staged residual
+                // box) and add up their partial row statistics through shared memory (one named barrier per exchange).
+                auto exchange = [&](float (&part)[4], int slot) {   // quad-reduced partials of rows (h, j) -> totals
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1);
+                        part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2);
+                    }
+                    if (NW == 2) {
+                        float *mine = sstat + ((slot * 4 + q) * 2 + half) * 32;
+                        const float *other = sstat + ((slot * 4 + q) * 2 + (half ^ 1)) * 32;
+                        if ((lane & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) mine[16 * (i >> 1) + 8 * (i & 1) + fr] = part[i];
+                        }
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+                        for (int i = 0; i < 4; i++) part[i] += other[16 * (i >> 1) + 8 * (i & 1) + fr];
+                    }
+                };
                 float sum[4] = {0.f, 0.f, 0.f, 0.f};
                 auto block = [&](int j0, float2 (&r)[2][8]) {
                     float v[2][16];
@@ -1091,7 +1136,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                     if (res_tma) {
                         add_res_smem(v, (j0 >> 5) & 1);
                     } else {
-                        add_tile(v, r);  // r is dead now: refill it with the tile two blocks ahead
+                        add_tile(v, r);  // r is dead now: refill it with this warp's next tile
                         if (j0 + 64 < E) issue_tile(r, p.R, p.ldr, wrow0, p.T, j0 + 64);
                     }
 #pragma unroll
@@ -1107,18 +1152,18 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                         mbar_wait(acc_full(j0 / BN), aphase);
                         tc_fence_after();
                     }
-                    block(j0, ra);
-                    block(j0 + 32, rb);
+                    if (NW == 1) {
+                        block(j0, ra);
+                        block(j0 + 32, rb);
+                    } else {
+                        block(j0 + 32 * half, ra);
+                    }
                 }
+                exchange(sum, 0);
                 float mean[4], rstd[4], sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float t = sum[i];
-                    t += __shfl_xor_sync(0xffffffffu, t, 1);
-                    t += __shfl_xor_sync(0xffffffffu, t, 2);
-                    mean[i] = t * (1.0f / E);
-                }
-                for (int j0 = 0; j0 < E; j0 += 32) {
+                for (int i = 0; i < 4; i++) mean[i] = sum[i] * (1.0f / E);
+                for (int j0 = 32 * half; j0 < E; j0 += 32 * NW) {
                     float v[2][16];
                     frag_ld(tacc + j0, v);
 #pragma unroll
@@ -1133,14 +1178,10 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                                     sq[h * 2 + j] = fmaf(d, d, sq[h * 2 + j]);
                                 }
                 }
+                exchange(sq, 1);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float t = sq[i];
-                    t += __shfl_xor_sync(0xffffffffu, t, 1);
-                    t += __shfl_xor_sync(0xffffffffu, t, 2);
-                    rstd[i] = rsqrtf(t * (1.0f / E) + p.eps);
-                }
-                for (int j0 = 0; j0 < E; j0 += 32) {
+                for (int i = 0; i < 4; i++) rstd[i] = rsqrtf(sq[i] * (1.0f / E) + p.eps);
+                for (int j0 = 32 * half; j0 < E; j0 += 32 * NW) {
                     float v[2][16];
                     frag_ld(tacc + j0, v);
 #pragma unroll
@@ -1157,7 +1198,8 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                             }
                     }
                     store_tile(v, p.out, p.ldo, wrow0, p.T, j0);
-                    if (CHUNKED && (j0 + 32) % BN == 0) {   // last block of a chunk: hand the chunk back to the MMA warp
+                    // this warp's last block of a chunk: hand the chunk back to the MMA warp (acc_empty counts every warp)
+                    if (CHUNKED && (j0 + 32 * NW) % BN == 32 * half) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -1185,7 +1227,7 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, A
                 const int mt0 = EW == 8 ? (ew >> 2) : 0;         // first m-tile of this warp
                 const int ns = p.ns;
                 const int g = fr, t2 = fc;  // fragment coordinates: row g, column pair t2 = 2 (lane % 4)
-                float *sV = reinterpret_cast<float *>(smem + C::PARAM_OFF) + 4 * 512 + 2 * 512 + q * 32 * kAttnVP;
+                float *sV = reinterpret_cast<float *>(smem + C::PARAM_OFF) + EW * 512 + 2 * 512 + 2 * 256 + q * 32 * kAttnVP;
                 auto split = [](float x, u32 &hi, u32 &lo) {
                     hi = __float_as_uint(x) & 0xffffe000u;
                     lo = __float_as_uint(x - __uint_as_float(hi));
@@ -1548,7 +1590,7 @@ int persistent_ctas() {
 
 template <int NPASS, int BN, int NCH, int ALOAD, int EPI, int CG>
 int launch_cg(GemmParams p, cudaStream_t s) {
-    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG>::value, ALOAD>;
+    using C = Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::value, ALOAD>;
     auto kern = tc_gemm_kernel<NPASS, BN, NCH, ALOAD, EPI, CG>;
     // per device and cheap: set on every launch (a cached flag would skip the second GPU of a process)
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

@@ -57,11 +57,16 @@ class PDAScalePlan:
         self.radius = mod.groupers[i].radius
         self.ns = mod.nsamples[i]
         pm, gm, fc = mod.position_mlp[i], mod.global_mlps[i], mod.fin_conv[i]
-        self.position = [PackedLinear(*_fold(pm[0], pm[1]), npass=npass), PackedLinear(*_fold(pm[3], pm[4]), npass=npass)]
+        # npass = 4 (fp16 single pass) is for the transformer, whose residual streams stay at fp32 level.  The small direct
+        # layers around it (position MLP on the unfused path, the two fin_conv layers on B*M pooled rows: < 1 % of the
+        # block's FLOPs) have no residual to lean on: their operands would be rounded to 11 bits with nothing to hide it
+        # (measured 5e-4 on the scale's output), so they keep the split-bf16 products (1e-5).
+        small = 2 if npass == 4 else npass
+        self.position = [PackedLinear(*_fold(pm[0], pm[1]), npass=small), PackedLinear(*_fold(pm[3], pm[4]), npass=small)]
         self.global_ = [LinearExact(*_fold(gm[0], gm[1])), LinearExact(*_fold(gm[3], gm[4]))]
         dn = mod.point_density[i].densitynet
         self.density = [LinearExact(*_fold(c, b)) for c, b in zip(dn.mlp_convs, dn.mlp_bns)]
-        self.fin = [PackedLinear(*_fold(fc[0], fc[1]), npass=npass), PackedLinear(*_fold(fc[3], fc[4]), npass=npass)]
+        self.fin = [PackedLinear(*_fold(fc[0], fc[1]), npass=small), PackedLinear(*_fold(fc[3], fc[4]), npass=small)]
         tf = mod.Local_pointformer[i]
         attn = tf.self_attn
         self.heads = attn.num_heads

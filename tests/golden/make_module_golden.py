@@ -12,7 +12,7 @@ It then
      tests/golden/ref_backbone_kitti.npz (indices exact, feature tensors strided).
 tests/test_host_cpu.py::test_backbone_matches_reference_modules_golden replays it on our modules.
 
-    python tests/golden/make_module_golden.py
+    python tests/golden/make_module_golden.py [kitti|once]      (once: one 65536-point scene, tests/golden/ref_backbone_once.npz)
 """
 import importlib
 import sys
@@ -76,14 +76,16 @@ def forced_topk_ops(picks):
     return ns
 
 
-def main():
+def main(name="kitti"):
     _, _, ref_backbone_mod = import_reference()
-    cfg = load_config("kitti")
+    cfg = load_config(name)
+    num_class = len(cfg.CLASS_NAMES)
+    B, N = (2, 16384) if name == "kitti" else (1, 65536)     # BASELINE.json configs[1] / configs[2] point counts
     torch.manual_seed(0)
-    ref = ref_backbone_mod.IASSD_Backbone(cfg.MODEL.BACKBONE_3D, num_class=3, input_channels=4).eval()
-    cfg2 = load_config("kitti")  # the reference mutates mlp specs in place (mlp_spec[0] += 3), use a fresh cfg
+    ref = ref_backbone_mod.IASSD_Backbone(cfg.MODEL.BACKBONE_3D, num_class=num_class, input_channels=4).eval()
+    cfg2 = load_config(name)  # the reference mutates mlp specs in place (mlp_spec[0] += 3), use a fresh cfg
     torch.manual_seed(0)
-    ours = IASSD_Backbone(cfg2.MODEL.BACKBONE_3D, num_class=3, input_channels=4, ops=torch_ops).eval()
+    ours = IASSD_Backbone(cfg2.MODEL.BACKBONE_3D, num_class=num_class, input_channels=4, ops=torch_ops).eval()
 
     sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
     assert list(sd_ref.keys()) == list(sd_ours.keys()), "state_dict keys / order differ from the reference"
@@ -91,16 +93,16 @@ def main():
         assert torch.equal(sd_ref[k], sd_ours[k]), f"seeded init differs at {k}"
     print(f"state_dict identical: {len(sd_ref)} tensors, {sum(v.numel() for v in sd_ref.values())} values")
 
-    batch = make_batch(2, 16384, cfg.POINT_CLOUD_RANGE, duplicate_frac=0.02)
+    batch = make_batch(B, N, cfg.POINT_CLOUD_RANGE, duplicate_frac=0.02)
     with torch.no_grad():
-        out = ref({"batch_size": 2, "points": batch["points"].clone()})
+        out = ref({"batch_size": B, "points": batch["points"].clone()})
         # torch.topk leaves the order of tied scores unspecified (and the fp32 sigmoid merges distinct logits), so the
         # class-aware layers are replayed with the reference's own picks; everything else must then agree exactly.
         ours.ops = forced_topk_ops([out["sample_list_id"][2], out["sample_list_id"][3]])
         for mod in ours.SA_modules:
             if hasattr(mod, "ops"):
                 mod.ops = ours.ops
-        mine = ours({"batch_size": 2, "points": batch["points"].clone()})
+        mine = ours({"batch_size": B, "points": batch["points"].clone()})
     for lvl, idx in ((2, out["sample_list_id"][2]), (3, out["sample_list_id"][3])):
         cls = out["sa_ins_preds"][lvl - 1][..., 1:]
         score = torch.sigmoid(cls.max(-1)[0])
@@ -123,7 +125,7 @@ def main():
         check(a, b, f"encoder_features[{i}]")
     print("our backbone reproduces the reference backbone on this input")
 
-    fx = {"seed": np.int64(0), "batch": np.int64(2), "npoints": np.int64(16384), "duplicate_frac": np.float64(0.02),
+    fx = {"seed": np.int64(0), "batch": np.int64(B), "npoints": np.int64(N), "duplicate_frac": np.float64(0.02),
           "centers": out["centers"].numpy(), "centers_origin": out["centers_origin"].numpy(),
           "ctr_offsets": out["ctr_offsets"].numpy(),
           "centers_features_strided": out["centers_features"][::4, ::8].contiguous().numpy(),
@@ -134,9 +136,10 @@ def main():
     for i in (1, 2, 3):
         f = out["encoder_features"][i]
         fx[f"features_L{i - 1}_strided"] = f[:, ::4, ::16].contiguous().numpy()
-    np.savez_compressed(ROOT / "tests/golden/ref_backbone_kitti.npz", **fx)
-    print("wrote tests/golden/ref_backbone_kitti.npz", (ROOT / "tests/golden/ref_backbone_kitti.npz").stat().st_size, "bytes")
+    path = ROOT / f"tests/golden/ref_backbone_{name}.npz"
+    np.savez_compressed(path, **fx)
+    print("wrote", path, path.stat().st_size, "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "kitti")

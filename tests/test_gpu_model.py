@@ -139,16 +139,29 @@ def test_scene_sharding_is_a_pure_partition(models):
             assert len(gpu({"batch_size": len(ids), "points": sub.reshape(-1, 5)})[0]) == len(ids)
 
 
-def test_cuda_backbone_matches_reference_modules_golden():
-    """The CUDA path (fused kernels included) against outputs of the REFERENCE's own Python modules."""
+@pytest.mark.parametrize("name", ["kitti", "once"])
+def test_cuda_backbone_matches_reference_modules_golden(name):
+    """The CUDA path (fused kernels included) against outputs of the REFERENCE's own Python modules; once = one
+    65536-point scene: clustered FPS 65536 -> 16384, cell-list L0, three wide L5 scales (nsample 16 / 32 / 64)."""
     from test_host_cpu import replay_reference_backbone_golden
     from pdanet_b200 import pointnet2_utils
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    replay_reference_backbone_golden(pointnet2_utils, "cuda", rtol=RTOL)
+    replay_reference_backbone_golden(pointnet2_utils, "cuda", rtol=RTOL, name=name)
 
 
-@pytest.mark.parametrize("tc_passes,tol", [(2, 1e-4), (4, 6e-4)])
+@pytest.mark.parametrize("name", ["kitti", "once"])
+def test_cuda_head_and_post_processing_match_reference_golden(name):
+    """The CUDA path's head, box decode and all three post-processing flavours (`post_processing`, `_batched`, `_padded`:
+    batched on-device NMS) against outputs of the REFERENCE's own IASSD_Head / decode_torch / post_processing /
+    class_agnostic_nms (tests/golden/make_head_golden.py)."""
+    from test_host_cpu import replay_reference_head_golden
+    from pdanet_b200 import iou3d_nms_utils, pointnet2_utils
+    torch.backends.cuda.matmul.allow_tf32 = False
+    replay_reference_head_golden(name, pointnet2_utils, iou3d_nms_utils, "cuda", rtol=1e-4)
+
+
+@pytest.mark.parametrize("tc_passes,tol", [(2, 1e-4), (4, 3e-4)])
 def test_pda_fast_path_equals_reference_statement_order(models, tc_passes, tol):
     """pda_block.py (token-major, folded BN, tensor-core projections) vs the module's reference-order forward (fp32 torch),
     same inputs.  tc_passes = 2: split-bf16 products; 4: fp16 single pass with fp16 activations between the kernels and
@@ -172,6 +185,27 @@ def test_pda_fast_path_equals_reference_statement_order(models, tc_passes, tol):
         scale = slow[1].abs().max().item()
         assert (fast[1] - slow[1]).abs().max().item() <= tol * scale
         assert (fast[2] - slow[2]).abs().max().item() <= tol * slow[2].abs().max().item()
+
+
+@pytest.mark.parametrize("name,B,N", [("kitti", 2, 16384), ("once", 1, 65536)])
+def test_no_scale_falls_back_to_the_unfused_grouper(name, B, N):
+    """Eval forward of BOTH yamls at their BASELINE point counts: every SA scale — the narrow L0 pair, the PDA scales and
+    all wide L5 scales, including ONCE's third one (r = 12.8, nsample 64) — runs on a fused kernel; none reaches
+    `groupers[i]` + eager convolutions (tools/cfgs/once_models/PDA-SSD.yaml:26-50, PB/pointnet2_modules.py:1655-1672)."""
+    cfg = load_config(name)
+    torch.manual_seed(0)
+    model = build_model(cfg).cuda().eval()
+    hit = []
+    for li, mod in enumerate(model.backbone_3d.SA_modules):
+        for gi, grouper in enumerate(getattr(mod, "groupers", [])):
+            grouper.register_forward_pre_hook(lambda m, a, li=li, gi=gi: hit.append((li, gi)))
+    batch = make_batch(B, N, cfg.POINT_CLOUD_RANGE)
+    with torch.no_grad():
+        preds, _ = model({"batch_size": B, "points": batch["points"].cuda()})
+    assert not hit, f"scales that fell back to the unfused grouper (layer, scale): {hit}"
+    assert len(preds) == B and all(torch.isfinite(p["pred_boxes"]).all() for p in preds)
+    wide = model.backbone_3d.SA_modules[5]
+    assert len(wide._wide) == len(wide.groupers) == (2 if name == "kitti" else 3)
 
 
 def test_pda_group_tokens_matches_channel_major_grouper():

@@ -105,18 +105,18 @@ def _forced_ops(base, picks):
     return ns
 
 
-def replay_reference_backbone_golden(ops_base, device, rtol):
-    """Our backbone vs tests/golden/ref_backbone_kitti.npz — outputs of the REFERENCE's own IASSD_Backbone /
+def replay_reference_backbone_golden(ops_base, device, rtol, name="kitti"):
+    """Our backbone vs tests/golden/ref_backbone_<name>.npz — outputs of the REFERENCE's own IASSD_Backbone /
     pointnet2_modules.py run over the oracle ops (tests/golden/make_module_golden.py).  Weights come from the same
     seed (the generator asserts the seeded state_dicts are identical); the class-aware layers replay the reference's
     picks because torch.topk's tie order is unspecified."""
     import numpy as np
     from conftest import GOLDEN
     from pdanet_b200.iassd_backbone import IASSD_Backbone
-    z = np.load(GOLDEN / "ref_backbone_kitti.npz")
-    cfg = load_config("kitti")
+    z = np.load(GOLDEN / f"ref_backbone_{name}.npz")
+    cfg = load_config(name)
     torch.manual_seed(int(z["seed"]))
-    bb = IASSD_Backbone(cfg.MODEL.BACKBONE_3D, num_class=3, input_channels=4, ops=ops_base).eval().to(device)
+    bb = IASSD_Backbone(cfg.MODEL.BACKBONE_3D, num_class=len(cfg.CLASS_NAMES), input_channels=4, ops=ops_base).eval().to(device)
     forced = _forced_ops(ops_base, [torch.from_numpy(z["sample_idx_L2"]), torch.from_numpy(z["sample_idx_L3"])])
     for mod in bb.SA_modules:
         if hasattr(mod, "ops"):
@@ -142,8 +142,10 @@ def replay_reference_backbone_golden(ops_base, device, rtol):
         close(out["encoder_features"][lvl + 1][:, ::4, ::16], z[f"features_L{lvl}_strided"], f"features L{lvl}")
 
 
-def test_backbone_matches_reference_modules_golden():
-    replay_reference_backbone_golden(torch_ops, "cpu", rtol=1e-5)
+@pytest.mark.parametrize("name", ["kitti", "once"])
+def test_backbone_matches_reference_modules_golden(name):
+    """kitti: two 16384-point scenes; once: one 65536-point scene (three wide L5 scales, nsample 64 among them)."""
+    replay_reference_backbone_golden(torch_ops, "cpu", rtol=1e-5, name=name)
 
 
 def test_derived_weight_caches_die_with_the_weights():
@@ -183,3 +185,64 @@ def test_derived_weight_caches_die_with_the_weights():
     model.train()
     assert plain._folded is None and pda._plans == {}
     model.eval()
+
+
+def replay_reference_head_golden(name, ops, nms_utils, device, rtol=1e-5):
+    """Head + box decode + post-processing vs tests/golden/ref_head_<name>.npz — outputs of the REFERENCE's own
+    `IASSD_Head`, `PointResidual_BinOri_Coder.decode_torch`, `Detector3DTemplate.post_processing` and
+    `class_agnostic_nms` (tests/golden/make_head_golden.py imports them unchanged).  The head runs on its seeded inputs;
+    every post-processing flavour then runs on the GOLDEN head outputs, so the NMS decisions are made on identical
+    numbers and the kept sets must agree exactly."""
+    import numpy as np
+    from conftest import GOLDEN
+    from util import head_golden_inputs, seeded_head_model
+    z = np.load(GOLDEN / f"ref_head_{name}.npz")
+    cfg = load_config(name)
+    model = seeded_head_model(cfg, ops=ops, nms_utils=nms_utils).to(device)
+    batch = head_golden_inputs(cfg, name, model.backbone_3d.num_point_features)
+    batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    B = batch["batch_size"]
+    with torch.no_grad():
+        out = model.point_head(dict(batch))
+
+    def close(got, want, what):
+        got, want = got.detach().cpu(), torch.from_numpy(want)
+        err = (got - want).abs().max().item()
+        assert err <= rtol * (want.abs().max().item() + 1e-12), f"{what}: {err:.3e}"
+
+    close(out["batch_cls_preds"], z["batch_cls_preds"], "head class logits")
+    close(out["batch_box_preds"], z["batch_box_preds"], "decoded boxes")
+
+    feed = dict(out)
+    feed["batch_cls_preds"] = torch.from_numpy(z["batch_cls_preds"]).to(device)
+    feed["batch_box_preds"] = torch.from_numpy(z["batch_box_preds"]).to(device)
+    flavours = [("post_processing", lambda d: model.post_processing(d)[0])]
+    if hasattr(model.nms_utils, "nms_batched"):
+        flavours.append(("post_processing_batched", lambda d: model.post_processing_batched(d)[0]))
+        flavours.append(("post_processing_padded", lambda d: model.unpack_padded(
+            {k: v.cpu() for k, v in model.post_processing_padded(d).items()})))
+    def table(boxes, scores, labels):
+        """(n, 9) rows [box(7), score, label] in a canonical order (scores tie massively: order by the box itself)."""
+        t = torch.cat([torch.as_tensor(boxes, dtype=torch.float64).reshape(-1, 7),
+                       torch.as_tensor(scores, dtype=torch.float64).reshape(-1, 1),
+                       torch.as_tensor(labels, dtype=torch.float64).reshape(-1, 1)], dim=1)
+        order = sorted(range(t.shape[0]), key=lambda i: tuple(round(x, 3) for x in t[i, :7].tolist()))
+        return t[order]
+
+    for what, fn in flavours:
+        with torch.no_grad():
+            preds = fn(dict(feed))
+        assert len(preds) == B
+        for s in range(B):
+            got = table(preds[s]["pred_boxes"].cpu(), preds[s]["pred_scores"].cpu(), preds[s]["pred_labels"].cpu())
+            want = table(z[f"pred_boxes_{s}"], z[f"pred_scores_{s}"], z[f"pred_labels_{s}"])
+            assert got.shape == want.shape, f"{what}, scene {s}: {got.shape[0]} detections kept, the reference keeps {want.shape[0]}"
+            # same boxes and labels (inputs are identical), scores to an ulp of the sigmoid (libm vs libdevice)
+            assert torch.equal(got[:, 8], want[:, 8]), f"{what}, scene {s}: labels differ"
+            assert torch.allclose(got[:, :7], want[:, :7], rtol=0, atol=1e-6), f"{what}, scene {s}: kept boxes differ"
+            assert torch.allclose(got[:, 7], want[:, 7], rtol=1e-6, atol=1e-7), f"{what}, scene {s}: scores differ"
+
+
+@pytest.mark.parametrize("name", ["kitti", "once"])
+def test_head_and_post_processing_match_reference_golden(name):
+    replay_reference_head_golden(name, torch_ops, torch_ops.nms_utils, "cpu")

@@ -43,3 +43,42 @@ def adversarial_boxes(seed, n):
     b[6 * q:7 * q] = b[:q]
     b[6 * q:7 * q, 0] += 1e-4 * torch.randn(q, generator=g)  # almost-duplicates
     return b.contiguous()
+
+
+def seeded_head_model(cfg, ops=None, nms_utils=None, **kw):
+    """The detector whose HEAD parameters the head golden was made with: model under manual_seed(0), then the head
+    re-initialised under manual_seed(1) in the reference's construction order, BatchNorm statistics randomised from
+    generator seed 3 (tests/golden/make_head_golden.py checks that the reference head built the same way is identical)."""
+    from oracle import torch_ops
+    from pdanet_b200.iassd import build_model
+    from pdanet_b200.iassd_head import IASSD_Head
+    torch.manual_seed(0)
+    model = build_model(cfg, ops=ops if ops is not None else torch_ops,
+                        nms_utils=nms_utils if nms_utils is not None else torch_ops.nms_utils, **kw).eval()
+    torch.manual_seed(1)
+    model.point_head = IASSD_Head(num_class=len(cfg.CLASS_NAMES), input_channels=model.backbone_3d.num_point_features,
+                                  model_cfg=cfg.MODEL.POINT_HEAD).eval()
+    model.module_list = [model.backbone_3d, model.point_head]
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for k, v in model.point_head.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            elif k.endswith("running_var"):
+                v.copy_(0.5 + torch.rand(v.shape, generator=g))
+    return model
+
+
+def head_golden_inputs(cfg, name, in_dim):
+    """Seeded head inputs of the head golden: post-ReLU centre features and clustered centres inside the range."""
+    g = torch.Generator().manual_seed(4)
+    B = 3
+    M = 256 if name == "kitti" else 1024
+    lo, hi = torch.tensor(cfg.POINT_CLOUD_RANGE[:3]), torch.tensor(cfg.POINT_CLOUD_RANGE[3:])
+    feats = torch.relu(torch.randn(B * M, in_dim, generator=g))
+    xyz = lo + (hi - lo) * torch.rand(B * M, 3, generator=g)
+    xyz[1::2] = xyz[0::2] + 0.5 * torch.randn(B * M // 2, 3, generator=g)   # neighbours: NMS has work to do
+    bidx = torch.arange(B).repeat_interleave(M).float()
+    centers = torch.cat([bidx[:, None], xyz], dim=1)
+    return {"batch_size": B, "centers_features": feats, "centers": centers, "ctr_offsets": centers.clone(),
+            "centers_origin": centers.clone(), "sa_ins_preds": [], "sample_list_id": []}
