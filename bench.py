@@ -34,8 +34,8 @@ UNIT = "scenes/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200, help="timed steps (default: ~1.2 s of device time per leg)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pdab", choices=["pdab", "reference"])
     ap.add_argument("--config", default="kitti", choices=["kitti", "once"])
     ap.add_argument("--batch", type=int, default=None, help="scenes per GPU per step (default 16 kitti / 4 once)")
@@ -110,18 +110,37 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------- CPU arm
 
-def cpu_model(cfg):
-    from oracle import torch_ops
+def cpu_model(cfg, name):
+    """The CPU arm's model.  Backbone (98 % of the FLOPs, every native op): the REFERENCE's own `IASSD_Backbone` and SA / PDA /
+    vote modules, imported unchanged from the copies oracle/build_ref.py stages under oracle/_ref/pyref
+    (oracle/ref_python.py), over the CPU oracle's C restatement of FPS / ball query / group / gather.  Head, decode and
+    post-processing: our mirror (pinned to the reference's by tests/golden/ref_head_*.npz) over the oracle NMS.  Without the
+    staged files the backbone is our mirror as well.  Returns (model, what)."""
+    from oracle import ref_python, torch_ops
+    from pdanet_b200.config import load_config
     from pdanet_b200.iassd import build_model
     torch.manual_seed(0)
-    return build_model(cfg, ops=torch_ops, nms_utils=torch_ops.nms_utils, batched_post_processing=False).eval()
+    model = build_model(cfg, ops=torch_ops, nms_utils=torch_ops.nms_utils, batched_post_processing=False).eval()
+    what = "oracle port (C ops + our module mirror on torch CPU)"
+    if ref_python.reference_root() is not None:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _, _, bb_mod = ref_python.import_reference()
+        fresh = load_config(name)   # the reference's constructor edits the mlp specs in place
+        ref_bb = bb_mod.IASSD_Backbone(fresh.MODEL.BACKBONE_3D, num_class=len(cfg.CLASS_NAMES),
+                                       input_channels=cfg.get("NUM_POINT_FEATURES", 4)).eval()
+        ref_bb.load_state_dict(model.backbone_3d.state_dict())
+        model.backbone_3d = ref_bb
+        model.module_list = [model.backbone_3d, model.point_head]
+        what = "the reference's own IASSD_Backbone / SA / PDA / vote modules (oracle/_ref/pyref) over the C oracle ops"
+    return model, what
 
 
-def time_cpu(cfg, n_points, scenes, warmup=1):
-    """The oracle port of the path (C restatement of FPS / ball query / group / NMS + the same module code on
-    torch CPU) on the host cores: `scenes` single-scene batches, returns (scenes/s, threads, per-scene seconds)."""
+def time_cpu(cfg, n_points, scenes, warmup=1, name="kitti"):
+    """The CPU arm on the host cores: `scenes` single-scene batches; returns (scenes/s, threads, per-scene seconds, what ran)."""
     from pdanet_b200.synthetic import make_batch
-    model = cpu_model(cfg)
+    model, what = cpu_model(cfg, name)
     torch.set_num_threads(os.cpu_count() or 1)
     times = []
     with torch.no_grad():
@@ -131,16 +150,17 @@ def time_cpu(cfg, n_points, scenes, warmup=1):
             model(batch)
             if s >= warmup:
                 times.append(time.perf_counter() - t0)
-    return len(times) / sum(times), torch.get_num_threads(), times
+    return len(times) / sum(times), torch.get_num_threads(), times, what
 
 
 def run_reference_arm(args, cfg, n_points, batch):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    per_step = max(1, min(2, batch))  # bounded sample: scenes per step
-    sps, threads, times = time_cpu(cfg, n_points, scenes=per_step * args.steps, warmup=max(1, args.warmup))
-    sample = f"{per_step} scene(s)/step x {args.steps} steps, one {n_points}-point scene per forward, batch 1"
+    per_step = 1 if args.steps > 20 else max(1, min(2, batch))  # bounded sample: scenes per step (~0.7 s of CPU work each)
+    sps, threads, times, what = time_cpu(cfg, n_points, scenes=per_step * args.steps, warmup=max(1, args.warmup),
+                                         name=args.config)
+    sample = f"{per_step} scene(s)/step x {args.steps} steps, one {n_points}-point scene per forward, batch 1; {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True,
@@ -221,6 +241,14 @@ def algorithmic_bytes(key: str, batch: int):
         return s * (28 * stride + 8 * stride * ((stride + 63) // 64) + 8 * stride)
     return None
 
+
+# C-ABI entry point -> the kernel it launches (launches are judged per kernel: the tcgen05 GEMM runs ~30 times per step at
+# different shapes / prologues / epilogues and is ONE kernel template)
+KERNEL_OF = {"pdab_tc_linear": "tc_gemm_kernel", "pdab_tc_linear_h": "tc_gemm_kernel", "pdab_tc_sa_gather_linear": "tc_gemm_kernel",
+             "pdab_tc_sa_gather_linear_h": "tc_gemm_kernel", "pdab_fps": "fps_kernel", "pdab_fps_with_dist": "fps_kernel",
+             "pdab_pda_encode_ln": "pda_encode_ln_kernel", "pdab_pda_encode_ln_h": "pda_encode_ln_kernel",
+             "pdab_group_attention": "group_attention_kernel", "pdab_group_attention_h": "group_attention_kernel",
+             "pdab_sa_fused_pair": "sa_fused_pair_kernel"}
 
 # tensor-pipe work per algorithmic flop, in bf16-MMA flops: split-bf16 ("bf16x3") issues 3 bf16 MMAs per product, 3xTF32
 # issues 3 TF32 MMAs (a TF32 MMA occupies the pipe like 2 bf16 MMAs), plain TF32 one
@@ -319,11 +347,13 @@ def run_gpu_arm(args, cfg, n_points, batch):
         barrier()
         return s.elapsed_time(e)
 
+    seq_steps = min(args.steps, 20)   # the sequential legs only feed the per-kernel table and the latency figure
+
     def timed_steps(fn):
-        """K sequential steps, each bracketed by its own CUDA events on the current stream; L2 flushed outside them."""
+        """`seq_steps` sequential steps, each bracketed by its own CUDA events on the current stream; L2 flushed outside them."""
         ms = []
         barrier()
-        for k in range(args.steps):
+        for k in range(seq_steps):
             flush.zero_()
             torch.cuda.synchronize()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,11 +401,12 @@ def run_gpu_arm(args, cfg, n_points, batch):
         avg = sum(ms) / len(ms)
         nbytes = algorithmic_bytes(key, batch)
         flops = algorithmic_flops(key)
-        per_kernel.append({"kernel": key, "calls_per_step": len(ms) / args.steps, "avg_ms": round(avg, 4),
-                           "ms_per_step": round(sum(ms) / args.steps, 4),
+        per_kernel.append({"kernel": key, "calls_per_step": len(ms) / seq_steps, "avg_ms": round(avg, 4),
+                           "ms_per_step": round(sum(ms) / seq_steps, 4),
                            "algorithmic_GBps": round(nbytes / avg / 1e6, 2) if nbytes else None,
                            "algorithmic_TFLOPs": round(flops[0] / avg / 1e9, 1) if flops else None})
-        g = groups.setdefault(key.partition("(")[0], {"ms": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0, "mma": 0.0})
+        g = groups.setdefault(KERNEL_OF.get(key.partition("(")[0], key.partition("(")[0]),
+                              {"ms": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0, "mma": 0.0})
         g["ms"] += sum(ms)
         g["launches"] += len(ms)
         g["bytes"] += (nbytes or 0) * len(ms)
@@ -394,24 +425,34 @@ def run_gpu_arm(args, cfg, n_points, batch):
                 "pdab_pda_encode_ln_h": "group_encode_pda", "pdab_group_attention_h": "attention",
                 "pdab_ball_query_grid": "group"}
     stages = {}
-    for name, g in groups.items():
-        st = stage_of.get(name, "other")
-        stages[st] = stages.get(st, 0.0) + g["ms"] / args.steps / batch * 1e3
+    for key, ms in kernel_ms.items():
+        st = stage_of.get(key.partition("(")[0], "other")
+        stages[st] = stages.get(st, 0.0) + sum(ms) / seq_steps / batch * 1e3
     stages = {k: round(v, 1) for k, v in sorted(stages.items())}
     roofline = None
     if groups:
-        name, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
-        step_ms = sum(inst_ms) / args.steps
-        common = {"kernel": name, "launches_per_step": g["launches"] / args.steps,
-                  "avg_launch_ms": round(g["ms"] / g["launches"], 4), "share_of_step": round(g["ms"] / args.steps / step_ms, 4),
+        # Dominant kernel = largest share of the GPU's work, i.e. of SM-time: a kernel's device time x the fraction of the SMs
+        # its grid occupies.  FPS is a latency chain on one CTA (cluster) per scene — 16 of 148 SMs for the KITTI batch, which
+        # is why ScenePipeline overlaps it with other batches — every other kernel of ours fills the machine.
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        fps_ctas = batch * max(1, -(-n_points // 16384))
+        occupancy = {"fps_kernel": min(1.0, fps_ctas / sms)}
+        sm_ms = {k: v["ms"] * occupancy.get(k, 1.0) for k, v in groups.items()}
+        name = max(sm_ms, key=sm_ms.get)
+        g = groups[name]
+        step_ms = sum(inst_ms) / seq_steps
+        common = {"kernel": name, "launches_per_step": g["launches"] / seq_steps,
+                  "avg_launch_ms": round(g["ms"] / g["launches"], 4), "share_of_step": round(g["ms"] / seq_steps / step_ms, 4),
+                  "share_of_sm_time": round(sm_ms[name] / sum(sm_ms.values()), 4),
+                  "sm_time_shares": {k: round(v / sum(sm_ms.values()), 4) for k, v in sorted(sm_ms.items(), key=lambda kv: -kv[1])[:6]},
                   "traffic": None}
-        tr = ROOT / "profiles" / "r01_tc_gemm_traffic.json"
-        if name == "pdab_tc_linear" and tr.exists() and args.config == "kitti" and batch == 16:
+        tr = ROOT / "profiles" / "r02_tc_gemm_traffic.json"
+        if name == "tc_gemm_kernel" and tr.exists() and args.config == "kitti" and batch == 16:
             t = json.loads(tr.read_text())  # ncu dram__bytes_read + write per launch, same workload (see its "source")
             common["traffic"] = round(t["dram_bytes_per_launch"])
             common["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's launches)"
             common["algorithmic_bytes_per_launch"] = round(g["bytes"] / g["launches"])
-            common["traffic_source"] = "profiles/r01_tc_gemm_traffic.json"
+            common["traffic_source"] = "profiles/r02_tc_gemm_traffic.json"
         if g["flops"] > 0:  # tensor-core kernel: algorithmic flops = 2*rows*k*nout of the fp32 product it computes
             achieved = g["flops"] / g["ms"] / 1e9
             roofline = {"bound": "tensor", "achieved": round(achieved, 1), "peak": tc_peak, "unit": "TFLOP/s",
@@ -419,10 +460,11 @@ def run_gpu_arm(args, cfg, n_points, batch):
                         "mma_issued_TFLOPs": round(g["mma"] / g["ms"] / 1e9, 1),
                         "mma_issued_frac": round(g["mma"] / g["ms"] / 1e9 / tc_peak, 4),
                         "hbm_GBps": round(g["bytes"] / g["ms"] / 1e6, 1),
-                        "note": "`achieved` = algorithmic flops (2*rows*k*nout, each fp32-level product counted once) / "
-                                "launch time against the dense bf16 peak; an fp32-level product costs 3 bf16 MMAs "
-                                "(split-bf16), so a perfectly tensor-bound launch reaches frac = 1/3; `mma_issued_frac` "
-                                "= share of the tensor pipe's bf16 rate the issued MMAs occupy", **common}
+                        "note": "`achieved` = algorithmic flops (2*rows*k*nout per launch, summed over the kernel's launches "
+                                "of one step) / their summed durations, against the measured dense bf16 peak; "
+                                "`mma_issued_frac` = the same with every product weighted by the MMAs it issues (1 in the "
+                                "fp16 single-pass mode, 3 in the split modes); `hbm_GBps` = the launches' algorithmic bytes / "
+                                "the same time (half of them are bound by that, not by the tensor pipe)", **common}
         else:
             achieved = g["bytes"] / g["ms"] / 1e6
             roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
@@ -433,10 +475,10 @@ def run_gpu_arm(args, cfg, n_points, batch):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sps, threads, times = time_cpu(cfg, n_points, scenes=args.cpu_scenes)
+        sps, threads, times, what = time_cpu(cfg, n_points, scenes=args.cpu_scenes, name=args.config)
         cpu = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.cpu_scenes} of the workload's scenes, one {n_points}-point scene per forward "
-                         f"(batch 1), {sum(times):.1f} s of CPU work"}
+                         f"(batch 1), {sum(times):.1f} s of CPU work; {what}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

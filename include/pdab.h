@@ -350,9 +350,11 @@ int pdab_nms_batched(const float *boxes, const int *counts, int nscenes, int str
                      int *num_keep, void *workspace, pdab_stream_t stream);
 
 /* Drop-in for the reference pybind signature: device boxes, HOST keep list,
- * returns num_to_keep (>= 0) or a negative error.  Allocates/frees its own
- * workspace through the stream-ordered allocator and synchronises `stream`
- * (the reference does cudaMalloc + blocking cudaMemcpy + cudaFree here).
+ * returns num_to_keep (>= 0) or a negative error.  Device scratch and a pinned
+ * staging buffer are cached per host thread (grow-only; freed at thread exit);
+ * the keep list returns in ONE device-to-host copy followed by one
+ * synchronisation of `stream` (the reference does cudaMalloc + blocking
+ * cudaMemcpy + cudaFree + a host loop here).
  * `normal` != 0 selects the axis-aligned variant (nms_normal_gpu,
  * IOU/src/iou3d_nms.cpp:139-185, kernel IOU/src/iou3d_nms_kernel.cu:328-372). */
 int pdab_nms_host(const float *boxes, int n, float thresh, int64_t *keep_host, int normal, pdab_stream_t stream);

@@ -18,6 +18,8 @@
 // polygon ordering uses a stable insertion sort on precomputed angles, which
 // yields the identical permutation as the reference's bubble sort with a
 // strict '>' comparator that recomputes atan2 per comparison.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -166,14 +168,25 @@ __device__ __forceinline__ float iou_axis_aligned(const float *a, const float *b
 }
 
 // ---- mask: grid (col tile, row tile, scene), only col >= row does work -------------------------
-// mask layout per scene: (stride rows) x (col_blocks words), col_blocks = ceil(stride/64)
+// mask layout per scene: (stride rows) x (col_blocks words), col_blocks = ceil(stride/64).
+// A CTA = 64 rows x kSplit column slices (256 threads): thread (row, slice) tests its row against 64 / kSplit columns, the
+// slices' bit fields meet in shared memory.  (One thread per row — the reference's shape — left 2 warps per SM doing 64
+// rotated-IoU evaluations back to back: the n = 1024 mask took longer than the reference's whole call.)
+constexpr int kSplit = 4;
+constexpr int kMaskThreads = kTileBoxes * kSplit;
+
+__device__ __forceinline__ int scene_count(const int *counts, int scene, int fixed_n, int stride) {
+    // a count outside [0, stride] would walk into the next scene's slab: clamp
+    return counts ? min(max(counts[scene], 0), stride) : fixed_n;
+}
+
 template <bool NORMAL>
-__global__ void __launch_bounds__(kTileBoxes)
+__global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float *__restrict__ boxes, const int *__restrict__ counts, int fixed_n, int stride,
                 float thresh, unsigned long long *__restrict__ mask) {
     const int col = blockIdx.x, rowt = blockIdx.y, scene = blockIdx.z;
     if (col < rowt) return;  // never read by the greedy scan (IOU/src/iou3d_nms.cpp:128)
-    const int n = counts ? counts[scene] : fixed_n;
+    const int n = scene_count(counts, scene, fixed_n, stride);
     if (rowt * kTileBoxes >= n || col * kTileBoxes >= n) return;
     boxes += (size_t)scene * stride * 7;
     const int col_blocks = pdab::div_up(stride, kTileBoxes);
@@ -182,59 +195,84 @@ nms_mask_kernel(const float *__restrict__ boxes, const int *__restrict__ counts,
     const int row_size = min(n - rowt * kTileBoxes, kTileBoxes);
     const int col_size = min(n - col * kTileBoxes, kTileBoxes);
     __shared__ float tile[kTileBoxes * 7];
-    for (int i = threadIdx.x; i < col_size * 7; i += kTileBoxes) tile[i] = boxes[(size_t)col * kTileBoxes * 7 + i];
+    __shared__ unsigned long long part[kSplit][kTileBoxes];
+    for (int i = threadIdx.x; i < col_size * 7; i += kMaskThreads) tile[i] = boxes[(size_t)col * kTileBoxes * 7 + i];
     __syncthreads();
-    if ((int)threadIdx.x < row_size) {
-        const int cur = rowt * kTileBoxes + threadIdx.x;
+    const int r = threadIdx.x & (kTileBoxes - 1), slice = threadIdx.x / kTileBoxes;
+    unsigned long long bits = 0ull;
+    if (r < row_size) {
+        const int cur = rowt * kTileBoxes + r;
         float me[7];
 #pragma unroll
         for (int q = 0; q < 7; q++) me[q] = boxes[(size_t)cur * 7 + q];
-        unsigned long long bits = 0ull;
-        const int start = (rowt == col) ? threadIdx.x + 1 : 0;
-        for (int i = start; i < col_size; i++) {
+        constexpr int W = kTileBoxes / kSplit;
+        const int lo = max(slice * W, (rowt == col) ? r + 1 : 0), hi = min((slice + 1) * W, col_size);
+        for (int i = lo; i < hi; i++) {
             const float v = NORMAL ? iou_axis_aligned(me, tile + i * 7) : iou_rotated(me, tile + i * 7);
             if (v > thresh) bits |= 1ull << i;
         }
-        mask[(size_t)cur * col_blocks + col] = bits;
+    }
+    part[slice][r] = bits;
+    __syncthreads();
+    if (slice == 0 && r < row_size) {
+#pragma unroll
+        for (int q = 1; q < kSplit; q++) bits |= part[q][r];
+        mask[(size_t)(rowt * kTileBoxes + r) * col_blocks + col] = bits;
     }
 }
 
-// ---- greedy scan: one CTA of 64 threads per scene -------------------------------------------
-__global__ void __launch_bounds__(kTileBoxes)
+// ---- greedy scan: one CTA per scene -----------------------------------------------------------
+// Tile by tile: the 64 mask rows of the tile (all words right of the diagonal) are staged in shared memory by the whole
+// CTA — coalesced, and one tile AHEAD of the serial part — thread 0 walks the tile's 64 boxes against the diagonal word,
+// then every thread ORs the kept rows into the removed-bits words it owns, from shared memory.  (The first version fetched
+// every kept row's word from global memory inside the OR loop: up to 64 dependent L2 round trips per tile.)
+constexpr int kScanThreads = 256;
+constexpr int kScanMaxWords = 64;   // words per staged row: stride <= 4096 takes this path, larger strides the direct one
+
+__global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ counts, int fixed_n, int stride,
                 long long *__restrict__ keep, int *__restrict__ num_keep) {
     const int scene = blockIdx.x;
-    const int n = counts ? counts[scene] : fixed_n;
+    const int n = scene_count(counts, scene, fixed_n, stride);
     const int col_blocks = pdab::div_up(stride, kTileBoxes);
     mask += (size_t)scene * stride * col_blocks;
     keep += (size_t)scene * stride;
     const int t = threadIdx.x;
+    const int ntiles = pdab::div_up(n, kTileBoxes);
 
-    __shared__ unsigned long long diag[kTileBoxes];
+    extern __shared__ unsigned long long rows[];        // [2][64][ntiles]: the tile's mask rows, double buffered
+    __shared__ unsigned long long remv[256];            // removed bits, one word per tile (stride <= 16384)
     __shared__ unsigned long long kept_bits;
     __shared__ int total;
-    // removed-bits words owned by this thread: w = t, t + 64, ...  (col_blocks <= 64 * kMaxOwn)
-    constexpr int kMaxOwn = 4;  // stride <= 16384
-    unsigned long long remv[kMaxOwn];
-#pragma unroll
-    for (int q = 0; q < kMaxOwn; q++) remv[q] = 0ull;
+    const bool staged = ntiles <= kScanMaxWords;
+    for (int w = t; w < ntiles; w += kScanThreads) remv[w] = 0ull;
     if (t == 0) total = 0;
-    __shared__ unsigned long long cur_word;
 
-    const int ntiles = pdab::div_up(n, kTileBoxes);
+    auto stage = [&](int tile, int buf) {   // words [tile, ntiles) of rows tile*64 .. +63 (lower-triangle words are never read)
+        const int size = min(n - tile * kTileBoxes, kTileBoxes);
+        const int nw = ntiles - tile;
+        unsigned long long *dst = rows + (size_t)buf * kTileBoxes * ntiles;
+        for (int i = t; i < size * nw; i += kScanThreads) {
+            const int q = i / nw, w = tile + (i - q * nw);
+            dst[q * ntiles + w] = mask[(size_t)(tile * kTileBoxes + q) * col_blocks + w];
+        }
+    };
+    if (staged && ntiles > 0) stage(0, 0);
+    __syncthreads();
     for (int tile = 0; tile < ntiles; tile++) {
         const int size = min(n - tile * kTileBoxes, kTileBoxes);
-        diag[t] = t < size ? mask[(size_t)(tile * kTileBoxes + t) * col_blocks + tile] : 0ull;
-        if ((tile & 63) == t) cur_word = remv[tile >> 6];
-        __syncthreads();
+        const int buf = tile & 1;
+        const unsigned long long *cur_rows = rows + (size_t)buf * kTileBoxes * ntiles;
+        if (staged && tile + 1 < ntiles) stage(tile + 1, buf ^ 1);      // overlaps the serial walk below
         if (t == 0) {
-            unsigned long long cur = cur_word, kb = 0ull;
+            unsigned long long cur = remv[tile], kb = 0ull;
             int tot = total;
             for (int q = 0; q < size; q++) {
                 if (!((cur >> q) & 1ull)) {
                     kb |= 1ull << q;
                     keep[tot++] = tile * kTileBoxes + q;
-                    cur |= diag[q];
+                    cur |= staged ? cur_rows[q * ntiles + tile]
+                                  : mask[(size_t)(tile * kTileBoxes + q) * col_blocks + tile];
                 }
             }
             kept_bits = kb;
@@ -243,19 +281,14 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restri
         __syncthreads();
         const unsigned long long kb = kept_bits;
         // OR the kept rows into the words right of this tile
-#pragma unroll
-        for (int own = 0; own < kMaxOwn; own++) {
-            const int w = t + own * 64;
-            if (w > tile && w < ntiles) {
-                unsigned long long acc = 0ull;
-                unsigned long long bits = kb;
-                while (bits) {
-                    const int q = __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-                    acc |= mask[(size_t)(tile * kTileBoxes + q) * col_blocks + w];
-                }
-                remv[own] |= acc;
+        for (int w = tile + 1 + t; w < ntiles; w += kScanThreads) {
+            unsigned long long acc = 0ull, bits = kb;
+            while (bits) {
+                const int q = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                acc |= staged ? cur_rows[q * ntiles + w] : mask[(size_t)(tile * kTileBoxes + q) * col_blocks + w];
             }
+            remv[w] |= acc;
         }
         __syncthreads();
     }
@@ -284,11 +317,15 @@ int run_nms(const float *boxes, const int *counts, int nscenes, int n_or_stride,
     dim3 grid(tiles, tiles, nscenes);
     auto *mask = static_cast<unsigned long long *>(workspace);
     if (normal)
-        nms_mask_kernel<true><<<grid, kTileBoxes, 0, stream>>>(boxes, counts, n_or_stride, n_or_stride, thresh, mask);
+        nms_mask_kernel<true><<<grid, kMaskThreads, 0, stream>>>(boxes, counts, n_or_stride, n_or_stride, thresh, mask);
     else
-        nms_mask_kernel<false><<<grid, kTileBoxes, 0, stream>>>(boxes, counts, n_or_stride, n_or_stride, thresh, mask);
+        nms_mask_kernel<false><<<grid, kMaskThreads, 0, stream>>>(boxes, counts, n_or_stride, n_or_stride, thresh, mask);
     PDAB_LAUNCH_CHECK();
-    nms_scan_kernel<<<nscenes, kTileBoxes, 0, stream>>>(mask, counts, n_or_stride, n_or_stride, keep, num_keep);
+    // staged rows: 2 buffers x 64 rows x tiles words (tiles <= 64: at most 64 KB)
+    const size_t smem = tiles <= kScanMaxWords ? sizeof(unsigned long long) * 2 * kTileBoxes * tiles : 0;
+    if (smem > 48 * 1024)
+        PDAB_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<<<nscenes, kScanThreads, smem, stream>>>(mask, counts, n_or_stride, n_or_stride, keep, num_keep);
     PDAB_LAUNCH_CHECK();
     return 0;
 }
@@ -313,6 +350,24 @@ extern "C" int pdab_nms_batched(const float *boxes, const int *counts, int nscen
                    false, pdab::to_stream(stream));
 }
 
+// Host-facing form (the reference pybind signature): device scratch and a pinned staging buffer are cached per host
+// thread and device (grow-only; the reference does cudaMalloc + blocking cudaMemcpy + cudaFree per call), and the keep
+// list comes back in ONE device-to-host copy of [num | keep] followed by one stream synchronisation.
+namespace {
+struct HostNmsCache {
+    int device = -1;
+    char *dev = nullptr;
+    size_t dev_bytes = 0;
+    char *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    ~HostNmsCache() {
+        if (dev) cudaFree(dev);
+        if (pinned) cudaFreeHost(pinned);
+    }
+};
+thread_local HostNmsCache g_host_nms;
+}  // namespace
+
 extern "C" int pdab_nms_host(const float *boxes, int n, float thresh, int64_t *keep_host, int normal,
                              pdab_stream_t stream) {
     if (n < 0 || (n > 0 && (!boxes || !keep_host))) return PDAB_EINVAL;
@@ -320,25 +375,41 @@ extern "C" int pdab_nms_host(const float *boxes, int n, float thresh, int64_t *k
     if (n > 16384) return PDAB_EUNSUPPORTED;
     cudaStream_t s = pdab::to_stream(stream);
     const size_t mask_bytes = pdab_nms_workspace_bytes(n);
-    const size_t keep_off = (mask_bytes + 255) / 256 * 256;
-    const size_t total = keep_off + sizeof(long long) * n + sizeof(int);
-    char *ws = nullptr;
-    cudaError_t e = cudaMallocAsync(&ws, total, s);
+    const size_t out_off = (mask_bytes + 255) / 256 * 256;
+    const size_t out_bytes = sizeof(long long) * ((size_t)n + 1);      // [num | keep[0..n)]
+    const size_t total = out_off + out_bytes;
+    HostNmsCache &c = g_host_nms;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return -(int)e - 1000;
-    long long *keep_dev = reinterpret_cast<long long *>(ws + keep_off);
-    int *num_dev = reinterpret_cast<int *>(ws + keep_off + sizeof(long long) * n);
-    int rc = run_nms(boxes, nullptr, 1, n, thresh, keep_dev, num_dev, ws, normal != 0, s);
-    int num = 0;
-    if (rc == 0) {
-        e = cudaMemcpyAsync(&num, num_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(keep_host, keep_dev, sizeof(long long) * n, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) rc = -(int)e - 1000;
-    } else if (rc > 0) {
-        rc = -rc - 1000;
+    if (c.device != dev || c.dev_bytes < total) {
+        if (c.dev) cudaFree(c.dev);
+        c.dev = nullptr;
+        c.dev_bytes = 0;
+        e = cudaMalloc(&c.dev, total * 2);                               // grow geometrically: few re-allocations
+        if (e != cudaSuccess) return -(int)e - 1000;
+        c.dev_bytes = total * 2;
+        c.device = dev;
     }
-    cudaFreeAsync(ws, s);
-    return rc == 0 ? num : rc;
+    if (c.pinned_bytes < out_bytes) {
+        if (c.pinned) cudaFreeHost(c.pinned);
+        c.pinned = nullptr;
+        c.pinned_bytes = 0;
+        e = cudaMallocHost(&c.pinned, out_bytes * 2);
+        if (e != cudaSuccess) return -(int)e - 1000;
+        c.pinned_bytes = out_bytes * 2;
+    }
+    long long *out_dev = reinterpret_cast<long long *>(c.dev + out_off);
+    int rc = run_nms(boxes, nullptr, 1, n, thresh, out_dev + 1, reinterpret_cast<int *>(out_dev), c.dev, normal != 0, s);
+    if (rc > 0) return -rc - 1000;
+    if (rc < 0) return rc;
+    e = cudaMemcpyAsync(c.pinned, out_dev, out_bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    const int num = *reinterpret_cast<const int *>(c.pinned);
+    if (num < 0 || num > n) return PDAB_EINVAL;
+    memcpy(keep_host, c.pinned + sizeof(long long), sizeof(long long) * (size_t)num);
+    return num;
 }
 
 static int pairwise(int na, const float *a, int nb, const float *b, float *out, int want_iou, cudaStream_t s) {

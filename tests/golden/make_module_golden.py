@@ -33,39 +33,12 @@ from pdanet_b200.iassd_backbone import IASSD_Backbone  # noqa: E402
 from pdanet_b200.synthetic import make_batch  # noqa: E402
 
 
-def _pkg(name, path):
-    m = types.ModuleType(name)
-    m.__path__ = [str(path)]
-    sys.modules[name] = m
-    return m
+from oracle.ref_python import _pkg, import_reference as _import_reference  # noqa: E402
 
 
 def import_reference():
-    _pkg("pcdet", REF / "pcdet")
-    _pkg("pcdet.ops", REF / "pcdet/ops")
-    _pkg("pcdet.ops.pointnet2", REF / "pcdet/ops/pointnet2")
-    pb = "pcdet.ops.pointnet2.pointnet2_batch"
-    _pkg(pb, REF / "pcdet/ops/pointnet2/pointnet2_batch")
-    sys.modules[pb + ".pointnet2_batch_cuda"] = oracle           # same pybind names/arity, CPU tensors
-    sys.modules[pb + ".semantic_view"] = types.ModuleType("semantic_view")  # open3d visualiser, unused
-    _pkg("pcdet.models", REF / "pcdet/models")
-    _pkg("pcdet.models.backbones_3d", REF / "pcdet/models/backbones_3d")
-    _pkg("pcdet.models.backbones_3d.cluster", REF / "pcdet/models/backbones_3d/cluster")
-    spv = types.ModuleType("spvnas_cluster")
-    spv.SPVNAS = None                                             # torchsparse model, imported but never built
-    sys.modules["pcdet.models.backbones_3d.cluster.spvnas_cluster"] = spv
-
-    utils = importlib.import_module(pb + ".pointnet2_utils")
-    # the reference Functions allocate outputs with torch.cuda.*Tensor: swap in CPU-allocating equivalents
-    utils.furthest_point_sample = utils.farthest_point_sample = torch_ops.furthest_point_sample
-    utils.furthest_point_sample_with_dist = torch_ops.furthest_point_sample_with_dist
-    utils.gather_operation = torch_ops.gather_operation
-    utils.grouping_operation = torch_ops.grouping_operation
-    utils.ball_query = torch_ops.ball_query
-    utils.ball_query_dilated = torch_ops.ball_query_dilated
-    modules = importlib.import_module(pb + ".pointnet2_modules")
-    backbone = importlib.import_module("pcdet.models.backbones_3d.IASSD_backbone")
-    return utils, modules, backbone
+    """The reference's own modules from /root/reference (oracle/ref_python.py holds the stub loader)."""
+    return _import_reference(REF)
 
 
 def forced_topk_ops(picks):

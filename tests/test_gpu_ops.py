@@ -128,6 +128,36 @@ def test_fps_full_kitti_and_once_sizes_properties(ops):
         assert (mins[:-1] >= mins[1:] - 1e-9).all()
 
 
+FFPS_CASES = [("rand_2048", 2, 2048, 512, None), ("ties_1500", 1, 1500, 300, 0.5), ("kitti_L1_4096", 2, 4096, 1024, None),
+              ("dups_1000", 2, 1000, 250, 1.0), ("n_equals_m", 1, 300, 300, None)]
+
+
+@pytest.mark.parametrize("tag,B,N,m,quant", FFPS_CASES, ids=[c[0] for c in FFPS_CASES])
+def test_fps_with_dist_bit_exact_vs_reference_kernel(ops, ref_pointnet2, tag, B, N, m, quant):
+    """F-FPS from a distance matrix against the reference's own furthest_point_sampling_with_dist_kernel
+    (PB/src/sampling_gpu.cu:256-416) rebuilt for sm_100a: indices and the `temp` scratch, bit for bit, with quantised
+    features (massive distance ties: the bit-reversed-thread tie rule decides) and N != power of two."""
+    from pdanet_b200 import pointnet2_batch_cuda
+    g = torch.Generator().manual_seed(seed_of(tag))
+    pts = torch.randn(B, N, 6, generator=g)
+    if quant:
+        pts = torch.round(pts / quant) * quant
+    dist = dev(torch.cdist(pts.double(), pts.double()).pow(2).float().contiguous())
+    temp_r = torch.full((B, N), 1e10, device="cuda")
+    idx_r = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    rc = ref_pointnet2.ref_fps_with_dist(B, N, m, C.c_void_p(dist.data_ptr()), C.c_void_p(temp_r.data_ptr()),
+                                         C.c_void_p(idx_r.data_ptr()))
+    assert rc == 0
+    temp = torch.full((B, N), 1e10, device="cuda")
+    idx = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    pointnet2_batch_cuda.furthest_point_sampling_with_dist_wrapper(B, N, m, dist, temp, idx)
+    assert torch.equal(idx, idx_r)
+    assert torch.equal(temp, temp_r)
+    assert torch.equal(ops.furthest_point_sample_with_dist(dist, m), idx_r)
+    assert torch.equal(oracle.fps_with_dist(dist.cpu(), m), idx_r.cpu())
+
+
 def test_fps_with_dist_bit_exact(ops):
     g = torch.Generator().manual_seed(5)
     pts = torch.randn(2, 700, 6, generator=g)
@@ -515,3 +545,36 @@ def test_points_in_boxes_bit_exact(B, T, M):
     cpu = oracle.points_in_boxes(pts, boxes)
     # libm vs libdevice cosf/sinf may differ in the last ulp: points within ~1e-6 of a face may flip
     assert (got != cpu).float().mean() < 1e-3
+
+
+@pytest.mark.gpu
+def test_custom_ops_match_the_op_api_and_differentiate(ops):
+    """torch.ops.pdab.* (torch.library registration over the C ABI) == the op API mirror, gradients of gather / group through
+    the dispatcher == the mirror's autograd Functions, and the ops trace under torch.compile(fullgraph=True)."""
+    import pdanet_b200.custom_ops  # noqa: F401
+    xyz = dev(scene_xyz(3, 2, 2048))
+    new_xyz = xyz[:, :300].contiguous()
+    feats = torch.randn(2, 16, 2048, device="cuda", requires_grad=True)
+    assert torch.equal(torch.ops.pdab.furthest_point_sample(xyz, 256), ops.furthest_point_sample(xyz, 256))
+    idx = torch.ops.pdab.ball_query(1.5, 16, xyz, new_xyz)
+    assert torch.equal(idx, ops.ball_query(1.5, 16, xyz, new_xyz))
+    g1 = torch.ops.pdab.grouping_operation(feats, idx)
+    g2 = ops.grouping_operation(feats, idx)
+    assert torch.equal(g1, g2)
+    w = torch.randn_like(g1)
+    (ga,) = torch.autograd.grad((g1 * w).sum(), feats)
+    (gb,) = torch.autograd.grad((g2 * w).sum(), feats)
+    assert torch.allclose(ga, gb, rtol=1e-5, atol=1e-5)
+    fps_idx = ops.furthest_point_sample(xyz, 128)
+    assert torch.equal(torch.ops.pdab.gather_operation(feats, fps_idx), ops.gather_operation(feats, fps_idx))
+
+    @torch.compile(fullgraph=True, backend="eager")
+    def traced(x, c, f):
+        i = torch.ops.pdab.ball_query(1.5, 16, x, c)
+        return torch.ops.pdab.grouping_operation(f, i).amax(dim=-1)
+    assert torch.equal(traced(xyz, new_xyz, feats.detach()), g2.detach().amax(dim=-1))
+    boxes = dev(random_boxes(5, 200))
+    keep, num = torch.ops.pdab.nms_keep(boxes, 0.1)
+    from pdanet_b200 import iou3d_nms_utils
+    want, _ = iou3d_nms_utils.nms_gpu(boxes, torch.arange(200, 0, -1, dtype=torch.float32, device="cuda"), 0.1)
+    assert keep[:int(num.item())].tolist() == want.tolist()

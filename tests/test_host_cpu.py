@@ -246,3 +246,24 @@ def replay_reference_head_golden(name, ops, nms_utils, device, rtol=1e-5):
 @pytest.mark.parametrize("name", ["kitti", "once"])
 def test_head_and_post_processing_match_reference_golden(name):
     replay_reference_head_golden(name, torch_ops, torch_ops.nms_utils, "cpu")
+
+
+def test_custom_ops_registered_with_schemas_and_fake_kernels():
+    """`torch.ops.pdab.*` (pdanet_b200/custom_ops.py): schemas registered, shape inference runs without a GPU (FakeTensor),
+    and a CPU tensor is refused by the dispatcher (there is no CPU kernel to fall back to)."""
+    import pdanet_b200.custom_ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in ("furthest_point_sample", "furthest_point_sample_with_dist", "ball_query", "gather_operation",
+                 "grouping_operation", "nms_keep"):
+        assert hasattr(torch.ops.pdab, name)
+    with FakeTensorMode():
+        xyz = torch.empty(2, 100, 3, device="cuda")
+        feats = torch.empty(2, 8, 100, device="cuda")
+        idx = torch.ops.pdab.ball_query(0.5, 16, xyz, xyz[:, :7])
+        assert idx.shape == (2, 7, 16) and idx.dtype == torch.int32
+        assert torch.ops.pdab.furthest_point_sample(xyz, 10).shape == (2, 10)
+        assert torch.ops.pdab.grouping_operation(feats, idx).shape == (2, 8, 7, 16)
+        keep, num = torch.ops.pdab.nms_keep(torch.empty(50, 7, device="cuda"), 0.1)
+        assert keep.shape == (50,) and keep.dtype == torch.int64 and num.shape == (1,)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.pdab.furthest_point_sample(torch.zeros(1, 8, 3), 4)
