@@ -235,6 +235,17 @@ int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a
  * nsample smallest indices among the hits — the same neighbour lists, bit-identical outputs, ~N / 30 of the tests. */
 size_t pdab_sa_grid_workspace_bytes(int b, int n);
 
+/* Deterministic gradient of gather / group / three_interpolate: a sorted segmented sum instead of the
+ * reference's float atomicAdd scatter (PB/src/group_points_gpu.cu:14-50, sampling_gpu.cu:46-83, interpolate_gpu.cu:120-160),
+ * bit-identical from run to run.  The forward op read point idx[b, p] at slot p (p in [0, e): e = npoints, npoints *
+ * nsample, or n * 3 for the interpolation); the caller passes `order` (B, e) int32 = the slots sorted by the point they
+ * read (stable) and `seg_start` (B, n + 1) int32 = where each point's run begins in that order.  Then
+ *   grad_points[b, c, i] = sum_{k in [seg_start[b,i], seg_start[b,i+1])} grad_out[b, c, order[b,k] / div] * weight[b, order[b,k]]
+ * added up in order (weight == NULL: 1; div = 3 for three_interpolate, whose grad_out is (B, c, e / 3), else 1).
+ * grad_points (B, c, n) is fully written (points nobody read get 0). */
+int pdab_segment_sum_grad(int b, int c, int n, int e, int div, const float *grad_out, const float *weight, const int *order,
+                          const int *seg_start, float *grad_points, pdab_stream_t stream);
+
 /* ---- tensor-core (tcgen05 / TMEM) contractions ---------------------------------- */
 
 /* Epilogues of pdab_tc_linear. */

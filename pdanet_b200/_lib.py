@@ -30,6 +30,7 @@ _SIGNATURES = {
     "pdab_ball_query_dilated": (_i, [_i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "pdab_group_points": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pdab_group_points_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pdab_segment_sum_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_three_nn": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_three_interpolate": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_three_interpolate_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

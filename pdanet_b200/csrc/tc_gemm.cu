@@ -669,22 +669,12 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::v
                 tma_prefetch_desc(&p.tmRh);
                 tma_prefetch_desc(&p.tmRl);
                 Pipe rp;
-                // The ring holds kResStages 64-column blocks; the rest of an item's residual slab (and the next item's) is pulled
-                // into L2 ahead of time, so a ring refill costs an L2 round trip, not a DRAM one.
-                auto prefetch_item = [&](long long item) {
-                    if (item >= n_items) return;
-                    const int r0 = (int)row0_of(item), c0 = (int)(item % p.n_groups) * NCH * BN;
-                    if (r0 >= p.T) return;
-                    for (int cb = 0; cb < NCH * BN / 64; cb++) {
-                        tma_prefetch_2d(&p.tmRh, c0 + 64 * cb, r0);
-                        tma_prefetch_2d(&p.tmRl, c0 + 64 * cb, r0);
-                    }
-                };
-                prefetch_item(item0);
+                // (An L2 prefetch of the rest of the item's slab and of the next item's — cp.async.bulk.prefetch.tensor — was
+                // measured: no shorter epilogue, and 25-60 % more DRAM reads per launch, the prefetched lines being evicted by
+                // the kernel's own output stream before the ring got to them; profiles/r02_ncu_tc_gemm_step_launches.csv.)
                 for (long long item = item0; item < n_items; item += item_step) {
                     const int rrow0 = (int)row0_of(item);
                     const int col0 = (int)(item % p.n_groups) * NCH * BN;
-                    prefetch_item(item + item_step);
                     for (int cb = 0; cb < NCH * BN / 64; cb++) {
                         mbar_wait(r_empty(rp.stage), rp.phase ^ 1);
                         mbar_arrive_expect_tx(r_full(rp.stage), (u32)kResStageBytes);

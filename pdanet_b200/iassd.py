@@ -38,7 +38,11 @@ class IASSD(nn.Module):
         for module in self.module_list:
             batch_dict = module(batch_dict)
         if self.training:
-            raise NotImplementedError("training losses are outside the built hot path")
+            # Train mode: every op of the path differentiates (gather / group / interpolate through the C ABI's gradient entry
+            # points, deterministic by default; the PDA block in the reference's statement order on autograd) and the head's
+            # raw predictions are returned for the caller's objective.  The reference's target assignment and loss terms
+            # (pcdet/models/dense_heads/IASSD_head.py:169-1330) are NOT ported: `point_head.get_loss` raises.
+            return batch_dict
         if self.output_padded:
             return self.post_processing_padded(batch_dict)
         if self.batched_post_processing:
@@ -125,10 +129,14 @@ class IASSD(nn.Module):
         live = torch.arange(P, device=boxes.device).unsqueeze(0) < num.unsqueeze(1)            # (B, P)
         sel = torch.gather(order, 1, torch.where(live, keep[:, :P], torch.zeros_like(keep[:, :P])))
         out_scores = src_cls.max(dim=-1)[0] if cfg.OUTPUT_RAW_SCORE else scores
+        # dead slots gather row order[:, 0]; they are SELECTED to zero, not multiplied (0 * inf from an overflowing decode
+        # would put NaN into rows the contract promises to be zero)
+        g_boxes = torch.gather(boxes, 1, sel.unsqueeze(-1).expand(-1, -1, boxes.shape[-1]))
+        g_scores, g_labels = torch.gather(out_scores, 1, sel), torch.gather(labels, 1, sel)
         return {
-            "pred_boxes": torch.gather(boxes, 1, sel.unsqueeze(-1).expand(-1, -1, boxes.shape[-1])) * live.unsqueeze(-1),
-            "pred_scores": torch.gather(out_scores, 1, sel) * live,
-            "pred_labels": torch.gather(labels, 1, sel) * live,
+            "pred_boxes": torch.where(live.unsqueeze(-1), g_boxes, torch.zeros_like(g_boxes)),
+            "pred_scores": torch.where(live, g_scores, torch.zeros_like(g_scores)),
+            "pred_labels": torch.where(live, g_labels, torch.zeros_like(g_labels)),
             "num": num,
         }
 

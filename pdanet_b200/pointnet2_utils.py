@@ -65,10 +65,35 @@ class FurthestPointSamplingWithDist(Function):
 furthest_point_sample_with_dist = FurthestPointSamplingWithDist.apply
 
 
+# Gradients of gather / group / three_interpolate: a sorted segmented sum (bit-identical from run to run) by default; False =
+# the reference's float atomicAdd scatter (PB/src/group_points_gpu.cu:30), faster for a handful of channels but its
+# summation order — and with it the last bits of every gradient — changes between runs.
+DETERMINISTIC_BACKWARD = True
+
+
+def _segment_sum_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int, weight: Optional[torch.Tensor] = None, div: int = 1):
+    """grad_out (B, C, E / div), idx (B, E) int: which of the n points each slot read -> (B, C, n), deterministic."""
+    B, C = grad_out.shape[0], grad_out.shape[1]
+    flat = idx.reshape(B, -1)
+    E = flat.shape[1]
+    vals, order = torch.sort(flat.long(), dim=1, stable=True)
+    bounds = torch.arange(n + 1, device=idx.device, dtype=torch.long).unsqueeze(0).expand(B, -1).contiguous()
+    seg = torch.searchsorted(vals.contiguous(), bounds).int().contiguous()
+    order = order.int().contiguous()
+    grad = torch.empty(B, C, n, dtype=torch.float32, device=grad_out.device)
+    g = grad_out.reshape(B, C, E // div).contiguous()
+    with torch.cuda.device(grad_out.device):
+        _lib.call("pdab_segment_sum_grad", B, C, n, E, div, g.data_ptr(),
+                  None if weight is None else weight.reshape(B, E).contiguous().data_ptr(), order.data_ptr(),
+                  seg.data_ptr(), grad.data_ptr(), torch.cuda.current_stream(grad_out.device).cuda_stream)
+    return grad
+
+
 class GatherOperation(Function):
     """features (B,C,N), idx (B,npoint) -> (B,C,npoint).  PB/pointnet2_utils.py:67-98."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         assert features.is_contiguous()
         assert idx.is_contiguous()
@@ -80,9 +105,12 @@ class GatherOperation(Function):
         return output
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out):
         idx, C, N = ctx.for_backwards
         B, npoint = idx.size()
+        if DETERMINISTIC_BACKWARD and grad_out.is_cuda:
+            return _segment_sum_grad(grad_out, idx, N), None
         grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
         pointnet2.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
         return grad_features, None
@@ -117,6 +145,7 @@ class ThreeInterpolate(Function):
     """features (B,C,M), idx (B,n,3), weight (B,n,3) -> (B,C,n).  PB/pointnet2_utils.py:136-181."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
         assert features.is_contiguous() and idx.is_contiguous() and weight.is_contiguous()
         B, c, m = features.size()
@@ -127,9 +156,12 @@ class ThreeInterpolate(Function):
         return output
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out: torch.Tensor):
         idx, weight, m = ctx.three_interpolate_for_backward
         B, c, n = grad_out.size()
+        if DETERMINISTIC_BACKWARD and grad_out.is_cuda:
+            return _segment_sum_grad(grad_out, idx, m, weight=weight, div=3), None, None
         grad_features = torch.zeros(B, c, m, dtype=torch.float32, device=grad_out.device)
         pointnet2.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
         return grad_features, None, None
@@ -142,6 +174,7 @@ class GroupingOperation(Function):
     """features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample).  PB/pointnet2_utils.py:184-222."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         assert features.is_contiguous()
         assert idx.is_contiguous()
@@ -153,9 +186,12 @@ class GroupingOperation(Function):
         return output
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out):
         idx, N = ctx.for_backwards
         B, C, npoint, nsample = grad_out.size()
+        if DETERMINISTIC_BACKWARD and grad_out.is_cuda:
+            return _segment_sum_grad(grad_out, idx, N), None
         grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
         pointnet2.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
         return grad_features, None

@@ -578,3 +578,51 @@ def test_custom_ops_match_the_op_api_and_differentiate(ops):
     from pdanet_b200 import iou3d_nms_utils
     want, _ = iou3d_nms_utils.nms_gpu(boxes, torch.arange(200, 0, -1, dtype=torch.float32, device="cuda"), 0.1)
     assert keep[:int(num.item())].tolist() == want.tolist()
+
+
+@pytest.mark.gpu
+def test_deterministic_backward_matches_atomic_scatter_and_repeats(ops):
+    """Gradients of group / gather / three_interpolate: the sorted segmented sum (`pdab_segment_sum_grad`, default) equals the
+    reference-style atomicAdd scatter to rounding, equals a float64 index_add, and is bit-identical across runs (the atomic
+    version is not required to be)."""
+    g = torch.Generator().manual_seed(21)
+    B, C, N, M, ns = 2, 24, 3000, 700, 32
+    feats = torch.randn(B, C, N, generator=g).cuda().requires_grad_(True)
+    idx = torch.randint(0, N // 8, (B, M, ns), generator=g, dtype=torch.int32).cuda()      # heavy index collisions
+    w = torch.randn(B, C, M, ns, generator=g).cuda()
+
+    def group_grad():
+        (gr,) = torch.autograd.grad((ops.grouping_operation(feats, idx) * w).sum(), feats)
+        return gr
+
+    assert ops.DETERMINISTIC_BACKWARD
+    a, b = group_grad(), group_grad()
+    assert torch.equal(a, b)
+    ref = torch.zeros(B, C, N, dtype=torch.float64, device="cuda")
+    ref.scatter_add_(2, idx.long().view(B, 1, -1).expand(B, C, -1), w.double().view(B, C, -1))
+    assert torch.allclose(a.double(), ref, rtol=1e-5, atol=1e-5)
+    try:
+        ops.DETERMINISTIC_BACKWARD = False
+        c = group_grad()
+    finally:
+        ops.DETERMINISTIC_BACKWARD = True
+    assert torch.allclose(a, c, rtol=1e-4, atol=1e-4)
+    # gather
+    gi = torch.randint(0, 50, (B, 400), generator=g, dtype=torch.int32).cuda()
+    wg = torch.randn(B, C, 400, generator=g).cuda()
+    (ga,) = torch.autograd.grad((ops.gather_operation(feats, gi) * wg).sum(), feats)
+    refg = torch.zeros(B, C, N, dtype=torch.float64, device="cuda")
+    refg.scatter_add_(2, gi.long().view(B, 1, -1).expand(B, C, -1), wg.double())
+    assert torch.allclose(ga.double(), refg, rtol=1e-5, atol=1e-5)
+    # three_interpolate: weights multiply in
+    known = torch.randn(B, C, 300, generator=g).cuda().requires_grad_(True)
+    ti = torch.randint(0, 300, (B, 1000, 3), generator=g, dtype=torch.int32).cuda()
+    tw = torch.rand(B, 1000, 3, generator=g).cuda()
+    wo = torch.randn(B, C, 1000, generator=g).cuda()
+    (gt,) = torch.autograd.grad((ops.three_interpolate(known, ti, tw) * wo).sum(), known)
+    (gt2,) = torch.autograd.grad((ops.three_interpolate(known, ti, tw) * wo).sum(), known)
+    assert torch.equal(gt, gt2)
+    reft = torch.zeros(B, C, 300, dtype=torch.float64, device="cuda")
+    contrib = (wo.double().unsqueeze(-1) * tw.double().unsqueeze(1)).view(B, C, -1)
+    reft.scatter_add_(2, ti.long().view(B, 1, -1).expand(B, C, -1), contrib)
+    assert torch.allclose(gt.double(), reft, rtol=1e-5, atol=1e-5)
