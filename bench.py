@@ -217,6 +217,9 @@ def algorithmic_bytes(key: str, batch: int):
         out_b = 4 if epi in (2, 3, 4) else 2
         resid = rows * nout * 4 if epi in (2, 3) else 0
         return rows * k * 2 + out_rows * out_cols * out_b + resid + nout * k * 2
+    if name == "pdab_tc_ffn_h":        # rows, e, nsample, ldc: ctx fp16 + y (hi, lo) read, pooled fp32 written, weights once
+        rows, e, ns = a[:3]
+        return rows * e * (2 + 4) + rows // ns * e * 4 + 2 * (e * e + e * e)
     if name == "pdab_tc_sa_gather_linear":
         b, c, n, m, ns, nout = a[:6]
         return b * (4 * c * n + 12 * n + 12 * m + 4 * m * ns) + b * m * ns * nout * 4
@@ -248,7 +251,7 @@ KERNEL_OF = {"pdab_tc_linear": "tc_gemm_kernel", "pdab_tc_linear_h": "tc_gemm_ke
              "pdab_tc_sa_gather_linear_h": "tc_gemm_kernel", "pdab_fps": "fps_kernel", "pdab_fps_with_dist": "fps_kernel",
              "pdab_pda_encode_ln": "pda_encode_ln_kernel", "pdab_pda_encode_ln_h": "pda_encode_ln_kernel",
              "pdab_group_attention": "group_attention_kernel", "pdab_group_attention_h": "group_attention_kernel",
-             "pdab_sa_fused_pair": "sa_fused_pair_kernel"}
+             "pdab_sa_fused_pair": "sa_fused_pair_kernel", "pdab_tc_ffn_h": "ffn_fused_kernel"}
 
 # tensor-pipe work per algorithmic flop, in bf16-MMA flops: split-bf16 ("bf16x3") issues 3 bf16 MMAs per product, 3xTF32
 # issues 3 TF32 MMAs (a TF32 MMA occupies the pipe like 2 bf16 MMAs), plain TF32 one
@@ -266,6 +269,10 @@ def algorithmic_flops(key: str):
     if name == "pdab_tc_linear_h":
         rows, k, nout = a[:3]
         f = 2.0 * rows * k * nout
+        return f, f * MMA_COST[4]
+    if name == "pdab_tc_ffn_h":        # out_proj (e x e) + linear1 (e x e/2) + linear2 (e/2 x e)
+        rows, e = a[:2]
+        f = 2.0 * rows * (e * e + e * e // 2 + e * e // 2)
         return f, f * MMA_COST[4]
     if name == "pdab_tc_sa_gather_linear":
         b, c, n, m, ns, nout, npass = a[:7]
@@ -423,7 +430,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
                 "pdab_tc_linear": "mlp_gemm", "pdab_group_attention": "attention", "pdab_nms_batched": "nms",
                 "pdab_tc_linear_h": "mlp_gemm", "pdab_tc_sa_gather_linear_h": "fused_group_mlp_maxpool",
                 "pdab_pda_encode_ln_h": "group_encode_pda", "pdab_group_attention_h": "attention",
-                "pdab_ball_query_grid": "group"}
+                "pdab_ball_query_grid": "group", "pdab_tc_ffn_h": "mlp_gemm"}
     stages = {}
     for key, ms in kernel_ms.items():
         st = stage_of.get(key.partition("(")[0], "other")

@@ -312,6 +312,20 @@ int pdab_tc_linear_h(long long rows, int k, int nout, int bn, int epilogue, cons
                      const float *gamma, const float *beta, float eps, int nsample, void *out, void *out_lo, int ldo,
                      int out_fmt, pdab_stream_t stream);
 
+/* Fused second half of the PDA transformer block, d_model e = 256, ONE launch (csrc/tc_ffn.cu):
+ *   z = LayerNorm(y + ctx . Wo^T + bo);  h = relu(z . W1^T + b1);  out[g] = max over the nsample rows of group g of (z + h . W2^T + b2)
+ * = pdab_tc_linear_h(ADD_LN) -> pdab_tc_linear_h(RELU) -> pdab_tc_linear_h(ADD_MAXPOOL) with z (rows, e) and h (rows, e/2)
+ * kept in shared memory / TMEM as the next MMA's operand: 6 e bytes of HBM traffic per row instead of 18 e.
+ * ctx fp16 (rows, ldc); y_hi / y_lo fp16 planes (rows, ldy), y = hi + lo; wo / w1 / w2 packed with
+ * pdab_tc_pack_weights(npass = 4; bn = 256, 128, 256); out fp32 (rows / nsample, ldo); nsample in {16, 32},
+ * rows % nsample == 0.  e != 256 returns PDAB_EUNSUPPORTED (the caller runs the three-launch chain).
+ * replaces: out_proj + residual + norm2 + linear1 + ReLU + linear2 + residual of TransformerEncoderLayerPreNorm and the
+ *           max over the neighbourhood, PB/PointFormer.py:31-37, PB/pointnet2_modules.py:929-931. */
+int pdab_tc_ffn_h(long long rows, int e, int nsample, const void *ctx, int ldc, const void *y_hi, const void *y_lo, int ldy,
+                  const float *wo_packed, const float *bo, const float *gamma, const float *beta, float eps,
+                  const float *w1_packed, const float *b1, const float *w2_packed, const float *b2, float *out, int ldo,
+                  pdab_stream_t stream);
+
 /* Number of floats pdab_tc_pack_weights writes for a (nout, k) weight matrix. */
 size_t pdab_tc_packed_floats(int nout, int k, int npass, int bn);
 /* Packs W (nout, k) row-major (device) into the shared-memory image the tensor-core kernels stream:

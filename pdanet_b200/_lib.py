@@ -52,6 +52,7 @@ _SIGNATURES = {
     "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
     "pdab_tc_linear_h": (_i, [C.c_longlong, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i,
                                _i, _vp]),
+    "pdab_tc_ffn_h": (_i, [C.c_longlong, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pdab_tc_sa_gather_linear_h": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "pdab_pda_encode_ln_h": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "pdab_set_persistent_ctas": (_i, [_i]),

@@ -24,6 +24,10 @@ constexpr int kNumSMs = 148;  // B200
 __host__ __device__ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline cudaStream_t to_stream(pdab_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Grid cap of the persistent tensor-core kernels for the calling thread: pdab_set_persistent_ctas, or every SM of the
+// current device (defined in tc_gemm.cu).
+int persistent_ctas();
+
 // Squared distance in the op order nvcc emits for the reference expression
 // (a-b)^2 summed x,y,z: t = rn(dy*dy); t = fma(dx,dx,t); d = fma(dz,dz,t)
 // (PB/src/sampling_gpu.cu:132, PB/src/ball_query_gpu.cu:34; checked in SASS).

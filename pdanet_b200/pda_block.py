@@ -26,7 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from .tc_linear import (EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_ATTN, EPI_RELU, EPI_STORE, OUT_F16, OUT_SPLIT, PackedLinear,
-                        SplitHalf, attn_in_proj)
+                        SplitHalf, attn_in_proj, ffn_fused, ffn_fused_supported)
 
 
 class LinearExact:
@@ -79,6 +79,7 @@ class PDAScalePlan:
         self.lin1 = PackedLinear(tf.linear1.weight, tf.linear1.bias, npass=npass)
         self.lin2 = PackedLinear(tf.linear2.weight, tf.linear2.bias, npass=npass)
         self.norm1, self.norm2 = tf.norm1, tf.norm2
+        self.fused_ffn = True    # d_model 256, fp16 mode: the FFN half of the block as one kernel (csrc/tc_ffn.cu)
         # fused token encoder (csrc/pda_encode.cu): grouper + position MLP + DensityNet + token assembly + LayerNorm 1
         self.fused_encode = True
         self._enc_params = None
@@ -150,8 +151,12 @@ class PDAScalePlan:
         else:
             qkv = self.in_proj(y.hi, EPI_STORE, out_fmt=OUT_F16)                         # (T, 3E) fp16
             ctx = ops.group_attention_h(qkv, ns, self.heads)                             # (T, E) fp16
-        z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2, out_fmt=OUT_SPLIT)   # LN2(y + attn) as (hi, lo)
-        h = self.lin1(z.hi, EPI_RELU, out_fmt=OUT_F16)
-        pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)                   # max_s (z + ffn), fp32 (G, E)
+        if self.fused_ffn and ffn_fused_supported(ctx.shape[1], ns, self.out_proj, self.lin1, self.lin2):
+            # d_model 256: out_proj + LN2 + linear1 + ReLU + linear2 + residual + max-pool in ONE kernel, z and h on chip
+            pooled = ffn_fused(ctx, y, self.out_proj, self.norm2, self.lin1, self.lin2, ns)
+        else:
+            z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2, out_fmt=OUT_SPLIT)   # LN2(y + attn) as (hi, lo)
+            h = self.lin1(z.hi, EPI_RELU, out_fmt=OUT_F16)
+            pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)               # max_s (z + ffn), fp32 (G, E)
         out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU)                       # (G, C_out)
         return out.view(B, M, -1).permute(0, 2, 1)

@@ -181,6 +181,28 @@ class PackedLinear:
         return out
 
 
+def ffn_fused_supported(e: int, nsample: int, *layers: "PackedLinear") -> bool:
+    """Shapes `ffn_fused` covers (csrc/tc_ffn.cu): d_model 256, nsample 16 / 32, every layer in the fp16 single-pass mode."""
+    return e == 256 and nsample in (16, 32) and all(l.npass == 4 for l in layers)
+
+
+def ffn_fused(ctx: torch.Tensor, y: SplitHalf, out_proj: "PackedLinear", norm: torch.nn.LayerNorm, lin1: "PackedLinear",
+              lin2: "PackedLinear", nsample: int) -> torch.Tensor:
+    """max over each neighbourhood of (z + lin2(relu(lin1(z)))), z = norm(y + out_proj(ctx)), in ONE kernel
+    (`pdab_tc_ffn_h`): ctx (T, 256) fp16, y (hi, lo) fp16 planes -> (T / nsample, 256) fp32; z and h never reach HBM."""
+    T, E = ctx.shape
+    assert ctx.dtype == torch.float16 and ctx.stride(1) == 1 and y.hi.shape == (T, E) and y.hi.stride() == y.lo.stride()
+    assert (out_proj.nout, out_proj.k, out_proj.bn) == (E, E, 256) and (lin1.nout, lin1.k, lin1.bn) == (E // 2, E, 128)
+    assert (lin2.nout, lin2.k, lin2.bn) == (E, E // 2, 256) and T % nsample == 0
+    out = torch.empty(T // nsample, E, dtype=torch.float32, device=ctx.device)
+    with torch.cuda.device(ctx.device):
+        _lib.call("pdab_tc_ffn_h", T, E, nsample, ctx.data_ptr(), ctx.stride(0), y.hi.data_ptr(), y.lo.data_ptr(),
+                  y.hi.stride(0), out_proj.packed.data_ptr(), out_proj.bias.data_ptr(), norm.weight.data_ptr(),
+                  norm.bias.data_ptr(), float(norm.eps), lin1.packed.data_ptr(), lin1.bias.data_ptr(),
+                  lin2.packed.data_ptr(), lin2.bias.data_ptr(), out.data_ptr(), out.stride(0), _stream(ctx))
+    return out
+
+
 def attn_in_proj(in_proj_weight: torch.Tensor, in_proj_bias: torch.Tensor, heads: int, npass: int = 2) -> "PackedLinear":
     """in_proj of nn.MultiheadAttention packed for the fused attention epilogue (EPI_ATTN, head_dim 64): the rows of the
     (3E, E) weight are regrouped head by head, [q_h | k_h | v_h] = one 192-column accumulator chunk per head, so that

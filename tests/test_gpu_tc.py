@@ -473,3 +473,43 @@ def test_h16_group_attention_vs_torch_mha(ns, hd):
     att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(groups * ns, E)
     assert _rel(ctx, ref) < 1.5e-3
+
+
+@pytest.mark.parametrize("ns", [16, 32])
+@pytest.mark.parametrize("groups", [3, 700, 9001])
+def test_h16_ffn_fused_equals_three_launch_chain(ns, groups):
+    """pdab_tc_ffn_h (out_proj + LN2 + linear1 + ReLU + linear2 + residual + max-pool in one kernel, z / h on chip) against
+    (a) the three-launch chain of pdab_tc_linear_h it replaces and (b) a float64 statement of the same mathematics on the
+    fp16-rounded operands.  Row counts: less than one CTA tile, ragged last pair tile, many tiles per CTA."""
+    from pdanet_b200.tc_linear import (PackedLinear, SplitHalf, EPI_ADD_LN, EPI_ADD_MAXPOOL, EPI_RELU, OUT_F16, OUT_SPLIT,
+                                       ffn_fused, ffn_fused_supported)
+    dev = _dev()
+    E = 256
+    T = groups * ns
+    g = torch.Generator().manual_seed(groups + ns)
+    ctx = (torch.randn(T, E, generator=g) * 0.7).to(dev).half()
+    y32 = torch.randn(T, E, generator=g).to(dev)
+    y = SplitHalf.from_float(y32)
+    wo, bo = torch.randn(E, E, generator=g) / E ** 0.5, torch.randn(E, generator=g) * 0.1
+    w1, b1 = torch.randn(E // 2, E, generator=g) / E ** 0.5, torch.randn(E // 2, generator=g) * 0.1
+    w2, b2 = torch.randn(E, E // 2, generator=g) / (E // 2) ** 0.5, torch.randn(E, generator=g) * 0.1
+    norm = torch.nn.LayerNorm(E).to(dev)
+    with torch.no_grad():
+        norm.weight.copy_(torch.rand(E, generator=g) + 0.5)
+        norm.bias.copy_(torch.randn(E, generator=g) * 0.1)
+    lo, l1, l2 = (PackedLinear(w.to(dev), b.to(dev), npass=4) for w, b in ((wo, bo), (w1, b1), (w2, b2)))
+    assert ffn_fused_supported(E, ns, lo, l1, l2)
+    fused = ffn_fused(ctx, y, lo, norm, l1, l2, ns)
+    z = lo(ctx, EPI_ADD_LN, residual=y, norm=norm, out_fmt=OUT_SPLIT)
+    h = l1(z.hi, EPI_RELU, out_fmt=OUT_F16)
+    chain = l2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)
+    assert fused.shape == chain.shape == (groups, E)
+    # Same products, same operand rounding; the two differ in the summation order of the LayerNorm statistics (row-split
+    # against column-split epilogue warps), which moves z by an fp32 ulp and so, now and then, flips the fp16 rounding of a
+    # z element that feeds linear1 (2^-11 of one of 256 inputs): ~1e-5 on the output
+    assert _rel(fused.cpu(), chain.cpu()) < 3e-5
+    d = lambda t: t.detach().cpu().double()
+    zz = torch.nn.functional.layer_norm(d(ctx) @ _h(wo).t() + bo.double() + d(y.float()), (E,), d(norm.weight), d(norm.bias), norm.eps)
+    hh = torch.relu(_h(zz.float()) @ _h(w1).t() + b1.double())
+    ref = (zz + _h(hh.float()) @ _h(w2).t() + b2.double()).view(groups, ns, E).max(dim=1)[0]
+    assert _rel(fused.cpu(), ref) < 4e-5
