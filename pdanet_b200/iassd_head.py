@@ -36,6 +36,8 @@ class IASSD_Head(nn.Module):
         self.box_iou3d_layers = (make_fc_layers(self.model_cfg.IOU_FC, dim, 1)
                                  if self.model_cfg.get("IOU_FC", None) is not None else None)
         self.forward_ret_dict = {}
+        self.fast_eval = True     # eval on CUDA: each Linear + BatchNorm1d + ReLU of the FC stacks as one tensor-core launch
+        self._packed = None       # (fingerprint, {stack name: [(PackedLinear, epilogue, width)]})
 
     def generate_predicted_boxes(self, points, point_cls_preds, point_box_preds):
         pred_classes = point_cls_preds.max(dim=-1)[1]
@@ -45,12 +47,49 @@ class IASSD_Head(nn.Module):
         raise NotImplementedError("IASSD_Head target assignment / losses (pcdet/models/dense_heads/IASSD_head.py:169-1330) "
                                   "are outside the built hot path; train-mode forward returns the raw predictions")
 
+    def _fc(self, name, feats):
+        """One FC stack (point_head_template.py:36-47).  Eval on CUDA: BatchNorm folded into the Linear before it, each
+        Linear + BN + ReLU one `tc_linear` launch (split-bf16 products, ~1e-5), the last Linear's width padded to a multiple
+        of 4; the packed copies are rebuilt whenever a parameter or buffer of the head changes."""
+        seq = getattr(self, name)
+        if seq is None:
+            return None
+        if self.training or torch.is_grad_enabled() or not self.fast_eval or not feats.is_cuda:
+            return seq(feats)
+        from .pointnet2_modules import fold_conv_bn
+        from .tc_linear import EPI_RELU, EPI_STORE, PackedLinear
+        fp = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if self._packed is None or self._packed[0] != fp:
+            self._packed = (fp, {})
+        cache = self._packed[1]
+        if name not in cache:
+            layers, mods, k = [], list(seq), 0
+            while k < len(mods):
+                lin = mods[k]
+                if k + 1 < len(mods) and isinstance(mods[k + 1], nn.BatchNorm1d):
+                    w, b = fold_conv_bn(lin, mods[k + 1])
+                    layers.append((PackedLinear(w, b, npass=2), EPI_RELU, w.shape[0]))
+                    k += 3
+                else:
+                    w = lin.weight.detach().float()
+                    b = lin.bias.detach().float() if lin.bias is not None else w.new_zeros(w.shape[0])
+                    pad = (-w.shape[0]) % 4
+                    if pad:
+                        w, b = torch.cat([w, w.new_zeros(pad, w.shape[1])]), torch.cat([b, b.new_zeros(pad)])
+                    layers.append((PackedLinear(w.contiguous(), b.contiguous(), npass=2), EPI_STORE, lin.weight.shape[0]))
+                    k += 1
+            cache[name] = layers
+        x = feats if feats.stride(1) == 1 else feats.contiguous()
+        for lin, epi, width in cache[name]:
+            x = lin(x, epi)
+        return x[:, :width]
+
     def forward(self, batch_dict):
         feats = batch_dict["centers_features"]
         coords = batch_dict["centers"]
-        cls_preds = self.cls_center_layers(feats)
-        box_codes = self.box_center_layers(feats)
-        iou_preds = self.box_iou3d_layers(feats) if self.box_iou3d_layers is not None else None
+        cls_preds = self._fc("cls_center_layers", feats)
+        box_codes = self._fc("box_center_layers", feats)
+        iou_preds = self._fc("box_iou3d_layers", feats)
         point_cls_preds, point_box_preds = self.generate_predicted_boxes(coords[:, 1:4], cls_preds, box_codes)
         batch_dict["batch_cls_preds"] = point_cls_preds
         batch_dict["batch_box_preds"] = point_box_preds

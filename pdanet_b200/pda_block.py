@@ -86,8 +86,11 @@ class PDAScalePlan:
         self._enc_src = (_fold(pm[0], pm[1]), _fold(pm[3], pm[4]), [_fold(c, b) for c, b in zip(dn.mlp_convs, dn.mlp_bns)])
 
     @torch.no_grad()
-    def __call__(self, ops, xyz, new_xyz, features_t, centre_feature_t):
-        """xyz (B,N,3), new_xyz (B,M,3), features_t (B,N,C), centre_feature_t (B,M,C) -> (B, C_out, M)."""
+    def __call__(self, ops, xyz, new_xyz, features_t, centre_feature_t, out=None):
+        """xyz (B,N,3), new_xyz (B,M,3), features_t (B,N,C), centre_feature_t (B,M,C) -> (B, C_out, M).
+        out: a (B*M, C_out) fp32 view (row stride free) the last layer writes its token-major result into — the module's
+        token-major path hands in a column slice of the buffer that the aggregation layer reads (no cat, no transpose)."""
+        self._out = out
         B, M, _ = new_xyz.shape
         ns = self.ns
         C = features_t.shape[2]
@@ -139,8 +142,8 @@ class PDAScalePlan:
         z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2)         # LN2(y + attn)
         h = self.lin1(z, EPI_RELU)
         pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)          # max_s (z + ffn), (:931)
-        out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU)              # (G, C_out)
-        return out.view(B, M, -1).permute(0, 2, 1)
+        out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU, out=self._out)   # (G, C_out)
+        return out if self._out is not None else out.view(B, M, -1).permute(0, 2, 1)
 
     def _transformer_h(self, ops, y: SplitHalf, B, M, ns):
         """The same block in the fp16 single-pass mode (tc_linear npass = 4): every GEMM operand is an fp16 matrix loaded
@@ -158,5 +161,5 @@ class PDAScalePlan:
             z = self.out_proj(ctx, EPI_ADD_LN, residual=y, norm=self.norm2, out_fmt=OUT_SPLIT)   # LN2(y + attn) as (hi, lo)
             h = self.lin1(z.hi, EPI_RELU, out_fmt=OUT_F16)
             pooled = self.lin2(h, EPI_ADD_MAXPOOL, residual=z, nsample=ns)               # max_s (z + ffn), fp32 (G, E)
-        out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU)                       # (G, C_out)
-        return out.view(B, M, -1).permute(0, 2, 1)
+        out = self.fin[1](self.fin[0](pooled, EPI_RELU), EPI_RELU, out=self._out)        # (G, C_out)
+        return out if self._out is not None else out.view(B, M, -1).permute(0, 2, 1)

@@ -151,6 +151,56 @@ class _SamplingSABase(nn.Module):
         self._cache_fp = None
         return super()._load_from_state_dict(*args, **kwargs)
 
+    # ---- token-major tail of the eval fast paths: aggregation and confidence layers as folded linears ------------------
+    # The scales' outputs are (B*M, C) token-major matrices.  The reference concatenates them along the channel axis of a
+    # (B, C, M) tensor and runs Conv1d + BatchNorm1d + ReLU stacks on it (PB/pointnet2_modules.py:936-953, 1674-1686):
+    # per layer a cat, two transposes, a cuDNN convolution, a BatchNorm kernel and a ReLU kernel per conv.  Here the
+    # scales write straight into column slices of one (B*M, sum C) buffer and every Conv1d + BN + ReLU is ONE tensor-core
+    # launch with the BatchNorm folded in (split-bf16 products, ~1e-5: these logits steer the class-aware top-k).  The
+    # result stays token-major; the (B, C, M) tensor the reference's callers expect is a free transposed VIEW of it, and
+    # the next layer's `features.transpose(1, 2).contiguous()` is then a no-op.
+    def _token_tail_ok(self):
+        return (not self.training and not torch.is_grad_enabled() and getattr(self, "token_major", True)
+                and hasattr(self.ops, "pda_group_tokens"))
+
+    def _token_tail(self, buf: torch.Tensor, B: int, M: int):
+        """buf (B*M, C_sum) fp32 -> (new_features (B, C, M) view, cls_out (B, M, num_class) | None)."""
+        from .tc_linear import EPI_RELU, EPI_STORE, PackedLinear
+        cache = self._tail
+        if "agg" not in cache:
+            def stack(seq):
+                layers, k = [], 0
+                mods = list(seq)
+                while k < len(mods):
+                    conv = mods[k]
+                    if k + 1 < len(mods) and isinstance(mods[k + 1], (nn.BatchNorm1d, nn.BatchNorm2d)):
+                        w, b = fold_conv_bn(conv, mods[k + 1])
+                        layers.append((PackedLinear(w, b, npass=2), EPI_RELU, w.shape[0]))
+                        k += 3
+                    else:  # final Conv1d with bias and no activation; output width padded to a multiple of 4
+                        w = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+                        b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+                        pad = (-w.shape[0]) % 4
+                        if pad:
+                            w = torch.cat([w, w.new_zeros(pad, w.shape[1])], dim=0)
+                            b = torch.cat([b, b.new_zeros(pad)], dim=0)
+                        layers.append((PackedLinear(w.contiguous(), b.contiguous(), npass=2), EPI_STORE, conv.weight.shape[0]))
+                        k += 1
+                return layers
+            cache["agg"] = stack(self.aggregation_layer) if self.aggregation_layer is not None else []
+            cache["conf"] = stack(self.confidence_layers) if self.confidence_layers is not None else None
+        x = buf
+        for lin, epi, _ in cache["agg"]:
+            x = lin(x, epi)
+        new_features = x.view(B, M, -1).transpose(1, 2)
+        cls_out = None
+        if cache["conf"] is not None:
+            y = x
+            for lin, epi, width in cache["conf"]:
+                y = lin(y, epi)
+            cls_out = y.view(B, M, -1)[..., :width]
+        return new_features, cls_out
+
     def _make_heads(self, out_channels, aggregation_mlp, confidence_mlp, num_class, have_scales):
         if aggregation_mlp and have_scales:
             layers, out_channels = _conv_bn_relu_1d(out_channels, aggregation_mlp)
@@ -249,6 +299,8 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         self._make_heads(out_channels, aggregation_mlp, confidence_mlp, num_class, len(self.mlps) > 0)
         self._folded = None  # BN-folded MLP parameters, built lazily in eval mode
         self._wide = {}      # scale -> packed tensor-core layers (tc_linear.PackedLinear), eval mode
+        self._tail = {}      # aggregation / confidence stacks as folded linears (token-major eval path)
+        self.token_major = True
         # tensor-core product mode (tc_linear.PackedLinear) of the wide scales' three 1x1-conv layers.  The reference runs
         # them as cuDNN convolutions, TF32 by torch's default on tensor-core GPUs (2^-11 operands).  4 (default) = fp16 x fp16
         # single pass (2^-12 operands, fp32 accumulation: the same class, one MMA per k-step, fp16 activations between the
@@ -258,6 +310,7 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
     def _drop_caches(self):
         self._folded = None
         self._wide = {}
+        self._tail = {}
 
     def _folded_params(self, i):
         if self._folded is None:
@@ -277,7 +330,7 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
                 and (self.nsamples[i] in (16, 32) or (self.nsamples[i] == 64 and self.tc_passes == 4))
                 and hasattr(self.ops, "ball_query") and features.is_cuda)
 
-    def _scale_wide(self, i, xyz, new_xyz, features_t):
+    def _scale_wide(self, i, xyz, new_xyz, features_t, out=None):
         from .tc_linear import EPI_RELU, EPI_RELU_MAXPOOL, PackedLinear
         if i not in self._wide:
             w, b = self._folded_params(i)
@@ -295,8 +348,8 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
         else:
             h = l1.sa_gather(idx, features_t, xyz, new_xyz)                 # (B*M*ns, c1): grouped tensor never exists
             h = l2(h, EPI_RELU)
-        pooled = l3(h, EPI_RELU_MAXPOOL, nsample=ns)                        # (B*M, c3)
-        return pooled.view(B, M, -1).permute(0, 2, 1)
+        pooled = l3(h, EPI_RELU_MAXPOOL, nsample=ns, out=out)               # (B*M, c3)
+        return pooled if out is not None else pooled.view(B, M, -1).permute(0, 2, 1)
 
     def _pair(self, xyz, new_xyz, features):
         """Both narrow scales in ONE kernel (one scan of the cloud for the two radii), already concatenated; None if the
@@ -359,6 +412,18 @@ class PointnetSAModuleMSG_WithSampling(_SamplingSABase):
                     and hasattr(self.ops, "sa_fused")
                     and any(self._wide_supported(i, features) for i in range(len(self.groupers)))):
                 features_t = features.transpose(1, 2).contiguous()
+            if (features_t is not None and self._token_tail_ok()
+                    and all(self._wide_supported(i, features) for i in range(len(self.groupers)))):
+                # every scale on the tensor-core path: scales -> aggregation (-> confidence) stay token-major
+                widths = [self.mlps[i][-3].out_channels for i in range(len(self.groupers))]
+                B, M, _ = new_xyz.shape
+                buf = torch.empty(B * M, sum(widths), dtype=torch.float32, device=xyz.device)
+                off = 0
+                for i, w in enumerate(widths):
+                    self._scale_wide(i, xyz, new_xyz, features_t, out=buf[:, off:off + w])
+                    off += w
+                new_features, cls_out = self._token_tail(buf, B, M)
+                return new_xyz, new_features, cls_out, sampled_idx
             new_features = self._pair(xyz, new_xyz, features)
             if new_features is None:
                 outs = [self._scale(i, xyz, new_xyz, features,
@@ -427,9 +492,12 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
         # (1e-5); 3 = 3xTF32 (1e-6); 1 = TF32
         self.tc_passes = 4
         self._plans = {}
+        self._tail = {}
+        self.token_major = True   # eval: scales -> aggregation -> confidence without leaving the (B*M, C) layout
 
     def _drop_caches(self):
         self._plans = {}
+        self._tail = {}
 
     def _fast_path_ok(self, features):
         return (self.fast_eval and not self.training and not torch.is_grad_enabled()
@@ -470,6 +538,9 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
         ops = self.ops
         if not self.training:
             self._caches_fresh()
+        if (ctr_xyz is None and features is not None and self._token_tail_ok() and features.is_cuda
+                and (len(self.groupers) == 0 or self._fast_path_ok(features))):
+            return self._forward_tokens(xyz, features, cls_features)
         sampled_idx = []
         centre_feature = None
         if ctr_xyz is None:
@@ -498,6 +569,38 @@ class PointnetSAModuleMSG_WithSampling_Ellipsoid(_SamplingSABase):
 
         cls_out = self.confidence_layers(new_features).transpose(1, 2) if self.confidence_layers is not None else None
         return new_xyz, new_features, cls_out, sampled_idx
+
+
+def _pda_forward_tokens(self, xyz, features, cls_features):
+    """Eval forward of a PDA SA layer without leaving the token-major layout: sampling -> row gathers of the centres'
+    coordinates / features -> the scales (pda_block.PDAScalePlan) writing into one (B*M, sum C_out) buffer -> aggregation
+    and confidence layers as folded tensor-core linears (`_token_tail`).  Same values as the channel-major statement order
+    of the reference (PB/pointnet2_modules.py:741-955); the returned (B, C, M) feature tensor is a transposed view."""
+    sampled_idx = self._sample(xyz, features, cls_features)
+    B, M = sampled_idx.shape
+    idx64 = sampled_idx.long()
+    new_xyz = torch.gather(xyz, 1, idx64.unsqueeze(-1).expand(-1, -1, 3))
+    features_t = features.transpose(1, 2).contiguous()          # (B, N, C): free when `features` is a token-major view
+    C = features_t.shape[2]
+    centre_t = torch.gather(features_t, 1, idx64.unsqueeze(-1).expand(-1, -1, C))    # (B, M, C)
+    if len(self.groupers) == 0:                                 # sampling-only layer (PB/pointnet2_modules.py:946-947)
+        new_features = centre_t.transpose(1, 2)
+        cls_out = self.confidence_layers(new_features).transpose(1, 2) if self.confidence_layers is not None else None
+        return new_xyz, new_features, cls_out, sampled_idx
+    from .pda_block import PDAScalePlan
+    widths = [self.fin_conv[i][3].out_channels for i in range(len(self.groupers))]
+    buf = torch.empty(B * M, sum(widths), dtype=torch.float32, device=xyz.device)
+    off = 0
+    for i, w in enumerate(widths):
+        if i not in self._plans:
+            self._plans[i] = PDAScalePlan(self, i, npass=self.tc_passes)
+        self._plans[i](self.ops, xyz, new_xyz, features_t, centre_t, out=buf[:, off:off + w])
+        off += w
+    new_features, cls_out = self._token_tail(buf, B, M)
+    return new_xyz, new_features, cls_out, sampled_idx
+
+
+PointnetSAModuleMSG_WithSampling_Ellipsoid._forward_tokens = _pda_forward_tokens
 
 
 class Vote_layer(nn.Module):
