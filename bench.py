@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pdab", choices=["pdab", "reference"])
     ap.add_argument("--config", default="kitti", choices=["kitti", "once"])
-    ap.add_argument("--batch", type=int, default=None, help="scenes per GPU per step (default 16 kitti / 4 once)")
+    ap.add_argument("--batch", type=int, default=None, help="scenes per GPU per step (default 16 kitti / 32 once: BASELINE configs)")
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -529,7 +529,16 @@ def main():
     from pdanet_b200.config import load_config
     cfg = load_config(args.config)
     n_points = args.points or cfg.NUM_POINTS
-    batch = args.batch or (16 if args.config == "kitti" else 4)
+    batch = args.batch or (16 if args.config == "kitti" else 32)
+    if args.config == "once":
+        global METRIC
+        METRIC = "PDA-SSD scenes/sec @65536 pts (ONCE cfg, full inference)"
+        if args.steps == 200:       # the default: ~80 ms per 32-scene step
+            args.steps = 20
+        if args.depth == 8:
+            args.depth = 3
+        if args.cpu_scenes == 8:    # ~20 s of CPU work per 65536-point scene
+            args.cpu_scenes = 1
     if args.impl == "reference":
         run_reference_arm(args, cfg, n_points, batch)
     else:
