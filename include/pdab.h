@@ -384,6 +384,24 @@ int pdab_nms_batched(const float *boxes, const int *counts, int nscenes, int str
  * IOU/src/iou3d_nms.cpp:139-185, kernel IOU/src/iou3d_nms_kernel.cu:328-372). */
 int pdab_nms_host(const float *boxes, int n, float thresh, int64_t *keep_host, int normal, pdab_stream_t stream);
 
+/* Batched post-processing around the NMS, no host synchronisation, fixed shapes.
+ * pdab_post_front: per scene (b scenes of m centres each): p_c = sigmoid(cls[., c]) (or cls itself if `normalized`), score =
+ * max_c p_c (first maximum), label = argmax + 1, valid = score >= score_thresh; the centres are ordered by (valid ? score :
+ * -inf) descending, ties by ascending index (`sort(descending, stable)`).  Writes order (b, m) int32, sorted_boxes (b, m, 7)
+ * = boxes gathered into that order (the NMS input), counts (b) = min(#valid, pre_max), scores / raw_max (b, m) (raw_max = the
+ * maximum LOGIT, for OUTPUT_RAW_SCORE) and labels (b, m) int64.  cls (b*m, ldc) with nc classes, boxes (b*m, ldb) with ldb >= 7;
+ * m <= 4096.
+ * pdab_post_select: after pdab_nms_batched: out row j < min(num_keep, p) = centre order[keep[j]] of the scene (boxes with nb
+ * columns, score, label); rows behind it are zero; out_num (b) = min(num_keep, p).
+ * replaces: the per-scene loop of Detector3DTemplate.post_processing (pcdet/models/detectors/detector3d_template.py:196-285)
+ *           and class_agnostic_nms (pcdet/models/model_utils/model_nms_utils.py:6-25) around nms_gpu. */
+int pdab_post_front(int b, int m, int nc, int ldc, int ldb, int normalized, float score_thresh, int pre_max, const float *cls,
+                    const float *boxes, int *order, float *sorted_boxes, int *counts, float *scores, float *raw_max,
+                    int64_t *labels, pdab_stream_t stream);
+int pdab_post_select(int b, int m, int p, int nb, int ldb, const int64_t *keep, const int *num_keep, const int *order,
+                     const float *boxes, const float *scores, const int64_t *labels, float *out_boxes, float *out_scores,
+                     int64_t *out_labels, int *out_num, pdab_stream_t stream);
+
 /* Pairwise rotated BEV overlap area / IoU: out (na, nb).
  * replaces: boxes_overlap_bev_gpu / boxes_iou_bev_gpu, IOU/src/iou3d_nms_api.cpp:12-13,
  *           IOU/src/iou3d_nms.cpp:46-88, kernels IOU/src/iou3d_nms_kernel.cu:236-265. */

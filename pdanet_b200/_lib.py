@@ -65,6 +65,8 @@ _SIGNATURES = {
     "pdab_nms_device": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),
     "pdab_nms_batched": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "pdab_nms_host": (_i, [_vp, _i, _f, _vp, _i, _vp]),
+    "pdab_post_front": (_i, [_i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_post_select": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_boxes_overlap_bev": (_i, [_i, _vp, _i, _vp, _vp, _vp]),
     "pdab_boxes_iou_bev": (_i, [_i, _vp, _i, _vp, _vp, _vp]),
 }

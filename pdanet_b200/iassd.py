@@ -33,6 +33,7 @@ class IASSD(nn.Module):
         self.nms_utils = nms_utils if nms_utils is not None else _cuda_nms
         self.batched_post_processing = batched_post_processing and hasattr(self.nms_utils, "nms_batched")
         self.output_padded = False  # True: forward returns post_processing_padded's fixed-shape device tensors
+        self.fused_post_processing = True   # post_processing_padded: two kernels around the batched NMS (csrc/post.cu)
 
     def forward(self, batch_dict):
         for module in self.module_list:
@@ -113,6 +114,16 @@ class IASSD(nn.Module):
         B = batch_dict["batch_size"]
         boxes = batch_dict["batch_box_preds"]
         M = boxes.shape[0] // B
+        if (self.fused_post_processing and hasattr(self.nms_utils, "post_front") and boxes.is_cuda and M <= 4096
+                and boxes.stride(1) == 1 and batch_dict["batch_cls_preds"].stride(1) == 1):
+            # the same steps as below in two kernels around the batched NMS (csrc/post.cu), bit-identical results
+            order, sorted_boxes, counts, scores, raw_max, labels = self.nms_utils.post_front(
+                batch_dict["batch_cls_preds"], boxes, B, batch_dict["cls_preds_normalized"], cfg.SCORE_THRESH,
+                nms_cfg.NMS_PRE_MAXSIZE)
+            keep, num = self.nms_utils.nms_batched(sorted_boxes, counts, nms_cfg.NMS_THRESH)
+            out_boxes, out_scores, out_labels, out_num = self.nms_utils.post_select(
+                keep, num, order, boxes, raw_max if cfg.OUTPUT_RAW_SCORE else scores, labels, min(M, nms_cfg.NMS_POST_MAXSIZE))
+            return {"pred_boxes": out_boxes, "pred_scores": out_scores, "pred_labels": out_labels, "num": out_num}
         boxes = boxes.view(B, M, boxes.shape[-1])
         src_cls = batch_dict["batch_cls_preds"].view(B, M, -1)
         probs = src_cls if batch_dict["cls_preds_normalized"] else torch.sigmoid(src_cls)

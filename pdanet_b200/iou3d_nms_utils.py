@@ -74,3 +74,41 @@ def nms_batched(boxes: torch.Tensor, counts: torch.Tensor, thresh: float):
         _lib.call("pdab_nms_batched", boxes.data_ptr(), counts.data_ptr(), S, stride, float(thresh), keep.data_ptr(),
                   num.data_ptr(), ws.data_ptr(), torch.cuda.current_stream(boxes.device).cuda_stream)
     return keep, num
+
+
+def post_front(cls: torch.Tensor, boxes: torch.Tensor, batch_size: int, normalized: bool, score_thresh: float, pre_max: int):
+    """One kernel for the front half of the batched post-processing (`pdab_post_front`): cls (B*M, num_class) logits (row
+    stride free), boxes (B*M, >= 7) -> order (B, M) int32, sorted_boxes (B, M, 7), counts (B) int32, scores (B, M),
+    raw_max (B, M), labels (B, M) int64."""
+    assert cls.is_cuda and boxes.is_cuda and cls.dtype == boxes.dtype == torch.float32
+    assert cls.stride(1) == 1 and boxes.stride(1) == 1
+    M = cls.shape[0] // batch_size
+    dev = cls.device
+    order = torch.empty(batch_size, M, dtype=torch.int32, device=dev)
+    sorted_boxes = torch.empty(batch_size, M, 7, dtype=torch.float32, device=dev)
+    counts = torch.empty(batch_size, dtype=torch.int32, device=dev)
+    scores = torch.empty(batch_size, M, dtype=torch.float32, device=dev)
+    raw_max = torch.empty(batch_size, M, dtype=torch.float32, device=dev)
+    labels = torch.empty(batch_size, M, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("pdab_post_front", batch_size, M, cls.shape[1], cls.stride(0), boxes.stride(0), int(bool(normalized)),
+                  float(score_thresh), int(pre_max), cls.data_ptr(), boxes.data_ptr(), order.data_ptr(),
+                  sorted_boxes.data_ptr(), counts.data_ptr(), scores.data_ptr(), raw_max.data_ptr(), labels.data_ptr(),
+                  torch.cuda.current_stream(dev).cuda_stream)
+    return order, sorted_boxes, counts, scores, raw_max, labels
+
+
+def post_select(keep, num_keep, order, boxes, scores, labels, P: int):
+    """Back half (`pdab_post_select`): padded (B, P, nb) boxes, (B, P) scores / labels and num (B), zeros behind num."""
+    B, M = order.shape
+    nb = boxes.shape[1]
+    dev = boxes.device
+    out_boxes = torch.empty(B, P, nb, dtype=torch.float32, device=dev)
+    out_scores = torch.empty(B, P, dtype=torch.float32, device=dev)
+    out_labels = torch.empty(B, P, dtype=torch.int64, device=dev)
+    out_num = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("pdab_post_select", B, M, P, nb, boxes.stride(0), keep.data_ptr(), num_keep.data_ptr(), order.data_ptr(),
+                  boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), out_boxes.data_ptr(), out_scores.data_ptr(),
+                  out_labels.data_ptr(), out_num.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    return out_boxes, out_scores, out_labels, out_num

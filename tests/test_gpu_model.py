@@ -324,3 +324,42 @@ def test_train_mode_forward_backward_reaches_every_parameter():
     assert sum(float(g.abs().sum()) > 0 for g in g1.values()) > 0.9 * len(g1)
     with pytest.raises(NotImplementedError):
         model.point_head.get_loss()
+
+
+@pytest.mark.parametrize("name", ["kitti", "once"])
+def test_fused_post_processing_equals_torch_statement(name):
+    """`post_processing_padded` through csrc/post.cu (two kernels around the batched NMS) == the same steps written in torch,
+    bit for bit: scores (same sigmoid expression), labels, the (score desc, index asc) order, counts, kept rows and the
+    zero padding.  Inputs with massive score ties (quantised logits), saturated logits and below-threshold rows."""
+    cfg = load_config(name)
+    torch.manual_seed(0)
+    model = build_model(cfg).cuda().eval()
+    B = 4
+    M = 256 if name == "kitti" else 1024
+    nc = len(cfg.CLASS_NAMES)
+    g = torch.Generator().manual_seed(31)
+    lo, hi = torch.tensor(cfg.POINT_CLOUD_RANGE[:3]), torch.tensor(cfg.POINT_CLOUD_RANGE[3:])
+    for quant in (None, 0.25):
+        logits = torch.randn(B * M, nc, generator=g) * 3
+        if quant:
+            logits = torch.round(logits / quant) * quant
+        logits[::17] = 40.0            # saturated sigmoid: exact ties at 1.0
+        logits[5::23] = -9.0           # below both score thresholds
+        padded = torch.zeros(B * M, 4 * ((nc + 3) // 4))
+        padded[:, :nc] = logits        # the head hands over a column slice of a padded matrix
+        ctr = lo + (hi - lo) * torch.rand(B * M, 3, generator=g)
+        ctr[1::2] = ctr[0::2] + 0.4 * torch.randn(B * M // 2, 3, generator=g)
+        boxes = torch.cat([ctr, 1.0 + 2.0 * torch.rand(B * M, 3, generator=g), 6.28 * torch.rand(B * M, 1, generator=g) - 3.14], dim=1)
+        feed = {"batch_size": B, "batch_cls_preds": padded.cuda()[:, :nc], "batch_box_preds": boxes.cuda(),
+                "cls_preds_normalized": False}
+        with torch.no_grad():
+            model.fused_post_processing = True
+            a = model.post_processing_padded(dict(feed))
+            model.fused_post_processing = False
+            b = model.post_processing_padded(dict(feed))
+            model.fused_post_processing = True
+        assert set(a) == set(b)
+        for k in a:
+            assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+            assert torch.equal(a[k], b[k]), f"{name} quant={quant}: {k} differs"
+        assert int(a["num"].min()) > 0
