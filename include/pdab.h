@@ -182,15 +182,6 @@ int pdab_pda_encode_ln_h(int b, int c, int n, int m, float radius, int nsample, 
 int pdab_pda_assemble_ln_split(long long tokens, int nsample, int c, int xpitch, const float *pos, const float *x,
                                const float *scale, const float *glob, const float *gamma, const float *beta,
                                float eps, float *hi, float *lo, pdab_stream_t stream);
-/* (hi, lo) = split(LayerNorm((a_hi + a_lo) + o)) */
-int pdab_add_ln_split(long long tokens, int e, const float *a_hi, const float *a_lo, const float *o,
-                      const float *gamma, const float *beta, float eps, float *hi, float *lo, pdab_stream_t stream);
-/* (hi, lo) = split(relu(h)), n elements (n % 4 == 0) */
-int pdab_relu_split(long long n, const float *h, float *hi, float *lo, pdab_stream_t stream);
-/* out[g, :] = max over the nsample rows of group g of ((a_hi + a_lo) + f);  out (groups, e) */
-int pdab_add_maxpool(long long groups, int nsample, int e, const float *a_hi, const float *a_lo, const float *f,
-                     float *out, pdab_stream_t stream);
-
 /* Self-attention inside each neighbourhood, all heads: ctx = softmax(q k^T / sqrt(head_dim)) v per (group, head).
  * replaces: the attention core of nn.MultiheadAttention in TransformerEncoderLayerPreNorm (q/k/v permutes, 2 bmm,
  *           softmax, permute back), PB/PointFormer.py:30, PB/pointnet2_modules.py:929.

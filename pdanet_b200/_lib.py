@@ -41,9 +41,6 @@ _SIGNATURES = {
     "pdab_pda_assemble_ln_split": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "pdab_pda_encode_param_floats": (_sz, [_i]),
     "pdab_pda_encode_ln": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
-    "pdab_add_ln_split": (_i, [C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
-    "pdab_relu_split": (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
-    "pdab_add_maxpool": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_group_attention": (_i, [C.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_group_attention_h": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -4,9 +4,8 @@
 // layer_norm launches that each made a full pass over the (tokens x channels) activations:
 //
 //   pdab_pda_assemble_ln_split : cat[pos, feat*scale, feat, glob] -> LayerNorm -> (hi, lo)      (1 read pass, 2 writes)
-//   pdab_add_ln_split          : LayerNorm((a_hi + a_lo) + o) -> (hi, lo)
-//   pdab_relu_split            : relu(h) -> (hi, lo)
-//   pdab_add_maxpool           : max over the ns tokens of a neighbourhood of ((a_hi + a_lo) + f)
+// (the stand-alone residual + LayerNorm, ReLU and max-pool kernels of the first version were removed once those steps had
+// moved into the epilogues of the tensor-core kernels; this one survives as the un-fused-encoder path of pda_block.py)
 //
 // hi keeps the top 19 bits of the fp32 value (exactly representable in TF32), lo = value - hi (exact in fp32),
 // so hi + lo reproduces the value bit for bit and the un-split tensor is never stored.
@@ -107,59 +106,6 @@ assemble_ln_split_kernel(long long T, int ns, int C, int xpitch, const float *__
     layer_norm_split<V4>(v, lane, gamma, beta, eps, hi + row * E, lo ? lo + row * E : nullptr);
 }
 
-template <int V4>
-__global__ void __launch_bounds__(kRowThreads)
-add_ln_split_kernel(long long T, const float *__restrict__ a_hi, const float *__restrict__ a_lo,
-                    const float *__restrict__ o, const float *__restrict__ gamma, const float *__restrict__ beta,
-                    float eps, float *__restrict__ hi, float *__restrict__ lo) {
-    constexpr int E = 128 * V4;
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
-    if (row >= T) return;
-    float4 v[V4];
-#pragma unroll
-    for (int i = 0; i < V4; i++) {
-        const long long off = row * E + (i * 32 + lane) * 4;
-        const float4 h = __ldcs(reinterpret_cast<const float4 *>(a_hi + off));
-        const float4 l = __ldcs(reinterpret_cast<const float4 *>(a_lo + off));
-        const float4 r = __ldcs(reinterpret_cast<const float4 *>(o + off));
-        v[i] = make_float4((h.x + l.x) + r.x, (h.y + l.y) + r.y, (h.z + l.z) + r.z, (h.w + l.w) + r.w);
-    }
-    layer_norm_split<V4>(v, lane, gamma, beta, eps, hi + row * E, lo + row * E);
-}
-
-__global__ void __launch_bounds__(256)
-relu_split_kernel(long long n4, const float4 *__restrict__ h, float4 *__restrict__ hi, float4 *__restrict__ lo) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n4) return;
-    float4 v = __ldcs(h + i);
-    v.x = fmaxf(v.x, 0.f);
-    v.y = fmaxf(v.y, 0.f);
-    v.z = fmaxf(v.z, 0.f);
-    v.w = fmaxf(v.w, 0.f);
-    split_store(v, hi + i, lo + i);
-}
-
-// out[g, :] = max_s ((a_hi + a_lo)[g*ns + s, :] + f[g*ns + s, :]);  thread per (group, float4 of channels)
-__global__ void __launch_bounds__(256)
-add_maxpool_kernel(long long G, int ns, int E4, const float4 *__restrict__ a_hi, const float4 *__restrict__ a_lo,
-                   const float4 *__restrict__ f, float4 *__restrict__ out) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= G * E4) return;
-    const long long g = i / E4;
-    const int c4 = (int)(i - g * E4);
-    float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
-    for (int s = 0; s < ns; s++) {
-        const long long off = (g * ns + s) * E4 + c4;
-        const float4 h = __ldcs(a_hi + off), l = __ldcs(a_lo + off), r = __ldcs(f + off);
-        m.x = fmaxf(m.x, (h.x + l.x) + r.x);
-        m.y = fmaxf(m.y, (h.y + l.y) + r.y);
-        m.z = fmaxf(m.z, (h.z + l.z) + r.z);
-        m.w = fmaxf(m.w, (h.w + l.w) + r.w);
-    }
-    out[i] = m;
-}
-
 int row_grid(long long T, dim3 &grid) {
     const long long blocks = (T + kRowThreads / 32 - 1) / (kRowThreads / 32);
     if (blocks > 2147483647LL) return PDAB_EUNSUPPORTED;
@@ -189,50 +135,6 @@ extern "C" int pdab_pda_assemble_ln_split(long long tokens, int nsample, int c, 
                                                                   beta, eps, hi, lo);
     else
         return PDAB_EUNSUPPORTED;
-    PDAB_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int pdab_add_ln_split(long long tokens, int e, const float *a_hi, const float *a_lo, const float *o,
-                                 const float *gamma, const float *beta, float eps, float *hi, float *lo,
-                                 pdab_stream_t stream) {
-    if (tokens < 0 || !a_hi || !a_lo || !o || !gamma || !beta || !hi || !lo) return PDAB_EINVAL;
-    if (tokens == 0) return 0;
-    dim3 grid;
-    if (int rc = row_grid(tokens, grid)) return rc;
-    cudaStream_t s = pdab::to_stream(stream);
-    if (e == 256)
-        add_ln_split_kernel<2><<<grid, kRowThreads, 0, s>>>(tokens, a_hi, a_lo, o, gamma, beta, eps, hi, lo);
-    else if (e == 512)
-        add_ln_split_kernel<4><<<grid, kRowThreads, 0, s>>>(tokens, a_hi, a_lo, o, gamma, beta, eps, hi, lo);
-    else
-        return PDAB_EUNSUPPORTED;
-    PDAB_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int pdab_relu_split(long long n, const float *h, float *hi, float *lo, pdab_stream_t stream) {
-    if (n < 0 || (n & 3) || !h || !hi || !lo) return PDAB_EINVAL;
-    if (n == 0) return 0;
-    const long long n4 = n / 4;
-    const long long blocks = (n4 + 255) / 256;
-    if (blocks > 2147483647LL) return PDAB_EUNSUPPORTED;
-    relu_split_kernel<<<(unsigned)blocks, 256, 0, pdab::to_stream(stream)>>>(
-        n4, reinterpret_cast<const float4 *>(h), reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo));
-    PDAB_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int pdab_add_maxpool(long long groups, int nsample, int e, const float *a_hi, const float *a_lo,
-                                const float *f, float *out, pdab_stream_t stream) {
-    if (groups < 0 || nsample < 1 || e < 4 || (e & 3) || !a_hi || !a_lo || !f || !out) return PDAB_EINVAL;
-    if (groups == 0) return 0;
-    const long long total = groups * (e / 4);
-    const long long blocks = (total + 255) / 256;
-    if (blocks > 2147483647LL) return PDAB_EUNSUPPORTED;
-    add_maxpool_kernel<<<(unsigned)blocks, 256, 0, pdab::to_stream(stream)>>>(
-        groups, nsample, e / 4, reinterpret_cast<const float4 *>(a_hi), reinterpret_cast<const float4 *>(a_lo),
-        reinterpret_cast<const float4 *>(f), reinterpret_cast<float4 *>(out));
     PDAB_LAUNCH_CHECK();
     return 0;
 }

@@ -409,34 +409,6 @@ def group_attention_h(qkv, nsample, heads):
     return ctx
 
 
-def add_ln_split(a_hi, a_lo, o, norm):
-    T, E = a_hi.shape
-    assert a_hi.is_contiguous() and a_lo.is_contiguous() and o.is_contiguous()
-    hi, lo = torch.empty_like(a_hi), torch.empty_like(a_hi)
-    with torch.cuda.device(a_hi.device):
-        _lib.call("pdab_add_ln_split", T, E, a_hi.data_ptr(), a_lo.data_ptr(), o.data_ptr(), norm.weight.data_ptr(),
-                  norm.bias.data_ptr(), float(norm.eps), hi.data_ptr(), lo.data_ptr(), _stream_of(a_hi))
-    return hi, lo
-
-
-def relu_split(h):
-    assert h.is_contiguous()
-    hi, lo = torch.empty_like(h), torch.empty_like(h)
-    with torch.cuda.device(h.device):
-        _lib.call("pdab_relu_split", h.numel(), h.data_ptr(), hi.data_ptr(), lo.data_ptr(), _stream_of(h))
-    return hi, lo
-
-
-def add_maxpool(a_hi, a_lo, f, groups, nsample):
-    E = a_hi.shape[-1]
-    assert a_hi.is_contiguous() and a_lo.is_contiguous() and f.is_contiguous()
-    out = torch.empty(groups, E, dtype=torch.float32, device=a_hi.device)
-    with torch.cuda.device(a_hi.device):
-        _lib.call("pdab_add_maxpool", groups, nsample, E, a_hi.data_ptr(), a_lo.data_ptr(), f.data_ptr(),
-                  out.data_ptr(), _stream_of(a_hi))
-    return out
-
-
 def sa_fused_supported(c0: int, dims: Sequence[int], nsample: int) -> bool:
     """Shapes the fused plain-SA kernel covers (see csrc/sa_fused.cu)."""
     return len(dims) == 3 and nsample <= 32 and c0 <= 8 and tuple(dims) in ((16, 16, 32), (32, 32, 64))

@@ -208,6 +208,34 @@ def test_no_scale_falls_back_to_the_unfused_grouper(name, B, N):
     assert len(wide._wide) == len(wide.groupers) == (2 if name == "kitti" else 3)
 
 
+@pytest.mark.parametrize("tc_passes", [2, 4])
+def test_pda_unfused_encoder_path_equals_fused_encoder(models, tc_passes):
+    """pda_block.py keeps an un-fused token encoder (pdab_pda_group_tokens + position MLP GEMMs + DensityNet +
+    pdab_pda_assemble_ln_split) for shapes the one-kernel encoder does not cover; with the fused encoder switched off the
+    scale must give the same result (both run the same transformer afterwards)."""
+    cfg, gpu, _ = models
+    g = torch.Generator().manual_seed(13)
+    for layer, (N, C) in ((1, (4096, 64)), (2, (1024, 128))):
+        mod = gpu.backbone_3d.SA_modules[layer]
+        xyz = (torch.rand(2, N, 3, generator=g) * torch.tensor([30.0, 30.0, 2.0])).cuda()
+        feats = torch.randn(2, C, N, generator=g).cuda()
+        cls = torch.randn(2, N, 3, generator=g).cuda()
+        prev = mod.tc_passes
+        try:
+            mod.tc_passes, mod._plans = tc_passes, {}
+            with torch.no_grad():
+                fused = mod(xyz, feats, cls)
+                for plan in mod._plans.values():
+                    assert plan.fused_encode
+                    plan.fused_encode = False
+                unfused = mod(xyz, feats, cls)
+        finally:
+            mod.tc_passes, mod._plans = prev, {}
+        assert torch.equal(fused[3], unfused[3])
+        scale = fused[1].abs().max().item()
+        assert (fused[1] - unfused[1]).abs().max().item() <= 2e-4 * scale
+
+
 def test_pda_group_tokens_matches_channel_major_grouper():
     from pdanet_b200 import pointnet2_utils as ops
     g = torch.Generator().manual_seed(5)
