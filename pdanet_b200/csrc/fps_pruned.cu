@@ -160,13 +160,16 @@ constexpr int kListLo = 6, kListHi = 20;   // the threshold gap is steered to ke
 // Shared memory: coordinates as three planes indexed [((q / 4) * NB * T + bucket) * 4 + q % 4] (a thread fetches four points of
 // its bucket with one LDS.128 per plane; a warp's 32 buckets are 512 contiguous bytes: conflict-free), the original index of
 // every position as u16 behind them: 14 bytes per point, 224 KB at 16384.
-template <int P, int NB, int T, bool CLUSTER>
+// MODE 0: one CTA per scene, rounds.  MODE 1: cluster of 2 / 4 / 8 CTAs per scene, rounds over a list exchanged through
+// distributed shared memory.  MODE 2: cluster of any size up to 16, one sample per step (the round-1 protocol).
+template <int P, int NB, int T, int MODE>
 __global__ void __launch_bounds__(T, 1)
 fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
                   int *__restrict__ idx_all, int L, int CL) {
     constexpr int NBT = NB * T;        // buckets per CTA
     constexpr int CAP = NBT * P;
     constexpr int kWarps = T / 32;
+    constexpr bool CLUSTER = MODE != 0;
     constexpr int V = P < 4 ? P : 4;   // points of one bucket that sit side by side in a plane: one LDS.(32 V) fetches them
     static_assert(P % V == 0 && (V == 1 || V == 2 || V == 4), "bucket rows");
     static_assert(kWarps <= 32, "CTA argmax: one lane per warp");
@@ -179,12 +182,14 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
     float *sx = reinterpret_cast<float *>(smem_raw), *sy = sx + CAP, *sz = sy + CAP;
     unsigned short *sorig = reinterpret_cast<unsigned short *>(smem_raw + (size_t)12 * CAP);
     // static shared memory is scarce (3 KB beside the 224 KB of a full scene): one block carved per mode.
-    //   cluster: red[2][32] (1 KB) | xchg[2][kMaxCluster] (1 KB)      rounds: list[2][kMaxList] (2 KB) | ranked[kMaxList] (768 B)
-    //   (the fallback's red[32] shares the bytes of `ranked`: a round runs one or the other, both between its two barriers)
+    //   steps (MODE 2): red[2][32] (1 KB) | xchg[2][kMaxCluster] (1 KB)
+    //   rounds:         list[2][kMaxList] (2 KB) | ranked[kMaxList] (768 B); a fallback round uses the bytes of `ranked` as
+    //                   red[32] (512 B) | fxchg[8] (256 B) instead — a round runs one or the other, between its two barriers
     __shared__ __align__(16) unsigned char sstat[2048 + 768];
     __shared__ int sbox[6];
     __shared__ int scount[3];                            // list lengths, rotating: a counter is zeroed a full round before its use
-    __shared__ __align__(8) unsigned long long xbar[2];  // mbarriers: the candidates of all CL CTAs have landed in xchg[buf]
+    __shared__ __align__(8) unsigned long long xbar[3];  // mbarriers: the candidates / lists of all CL CTAs have landed in buffer
+                                                         // [buf]; [2]: the fallback candidates of a cluster round
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     unsigned rank = 0;
@@ -200,7 +205,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
     int *idxs = idx_all + (size_t)scene * m;
     if (CLUSTER) {
         if (t == 0) {
-            for (int i = 0; i < 2; i++)
+            for (int i = 0; i < 3; i++)
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&xbar[i])));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -213,7 +218,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
     if (t < 3) sbox[t] = 0x7fffffff;
     else if (t < 6) sbox[t] = (int)0x80000000;
     if (t < 3) scount[t] = 0;
-    if (CLUSTER && t < 64) reinterpret_cast<WarpBest *>(sstat)[t].key = 0ull;   // lanes beyond kWarps never win the CTA argmax
+    if (MODE == 2 && t < 64) reinterpret_cast<WarpBest *>(sstat)[t].key = 0ull;   // lanes beyond kWarps never win the CTA argmax
     __syncthreads();
     {
         float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
@@ -484,14 +489,52 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
     unsigned tick_ = (unsigned)clock();
 #endif
 
-    if constexpr (!CLUSTER) {
+    // mbarrier helpers of the cluster modes (a CTA waits on its own barrier for the bytes its peers st.async into it)
+    auto bar_expect = [&](unsigned bar, int bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    };
+    auto bar_wait = [&](unsigned bar, unsigned parity) {
+        unsigned ok = 0;
+        const long long t0 = clock64();
+        while (!ok) {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+            if (!ok && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU on a protocol bug
+        }
+    };
+    // 16 bytes into the same shared-memory offset of CTA `peer`, completing on that CTA's barrier
+    auto send16 = [&](unsigned local_addr, unsigned local_bar, int peer, unsigned a, unsigned b, unsigned c, unsigned e) {
+        unsigned dst, rbar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(local_addr), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(peer));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                     "r"(a), "r"(b), "r"(c), "r"(e), "r"(rbar)
+                     : "memory");
+    };
+
+    if constexpr (MODE != 2) {
         // ======================= rounds: several samples per barrier pair (header: ROUNDS) =================================
+        // MODE 1: the list is global — CTA r owns slots [r S, r S + S), S = kMaxList / CL, fills them from its own threads and
+        // sends them to every CTA of the cluster (zero-padded; a CTA with more than S candidates sends an overflow mark), so
+        // all CTAs rank the same 32 slots and take the same decisions.  Buffer reuse: a peer sends round r + 2 only after it
+        // has consumed round r + 1, which needs this CTA's round r + 1 segment, sent after this CTA's barrier of round r + 1,
+        // i.e. after all its threads are through with round r's buffer.
         RoundCand(*list)[kMaxList] = reinterpret_cast<RoundCand(*)[kMaxList]>(sstat);
-        RankedCand *ranked = reinterpret_cast<RankedCand *>(sstat + 2048);   // shares its bytes with `red` (exclusive per round)
+        RankedCand *ranked = reinterpret_cast<RankedCand *>(sstat + 2048);
         WarpBest *red = reinterpret_cast<WarpBest *>(sstat + 2048);
+        Candidate *fxchg = reinterpret_cast<Candidate *>(sstat + 2048 + 512);
+        const int S = MODE == 1 ? kMaxList / CL : kMaxList;
+        const int seg = (int)rank * S;
+        constexpr unsigned long long kOverflow = ~0ull;   // not a key: its distance bits would be a NaN
         // the samples whose insertion is pending live in lanes 0 .. npend-1 of EVERY warp
         float psx = __ldg(xyz0 + 0), psy = __ldg(xyz0 + 1), psz = __ldg(xyz0 + 2);
         int npend = 1, it = 1, buf = 0, cb = 0;
+        unsigned lpar = 0u, fpar = 0u;   // parities of the list barriers (bit buf) and of the fallback barrier
         float vref = 0.f, gap = 0.25f;   // tau = vref * (1 - gap); vref = min-distance of the last accepted sample
         while (m > 1) {
             // -- insert the pending samples.  Per block j of the warp: lane r tests sample r against the block's sphere (one
@@ -540,17 +583,42 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
                 c.sec = mysec;
                 c.pad0 = c.pad1 = 0.f;
                 slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(pm & ((1u << lane) - 1u));
-                if (push && slot < kMaxList) list[buf][slot] = c;
+                if (push && slot < S) list[buf][seg + slot] = c;
             }
             const int cnext = cb == 2 ? 0 : cb + 1;
             if (t == 0) scount[cnext] = 0;   // last read two rounds ago, next used after the coming barrier
             PDAB_FPS_TICK(1, pm);
             __syncthreads();
-            const int nc = scount[cb];
+            const int nloc = scount[cb];
+            unsigned vm;           // valid slots of the list
+            bool fallback;         // empty list (tau too high) or an overflowing segment (ties en masse): plain argmax this round
+            bool overflow;
+            if constexpr (MODE == 1) {
+                const unsigned lbar = (unsigned)__cvta_generic_to_shared(&xbar[buf]);
+                if (t == 0) bar_expect(lbar, CL * S * 32);
+                if (t < 2 * S) {   // lane pair e: the two halves of slot e of this CTA's segment
+                    const int e = t >> 1, h = t & 1;
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(&list[buf][seg + e]) + 16u * h;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (e < nloc && nloc <= S) v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(&list[buf][seg + e]) + 16 * h);
+                    if (nloc > S && e == 0 && h == 0) v.x = v.y = 0xffffffffu;
+                    for (int peer = 0; peer < CL; peer++) send16(src, lbar, peer, v.x, v.y, v.z, v.w);
+                }
+                bar_wait(lbar, (lpar >> buf) & 1u);
+                lpar ^= 1u << buf;
+                const unsigned long long k = list[buf][lane].key;
+                overflow = __any_sync(0xffffffffu, k == kOverflow);
+                vm = __ballot_sync(0xffffffffu, k != 0ull && k != kOverflow);
+            } else {
+                overflow = nloc > kMaxList;
+                vm = nloc >= 32 ? 0xffffffffu : ((1u << nloc) - 1u);
+            }
+            const int nc = __popc(vm);
+            fallback = overflow || nc == 0;
             PDAB_FPS_TICK(2, (unsigned)nc);
             int A;
-            if (nc == 0 || nc > kMaxList) {
-                // -- plain 2-level argmax (empty list: tau too high; overflow: ties en masse) -----------------------------
+            if (fallback) {
+                // -- plain 2-level argmax ----------------------------------------------------------------------------------------
                 const unsigned long long wkey = warp_max_u64(mykey);
                 const unsigned owner = __ballot_sync(0xffffffffu, mykey == wkey);
                 const int wpos = __shfl_sync(0xffffffffu, mypos, __ffs(owner) - 1);
@@ -561,22 +629,44 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
                 __syncthreads();
                 const unsigned long long rkey = lane < kWarps ? red[lane].key : 0ull;
                 const int rpos = lane < kWarps ? red[lane].pos : 0;
-                const unsigned long long best = warp_max_u64(rkey);
+                unsigned long long best = warp_max_u64(rkey);
                 const unsigned src = __ballot_sync(0xffffffffu, rkey == best);
                 const int slot = __shfl_sync(0xffffffffu, rpos, __ffs(src) - 1);
-                if (t == 0) idxs[it] = tie_key_decode(~(unsigned)best, L);
                 psx = sx[slot];
                 psy = sy[slot];
                 psz = sz[slot];
+                if constexpr (MODE == 1) {
+                    // the CL local winners, as in the step protocol (fxchg is written by the peers of THIS fallback round only:
+                    // they get here after this CTA's list of the round, sent after its threads left the previous fallback)
+                    const unsigned fbar = (unsigned)__cvta_generic_to_shared(&xbar[2]);
+                    if (t == 0) bar_expect(fbar, CL * 32);
+                    if (t < CL) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(&fxchg[rank]);
+                        const bool any = best != 0ull;
+                        send16(dst, fbar, t, (unsigned)best, (unsigned)(best >> 32), any ? __float_as_uint(psx) : 0u,
+                               any ? __float_as_uint(psy) : 0u);
+                        send16(dst + 16u, fbar, t, any ? __float_as_uint(psz) : 0u, 0u, 0u, 0u);
+                    }
+                    bar_wait(fbar, fpar);
+                    fpar ^= 1u;
+                    const unsigned long long mine = lane < CL ? fxchg[lane].key : 0ull;
+                    best = warp_max_u64(mine);
+                    const int wi = __ffs(__ballot_sync(0xffffffffu, mine == best && lane < CL)) - 1;
+                    psx = fxchg[wi].x;
+                    psy = fxchg[wi].y;
+                    psz = fxchg[wi].z;
+                }
+                if (t == 0 && rank == 0) idxs[it] = tie_key_decode(~(unsigned)best, L);
                 vref = __uint_as_float((unsigned)(best >> 32));
-                gap = nc == 0 ? fminf(gap * 4.f, 0.5f) : fmaxf(gap * 0.25f, 1e-7f);
+                gap = overflow ? fmaxf(gap * 0.25f, 1e-7f) : fminf(gap * 4.f, 0.5f);
                 A = 1;
-                PDAB_FPS_COUNT(nc == 0 ? 5 : 6, 1);
+                PDAB_FPS_COUNT(overflow ? 6 : 5, 1);
             } else {
-                // -- rank the candidates: warp w takes candidates w, w + kWarps, ...; lane j holds candidate j ------------------
-                const bool valid = lane < nc;
-                const RoundCand cj = list[buf][valid ? lane : 0];
-                for (int i = warp; i < nc; i += kWarps) {
+                // -- rank the candidates: warp w takes slots w, w + kWarps, ...; lane j holds slot j ---------------------------
+                const bool valid = (vm >> lane) & 1u;
+                const RoundCand cj = list[buf][lane];
+                for (int i = warp; i < kMaxList; i += kWarps) {
+                    if (!((vm >> i) & 1u)) continue;
                     const RoundCand me = list[buf][i];   // broadcast
                     const float vme = __uint_as_float((unsigned)(me.key >> 32));
                     const bool gt = valid && cj.key > me.key;
@@ -598,13 +688,13 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
                 }
                 __syncthreads();
                 // -- accept the longest prefix without a blocked candidate; lane r keeps the sample of rank r ----------------
-                const RankedCand mine = ranked[valid ? lane : 0];
-                A = __reduce_min_sync(0xffffffffu, (valid && mine.blocked) ? lane : nc);
+                const RankedCand mine = ranked[lane < nc ? lane : 0];
+                A = __reduce_min_sync(0xffffffffu, (lane < nc && mine.blocked) ? lane : nc);
                 A = min(A, m - it);
                 psx = mine.x;
                 psy = mine.y;
                 psz = mine.z;
-                if (warp == 0 && lane < A) idxs[it + lane] = tie_key_decode(~mine.low, L);
+                if (warp == 0 && rank == 0 && lane < A) idxs[it + lane] = tie_key_decode(~mine.low, L);
                 vref = __shfl_sync(0xffffffffu, mine.val, A - 1);
                 if (nc < kListLo) gap = fminf(gap * 1.5f, 0.5f);
                 else if (nc > kListHi) gap = fmaxf(gap * (1.f / 1.5f), 1e-7f);
@@ -618,7 +708,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
             cb = cnext;
         }
     } else {
-        // ======================= cluster: one sample per step, candidates exchanged over DSMEM =============================
+        // ======================= MODE 2: one sample per step, candidates exchanged over DSMEM ==============================
         WarpBest(*red)[32] = reinterpret_cast<WarpBest(*)[32]>(sstat);
         Candidate(*xchg)[kMaxCluster] = reinterpret_cast<Candidate(*)[kMaxCluster]>(sstat + 1024);
         unsigned long long wkey = 0ull;
@@ -718,17 +808,19 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ xyz_all, float *
 }
 
 template <int P, int NB, int T>
-int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, int CL, cudaStream_t stream) {
+int launch(int b, int n, int m, const float *xyz, float *temp, int *idx, int L, int CL, cudaStream_t stream, bool steps_only = false) {
     constexpr int CAP = P * NB * T;
     const size_t smem = (size_t)12 * CAP + (size_t)2 * CAP;
     if (CL == 1) {
-        auto kern = fps_pruned_kernel<P, NB, T, false>;
+        auto kern = fps_pruned_kernel<P, NB, T, 0>;
         PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<b, T, smem, stream>>>(n, m, xyz, temp, idx, L, 1);
         PDAB_LAUNCH_CHECK();
         return 0;
     }
-    auto kern = fps_pruned_kernel<P, NB, T, true>;
+    // rounds need the 32 list slots split evenly over the CTAs, at least 4 each
+    const bool rounds = steps_only ? false : (CL == 2 || CL == 4 || CL == 8);
+    auto kern = rounds ? fps_pruned_kernel<P, NB, T, 1> : fps_pruned_kernel<P, NB, T, 2>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -777,6 +869,7 @@ int fps_pruned(int b, int n, int m, const float *xyz, float *temp, int *idx, int
         case 15: return launch<8, 2, 256>(b, n, m, xyz, temp, idx, L, CL, stream);
         case 16: return launch<16, 1, 256>(b, n, m, xyz, temp, idx, L, CL, stream);
         case 17: return launch<8, 4, 128>(b, n, m, xyz, temp, idx, L, CL, stream);
+        case 20: return launch<16, 2, 512>(b, n, m, xyz, temp, idx, L, CL, stream, true);   // cluster: one sample per step
         default: break;
     }
 #endif

@@ -113,6 +113,58 @@ def test_fps_bit_exact_vs_reference_kernel(ops, ref_pointnet2, tag, B, N, m, kw)
     assert torch.equal(temp.cpu(), want_temp)  # the scratch buffer ends in the same state too
 
 
+# long chains on clusters: the rounds of the batched kernel (several samples per list exchange) only get going after a few
+# hundred samples; the cluster size is pinned through the launch policy so that 2, 4, 8 (rounds) and 16 (steps) are all run
+CLUSTER_ROUND_CASES = [
+    ("cl2_30000_m1500", 2, 1, 30000, 1500, {}),
+    ("cl4_once_m2048", 4, 1, 65536, 2048, {}),
+    ("cl4_ties_m1200", 4, 2, 50000, 1200, dict(quantize=0.5, duplicate_frac=0.1)),
+    ("cl8_once_m1024", 8, 1, 65536, 1024, {}),
+    ("cl8_ragged_m900", 8, 1, 100003, 900, dict(duplicate_frac=0.02)),
+    ("cl16_262144_m300", 16, 1, 262144, 300, {}),
+]
+
+
+@pytest.mark.parametrize("tag,cl,B,N,m,kw", CLUSTER_ROUND_CASES, ids=[c[0] for c in CLUSTER_ROUND_CASES])
+def test_fps_cluster_rounds_bit_exact_vs_reference_kernel(ops, ref_pointnet2, tag, cl, B, N, m, kw):
+    from pdanet_b200 import _lib, pointnet2_batch_cuda
+    xyz = scene_xyz(seed_of(tag), B, N, **kw)
+    want_idx, want_temp = ref_fps(ref_pointnet2, xyz, m)
+    x = dev(xyz)
+    temp = torch.full((B, N), 1e10, device="cuda")
+    idx = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    lib = _lib.lib()
+    _lib.check("pdab_set_fps_max_cluster", lib.pdab_set_fps_max_cluster(cl))
+    try:
+        pointnet2_batch_cuda.farthest_point_sampling_wrapper(B, N, m, x, temp, idx)
+        torch.cuda.synchronize()
+    finally:
+        lib.pdab_set_fps_max_cluster(16)
+    assert torch.equal(idx.cpu(), want_idx)
+    assert torch.equal(temp.cpu(), want_temp)
+
+
+def test_fps_once_l0_full_size_vs_reference_kernel(ops, ref_pointnet2):
+    """ONCE L0 at full size (65536 -> 16384, a 0.2 s run of the reference kernel): idx and temp, clusters of 4 (what the
+    pipelined runner uses at batch 32) and of 8."""
+    from pdanet_b200 import _lib, pointnet2_batch_cuda
+    B, N, m = 1, 65536, 16384
+    xyz = scene_xyz(seed_of("once_l0_full"), B, N)
+    want_idx, want_temp = ref_fps(ref_pointnet2, xyz, m)
+    lib = _lib.lib()
+    for cl in (4, 8):
+        temp = torch.full((B, N), 1e10, device="cuda")
+        idx = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+        _lib.check("pdab_set_fps_max_cluster", lib.pdab_set_fps_max_cluster(cl))
+        try:
+            pointnet2_batch_cuda.farthest_point_sampling_wrapper(B, N, m, dev(xyz), temp, idx)
+            torch.cuda.synchronize()
+        finally:
+            lib.pdab_set_fps_max_cluster(16)
+        assert torch.equal(idx.cpu(), want_idx), cl
+        assert torch.equal(temp.cpu(), want_temp), cl
+
+
 def test_fps_full_kitti_and_once_sizes_properties(ops):
     """At BASELINE sizes the oracle is too slow to run per test: check size-independent properties —
     first index 0, all distinct, non-increasing selection distance, and agreement of the prefix with the oracle."""
