@@ -230,7 +230,7 @@ def algorithmic_bytes(key: str, batch: int):
         b, c, n, m = a[:4]
         ns = a[4] if len(a) > 4 else 16     # (radius is a float and not in the key; nsample is)
         return b * (12 * n + 4 * c * n + 12 * m + 4 * c * m + 16 * c * m * ns)   # output (tokens, 4c) at 4 B dominates
-    if name == "pdab_sa_fused_pair":
+    if name in ("pdab_sa_fused_pair", "pdab_sa_fused_pair_h"):
         b, c, n, m = a[:4]
         return b * (12 * n + 4 * c * n + 12 * m + 4 * 96 * m)   # both scales: 32 + 64 output channels per centre
     if name == "pdab_group_attention":
@@ -251,7 +251,7 @@ KERNEL_OF = {"pdab_tc_linear": "tc_gemm_kernel", "pdab_tc_linear_h": "tc_gemm_ke
              "pdab_tc_sa_gather_linear_h": "tc_gemm_kernel", "pdab_fps": "fps_kernel", "pdab_fps_with_dist": "fps_kernel",
              "pdab_pda_encode_ln": "pda_encode_ln_kernel", "pdab_pda_encode_ln_h": "pda_encode_ln_kernel",
              "pdab_group_attention": "group_attention_kernel", "pdab_group_attention_h": "group_attention_kernel",
-             "pdab_sa_fused_pair": "sa_fused_pair_kernel", "pdab_tc_ffn_h": "ffn_fused_kernel"}
+             "pdab_sa_fused_pair": "sa_fused_pair_kernel", "pdab_sa_fused_pair_h": "sa_fused_pair_kernel", "pdab_tc_ffn_h": "ffn_fused_kernel"}
 
 # tensor-pipe work per algorithmic flop, in bf16-MMA flops: split-bf16 ("bf16x3") issues 3 bf16 MMAs per product, 3xTF32
 # issues 3 TF32 MMAs (a TF32 MMA occupies the pipe like 2 bf16 MMAs), plain TF32 one
@@ -282,7 +282,7 @@ def algorithmic_flops(key: str):
         b, c, n, m, ns, nout = a[:6]
         f = 2.0 * b * m * ns * (c + 3) * nout
         return f, f * MMA_COST[4]
-    if name == "pdab_sa_fused_pair":       # L0: (4 -> 16 -> 16 -> 32) x ns_a + (4 -> 32 -> 32 -> 64) x ns_b rows per centre
+    if name in ("pdab_sa_fused_pair", "pdab_sa_fused_pair_h"):       # L0: (4 -> 16 -> 16 -> 32) x ns_a + (4 -> 32 -> 32 -> 64) x ns_b rows per centre
         b, c, n, m = a[:4]
         ns_a, ns_b = 16, 32
         f = 2.0 * b * m * (ns_a * ((3 + c) * 16 + 16 * 16 + 16 * 32) + ns_b * ((3 + c) * 32 + 32 * 32 + 32 * 64))
@@ -426,7 +426,7 @@ def run_gpu_arm(args, cfg, n_points, batch):
                 "pdab_ball_query": "group", "pdab_gather_points": "group", "pdab_group_points": "group",
                 "pdab_pda_group": "group", "pdab_pda_group_tokens": "group", "pdab_pda_encode_ln": "group_encode_pda",
                 "pdab_pda_assemble_ln_split": "group_encode_pda", "pdab_sa_fused": "fused_group_mlp_maxpool",
-                "pdab_sa_fused_pair": "fused_group_mlp_maxpool", "pdab_tc_sa_gather_linear": "fused_group_mlp_maxpool",
+                "pdab_sa_fused_pair": "fused_group_mlp_maxpool", "pdab_sa_fused_pair_h": "fused_group_mlp_maxpool", "pdab_tc_sa_gather_linear": "fused_group_mlp_maxpool",
                 "pdab_tc_linear": "mlp_gemm", "pdab_group_attention": "attention", "pdab_nms_batched": "nms",
                 "pdab_tc_linear_h": "mlp_gemm", "pdab_tc_sa_gather_linear_h": "fused_group_mlp_maxpool",
                 "pdab_pda_encode_ln_h": "group_encode_pda", "pdab_group_attention_h": "attention",

@@ -220,6 +220,14 @@ int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a
                        const float *xyz, const float *new_xyz, const float *features, const int *dims_a_host,
                        const int *dims_b_host, const float *const *weights_host, const float *const *biases_host,
                        float *out, void *workspace, pdab_stream_t stream);
+/* The same layer with the MLP contractions as fp16 x fp16 single-pass products (fp32 accumulation, bias / ReLU / max in fp32):
+ * the product class of the `_h` tensor-core entry points and of the TF32 cuDNN convolutions the reference runs these layers
+ * as (PB/pointnet2_modules.py:1655-1672); the neighbour lists are the same bit for bit, features differ by <= 1e-3 relative.
+ * One mma.sync per product instead of three. */
+int pdab_sa_fused_pair_h(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
+                         const float *xyz, const float *new_xyz, const float *features, const int *dims_a_host,
+                         const int *dims_b_host, const float *const *weights_host, const float *const *biases_host,
+                         float *out, void *workspace, pdab_stream_t stream);
 /* workspace: NULL = every centre scans the whole cloud (M * N distance tests per scene); otherwise a device buffer of
  * pdab_sa_grid_workspace_bytes(b, n) bytes (16-byte aligned): the call first buckets every scene's points into a hashed
  * cell list (cell edge = the larger radius, + 0.1 %) and the centres then test only the 27 cells around them, keeping the

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "pdab_group_attention_h": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _vp]),
     "pdab_sa_fused": (_i, [_i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_fused_pair": (_i, [_i, _i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pdab_sa_fused_pair_h": (_i, [_i, _i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdab_sa_grid_workspace_bytes": (_sz, [_i, _i]),
     "pdab_tc_linear": (_i, [C.c_longlong, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _i, _vp]),
     "pdab_tc_linear_h": (_i, [C.c_longlong, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i,
@@ -115,7 +116,7 @@ def check(fn: str, code: int) -> int:
 
 
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches` count)
-KERNELS_PER_CALL = {"pdab_nms_device": 2, "pdab_nms_batched": 2, "pdab_nms_host": 2, "pdab_sa_fused_pair": 2, "pdab_ball_query_grid": 3}
+KERNELS_PER_CALL = {"pdab_nms_device": 2, "pdab_nms_batched": 2, "pdab_nms_host": 2, "pdab_sa_fused_pair": 2, "pdab_sa_fused_pair_h": 2, "pdab_ball_query_grid": 3}
 
 launch_counts: dict = {}      # entry point -> number of kernels launched through `call`
 _timing = None                # when enabled: entry point -> list of (start_event, end_event)

@@ -180,7 +180,69 @@ __device__ __forceinline__ void mma_layer16(const unsigned *sWh, const unsigned 
         for (int e = 0; e < 4; e++) out[nt][e] = fmaxf(out[nt][e], 0.f);
 }
 
-template <int C0P, int C1, int C2, int C3>
+// ---- the fp16 single-pass form of the three layers (the `_h` entry point; the product class of the big GEMMs' fp16 mode:
+// 11-bit operands, fp32 accumulation — what the reference's cuDNN convolutions run as TF32).  ONE mma.sync m16n8k16 per
+// (k-step, n-tile) instead of three, no operand splitting; layer 1 pads its 4..8 inputs to one k16 step (lanes t < C0P / 2
+// hold the channel pair 2t, 2t+1; the upper eight k are zero, so the second B register is a literal 0).
+__device__ __forceinline__ unsigned pack_f16x2(float x0, float x1) {
+    unsigned r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    return r;
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__host__ __device__ constexpr int p1h() { return 4; }   // layer-1 fp16 image: words 0..3 of a row = channel pairs (k < 8)
+
+// layer 1: a0 / a1 = the packed channel pair (2t, 2t+1) of rows g / g + 8
+template <int N>
+__device__ __forceinline__ void mma_layer1_h(const unsigned *sW, const float *sb, int g, int t, unsigned a0, unsigned a1,
+                                             float (&out)[N / 8][4]) {
+    const unsigned a[4] = {a0, a1, 0u, 0u};
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++) {
+        const float b0 = sb[nt * 8 + 2 * t], b1 = sb[nt * 8 + 2 * t + 1];
+        out[nt][0] = b0;
+        out[nt][1] = b1;
+        out[nt][2] = b0;
+        out[nt][3] = b1;
+        mma_f16(out[nt], a, sW[(nt * 8 + g) * p1h() + t], 0u);
+#pragma unroll
+        for (int e = 0; e < 4; e++) out[nt][e] = fmaxf(out[nt][e], 0.f);
+    }
+}
+
+template <int K, int N>
+__device__ __forceinline__ void mma_layer16_h(const unsigned *sW, const float *sb, int g, int t, const float (&in)[K / 8][4],
+                                              float (&out)[N / 8][4]) {
+    constexpr int P = p16(K);
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++) {
+        const float b0 = sb[nt * 8 + 2 * t], b1 = sb[nt * 8 + 2 * t + 1];
+        out[nt][0] = b0;
+        out[nt][1] = b1;
+        out[nt][2] = b0;
+        out[nt][3] = b1;
+    }
+#pragma unroll
+    for (int s = 0; s < K / 16; s++) {
+        const unsigned a[4] = {pack_f16x2(in[2 * s][0], in[2 * s][1]), pack_f16x2(in[2 * s][2], in[2 * s][3]),
+                               pack_f16x2(in[2 * s + 1][0], in[2 * s + 1][1]), pack_f16x2(in[2 * s + 1][2], in[2 * s + 1][3])};
+#pragma unroll
+        for (int nt = 0; nt < N / 8; nt++) {
+            const int w = (nt * 8 + g) * P + s * 8 + t;
+            mma_f16(out[nt], a, sW[w], sW[w + 4]);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) out[nt][e] = fmaxf(out[nt][e], 0.f);
+}
+
+template <int C0P, int C1, int C2, int C3, bool H = false>
 __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, const float *__restrict__ xyz,
                                           const float *__restrict__ features, const float *sW1, const float *sb1,
                                           const unsigned *sW2, const float *sb2, const unsigned *sW3, const float *sb3,
@@ -194,7 +256,8 @@ __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, c
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
             const int jl = min(base + (whole ? 0 : mt), nctr - 1);  // tail: duplicate the last centre (idempotent store)
-            // layer-1 A fragments straight from the cloud: rows r0 = 16 mt + g and r0 + 8, columns t (and t + 4)
+            // layer-1 A fragments straight from the cloud: rows r0 = 16 mt + g and r0 + 8, columns t and t + 4 (TF32 k8) or
+            // the pair 2t, 2t + 1 (fp16 k16)
             float in[2][2];
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
@@ -202,7 +265,7 @@ __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, c
                 const int k = sidx[min(row, nsample - 1) * kStride + jl];
 #pragma unroll
                 for (int cc = 0; cc < 2; cc++) {
-                    const int col = t + 4 * cc;
+                    const int col = H ? 2 * t + cc : t + 4 * cc;
                     float v = 0.f;
                     if (col < 3) v = __ldg(xyz + (size_t)k * 3 + col) - sctr[jl * 3 + col];  // grouped_xyz -= new_xyz
                     else if (col - 3 < c && col < C0P) v = __ldg(features + (size_t)(col - 3) * n + k);
@@ -210,14 +273,21 @@ __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, c
                 }
             }
             float h1[C1 / 8][4], h2[C2 / 8][4], h3[C3 / 8][4];
-            mma_layer<C0P, C1>(sW1, sb1, g, t, [&](int, float (&a)[4]) {
-                a[0] = in[0][0];
-                a[1] = in[1][0];
-                a[2] = in[0][1];
-                a[3] = in[1][1];
-            }, h1);
-            mma_layer16<C1, C2>(sW2, sW2 + C2 * p16(C1), sb2, g, t, h1, h2);
-            mma_layer16<C2, C3>(sW3, sW3 + C3 * p16(C2), sb3, g, t, h2, h3);
+            if constexpr (H) {
+                mma_layer1_h<C1>(reinterpret_cast<const unsigned *>(sW1), sb1, g, t, pack_f16x2(in[0][0], in[0][1]),
+                                 pack_f16x2(in[1][0], in[1][1]), h1);
+                mma_layer16_h<C1, C2>(sW2, sb2, g, t, h1, h2);
+                mma_layer16_h<C2, C3>(sW3, sb3, g, t, h2, h3);
+            } else {
+                mma_layer<C0P, C1>(sW1, sb1, g, t, [&](int, float (&a)[4]) {
+                    a[0] = in[0][0];
+                    a[1] = in[1][0];
+                    a[2] = in[0][1];
+                    a[3] = in[1][1];
+                }, h1);
+                mma_layer16<C1, C2>(sW2, sW2 + C2 * p16(C1), sb2, g, t, h1, h2);
+                mma_layer16<C2, C3>(sW3, sW3 + C3 * p16(C2), sb3, g, t, h2, h3);
+            }
             // max over the 16 rows of this m-tile: rows g / g+8 in the thread, then over g by shuffles
 #pragma unroll
             for (int nt = 0; nt < C3 / 8; nt++)
@@ -262,6 +332,24 @@ __device__ __forceinline__ void stage_weights16(unsigned *sW, const float *__res
         split_bf16x2(W[r * K + 2 * j], W[r * K + 2 * j + 1], hi, lo);
         sW[r * P + j] = hi;
         sWl[r * P + j] = lo;
+    }
+}
+
+// fp16 images (the `_h` kernels).  Layer 1: W (rows x kreal) -> rows of p1h() words, word j = channels 2j, 2j+1 (zero padded
+// to 8 channels).  Layers 2, 3: W (rows x K) -> rows of pitch p16(K) words (the hi image's layout; no lo image).
+__device__ __forceinline__ void stage_weights1_h(unsigned *sW, const float *__restrict__ W, int rows, int kreal) {
+    for (int i = threadIdx.x; i < rows * p1h(); i += kMlpThreads) {
+        const int r = i / p1h(), j = i - r * p1h();
+        const float w0 = 2 * j < kreal ? W[r * kreal + 2 * j] : 0.f, w1 = 2 * j + 1 < kreal ? W[r * kreal + 2 * j + 1] : 0.f;
+        sW[i] = pack_f16x2(w0, w1);
+    }
+}
+template <int K>
+__device__ __forceinline__ void stage_weights16_h(unsigned *sW, const float *__restrict__ W, int rows) {
+    constexpr int P = p16(K);
+    for (int i = threadIdx.x; i < rows * (K / 2); i += kMlpThreads) {
+        const int r = i / (K / 2), j = i - r * (K / 2);
+        sW[r * P + j] = pack_f16x2(W[r * K + 2 * j], W[r * K + 2 * j + 1]);
     }
 }
 
@@ -354,7 +442,8 @@ int launch_narrow(int b, int c, int n, int m, float radius, int nsample, const f
 // along the channel axis as PB/pointnet2_modules.py:1674 (torch.cat of the scales) wants it.
 // GRID: the hit lists come from the scene's hashed cell list (grid_build_kernel, ball_scan.cuh) instead of a scan of the
 // whole cloud — 27 cells per centre instead of N points; same lists, bit-identical outputs.
-template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3, bool GRID>
+// H: the fp16 single-pass form of the MLP phase (same shared-memory carve-up; the fp16 images use the front of each slot).
+template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3, bool GRID, bool H>
 __global__ void __launch_bounds__(kMlpThreads, 2)
 sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns_b, const unsigned char *__restrict__ ws,
                      float inv_edge, const float *__restrict__ xyz,
@@ -385,12 +474,22 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     xyz += (size_t)scene * n * 3;
     if (c > 0) features += (size_t)scene * c * n;
 
-    stage_weights<C0P>(sWa1, Wa1, A1, c0);
-    stage_weights<C0P>(sWb1, Wb1, B1, c0);
-    stage_weights16<A1>(reinterpret_cast<unsigned *>(sWa2), Wa2, A2);
-    stage_weights16<A2>(reinterpret_cast<unsigned *>(sWa3), Wa3, A3);
-    stage_weights16<B1>(reinterpret_cast<unsigned *>(sWb2), Wb2, B2);
-    stage_weights16<B2>(reinterpret_cast<unsigned *>(sWb3), Wb3, B3);
+    if constexpr (H) {
+        static_assert(C0P <= 8 && p1h() <= wpitch(C0P), "layer-1 fp16 image fits the fp32 slot");
+        stage_weights1_h(reinterpret_cast<unsigned *>(sWa1), Wa1, A1, c0);
+        stage_weights1_h(reinterpret_cast<unsigned *>(sWb1), Wb1, B1, c0);
+        stage_weights16_h<A1>(reinterpret_cast<unsigned *>(sWa2), Wa2, A2);
+        stage_weights16_h<A2>(reinterpret_cast<unsigned *>(sWa3), Wa3, A3);
+        stage_weights16_h<B1>(reinterpret_cast<unsigned *>(sWb2), Wb2, B2);
+        stage_weights16_h<B2>(reinterpret_cast<unsigned *>(sWb3), Wb3, B3);
+    } else {
+        stage_weights<C0P>(sWa1, Wa1, A1, c0);
+        stage_weights<C0P>(sWb1, Wb1, B1, c0);
+        stage_weights16<A1>(reinterpret_cast<unsigned *>(sWa2), Wa2, A2);
+        stage_weights16<A2>(reinterpret_cast<unsigned *>(sWa3), Wa3, A3);
+        stage_weights16<B1>(reinterpret_cast<unsigned *>(sWb2), Wb2, B2);
+        stage_weights16<B2>(reinterpret_cast<unsigned *>(sWb3), Wb3, B3);
+    }
     for (int i = t; i < A1; i += kMlpThreads) sba1[i] = ba1[i];
     for (int i = t; i < A2; i += kMlpThreads) sba2[i] = ba2[i];
     for (int i = t; i < A3; i += kMlpThreads) sba3[i] = ba3[i];
@@ -421,9 +520,9 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     }
 
     const int nctr = min(kThreads, m - j0);
-    mlp_phase<C0P, A1, A2, A3>(c, n, ns_a, nctr, xyz, features, sWa1, sba1, reinterpret_cast<const unsigned *>(sWa2), sba2,
+    mlp_phase<C0P, A1, A2, A3, H>(c, n, ns_a, nctr, xyz, features, sWa1, sba1, reinterpret_cast<const unsigned *>(sWa2), sba2,
                                reinterpret_cast<const unsigned *>(sWa3), sba3, sctr, sidx_a, sout);
-    mlp_phase<C0P, B1, B2, B3>(c, n, ns_b, nctr, xyz, features, sWb1, sbb1, reinterpret_cast<const unsigned *>(sWb2), sbb2,
+    mlp_phase<C0P, B1, B2, B3, H>(c, n, ns_b, nctr, xyz, features, sWb1, sbb1, reinterpret_cast<const unsigned *>(sWb2), sbb2,
                                reinterpret_cast<const unsigned *>(sWb3), sbb3, sctr, sidx_b, sout + A3 * kStride);
     __syncthreads();
     for (int i = t; i < (A3 + B3) * nctr; i += kMlpThreads) {
@@ -432,7 +531,7 @@ sa_fused_pair_kernel(int c, int n, int m, float r2a, int ns_a, float r2b, int ns
     }
 }
 
-template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3>
+template <int C0P, int A1, int A2, int A3, int B1, int B2, int B3, bool H>
 int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns_b, const float *xyz,
                 const float *new_xyz, const float *features, const float *const *W, const float *const *B, float *out,
                 void *workspace, cudaStream_t stream) {
@@ -447,14 +546,14 @@ int launch_pair(int b, int c, int n, int m, float ra, int ns_a, float rb, int ns
         unsigned char *ws = static_cast<unsigned char *>(workspace);
         pdab::grid_build_kernel<<<b, pdab::kBuildThreads, 0, stream>>>(n, inv_edge, xyz, ws);
         PDAB_LAUNCH_CHECK();
-        auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, true>;
+        auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, true, H>;
         PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, ra * ra, ns_a, rb * rb, ns_b, ws, inv_edge, xyz, new_xyz, features,
                                                   W[0], B[0], W[1], B[1], W[2], B[2], W[3], B[3], W[4], B[4], W[5], B[5], out);
         PDAB_LAUNCH_CHECK();
         return 0;
     }
-    auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, false>;
+    auto kern = sa_fused_pair_kernel<C0P, A1, A2, A3, B1, B2, B3, false, H>;
     PDAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kMlpThreads, smem, stream>>>(c, n, m, ra * ra, ns_a, rb * rb, ns_b, nullptr, 0.f, xyz, new_xyz, features,
                                               W[0], B[0], W[1], B[1], W[2], B[2], W[3], B[3], W[4], B[4], W[5], B[5], out);
@@ -490,10 +589,11 @@ extern "C" int pdab_sa_fused(int b, int c, int n, int m, float radius, int nsamp
     return PDAB_EUNSUPPORTED;
 }
 
-extern "C" int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b,
-                                  int nsample_b, const float *xyz, const float *new_xyz, const float *features,
-                                  const int *dims_a_host, const int *dims_b_host, const float *const *weights_host,
-                                  const float *const *biases_host, float *out, void *workspace, pdab_stream_t stream) {
+template <bool H>
+static int sa_fused_pair_entry(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
+                               const float *xyz, const float *new_xyz, const float *features, const int *dims_a_host,
+                               const int *dims_b_host, const float *const *weights_host, const float *const *biases_host,
+                               float *out, void *workspace, pdab_stream_t stream) {
     if (b < 0 || c < 0 || n < 1 || m < 0 || nsample_a < 1 || nsample_b < 1 || !xyz || !new_xyz || !out || !dims_a_host ||
         !dims_b_host || !weights_host || !biases_host || (c > 0 && !features))
         return PDAB_EINVAL;
@@ -507,12 +607,28 @@ extern "C" int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, in
     const bool a_small = dims_a_host[1] == 16 && dims_a_host[2] == 16 && dims_a_host[3] == 32;
     const bool b_large = dims_b_host[1] == 32 && dims_b_host[2] == 32 && dims_b_host[3] == 64;
     if (a_small && b_large && d0 <= 4)
-        return launch_pair<4, 16, 16, 32, 32, 32, 64>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
-                                                      features, weights_host, biases_host, out, workspace, s);
+        return launch_pair<4, 16, 16, 32, 32, 32, 64, H>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
+                                                         features, weights_host, biases_host, out, workspace, s);
     if (a_small && b_large && d0 <= 8)
-        return launch_pair<8, 16, 16, 32, 32, 32, 64>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
-                                                      features, weights_host, biases_host, out, workspace, s);
+        return launch_pair<8, 16, 16, 32, 32, 32, 64, H>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz,
+                                                         features, weights_host, biases_host, out, workspace, s);
     return PDAB_EUNSUPPORTED;
+}
+
+extern "C" int pdab_sa_fused_pair(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b,
+                                  int nsample_b, const float *xyz, const float *new_xyz, const float *features,
+                                  const int *dims_a_host, const int *dims_b_host, const float *const *weights_host,
+                                  const float *const *biases_host, float *out, void *workspace, pdab_stream_t stream) {
+    return sa_fused_pair_entry<false>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz, features, dims_a_host,
+                                      dims_b_host, weights_host, biases_host, out, workspace, stream);
+}
+
+extern "C" int pdab_sa_fused_pair_h(int b, int c, int n, int m, float radius_a, int nsample_a, float radius_b,
+                                    int nsample_b, const float *xyz, const float *new_xyz, const float *features,
+                                    const int *dims_a_host, const int *dims_b_host, const float *const *weights_host,
+                                    const float *const *biases_host, float *out, void *workspace, pdab_stream_t stream) {
+    return sa_fused_pair_entry<true>(b, c, n, m, radius_a, nsample_a, radius_b, nsample_b, xyz, new_xyz, features, dims_a_host,
+                                     dims_b_host, weights_host, biases_host, out, workspace, stream);
 }
 
 extern "C" size_t pdab_sa_grid_workspace_bytes(int b, int n) {

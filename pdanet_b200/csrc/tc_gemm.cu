@@ -522,7 +522,18 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::v
         const int fr = lane >> 2, fc = (lane & 3) * 2;
         // Per-column parameters live in shared memory: with ~200 KB of it carved out the L1 is a few KB and thrashed by
         // the A stream, so an __ldg of bias / gamma / beta inside the block loop was an L2 round trip on the critical path.
-        float *sbias = reinterpret_cast<float *>(smem + C::PARAM_OFF) + ew * 512;
+        // The bias of ALL column groups is staged once per kernel when it fits the EW x 512 floats set aside for it (every
+        // shape of the model); an item then only moves a pointer.  (It used to be re-read per item by each warp, "while the
+        // MMAs still run" — but a rolled loop of dependent LDG -> STS pairs is ~6 L2 round trips, and in the epilogue-bound
+        // kernels (attention) nothing was waiting for the MMAs: 12 % of the kernel's warp samples sat on that one STS.)
+        float *const sbias_all = reinterpret_cast<float *>(smem + C::PARAM_OFF);
+        const bool bias_resident = p.n_groups * NCH * BN <= EW * 512;
+        const float *sbias = sbias_all + ew * 512;
+        if (bias_resident) {
+            for (int i = ew * 32 + lane; i < p.n_groups * NCH * BN; i += EW * 32)
+                sbias_all[i] = (p.bias && i < p.Nout) ? __ldg(p.bias + i) : 0.f;
+            asm volatile("bar.sync 8, %0;" ::"n"(EW * 32) : "memory");   // the epilogue warps only
+        }
         const float *sgamma = reinterpret_cast<const float *>(smem + C::PARAM_OFF) + EW * 512;
         const float *sbeta = sgamma + 512;
         float *sstat = const_cast<float *>(sbeta) + 512;   // [2 exchanges][4 quadrants][2 halves][32 rows]
@@ -705,12 +716,22 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::v
             const long long m0 = row0_of(item);
             const int n_group = (int)(item % p.n_groups);
             const long long wrow0 = m0 + q * 32;     // first row of this warp's 32-row slab
-            __syncwarp();
-            for (int i = lane; i < NCH * BN; i += 32) {   // this item's bias -> smem while the MMAs still run
-                const int n = n_group * NCH * BN + i;
-                sbias[i] = (p.bias && n < p.Nout) ? __ldg(p.bias + n) : 0.f;
+            if (bias_resident) {
+                sbias = sbias_all + n_group * NCH * BN;
+            } else {   // this item's bias -> the warp's own slot: independent loads first, then the stores
+                __syncwarp();
+                constexpr int NBI = (NCH * BN + 31) / 32;
+                float bv[NBI];
+#pragma unroll
+                for (int u = 0; u < NBI; u++) {
+                    const int n = n_group * NCH * BN + lane + 32 * u;
+                    bv[u] = (p.bias && lane + 32 * u < NCH * BN && n < p.Nout) ? __ldg(p.bias + n) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < NBI; u++)
+                    if (lane + 32 * u < NCH * BN) sbias_all[ew * 512 + lane + 32 * u] = bv[u];
+                __syncwarp();
             }
-            __syncwarp();
             // residual tiles: two register sets, each refilled as soon as it has been consumed, so a tile has ~1.5 column
             // blocks (and, for the first two, the whole accumulator wait) to arrive from L2 / HBM
             // (EW = 8: the two warps of a quadrant take the even / odd 32-column blocks, one register set each)

@@ -445,10 +445,12 @@ def sa_fused_pair_supported(c0: int, dims_a: Sequence[int], ns_a: int, dims_b: S
     return (c0 <= 8 and tuple(dims_a) == (16, 16, 32) and tuple(dims_b) == (32, 32, 64) and ns_a <= 32 and ns_b <= 32)
 
 
-def sa_fused_pair(radii, nsamples, xyz, new_xyz, features, weights, biases, cell_list: Optional[bool] = None) -> torch.Tensor:
+def sa_fused_pair(radii, nsamples, xyz, new_xyz, features, weights, biases, cell_list: Optional[bool] = None,
+                  half: bool = False) -> torch.Tensor:
     """Both scales of a plain SA layer in one kernel (forward only).  radii / nsamples: 2 entries; weights / biases:
     6 BN-folded tensors (scale a's three layers, then scale b's).  Returns (B, cout_a + cout_b, M), the scales
-    concatenated along the channel axis.  cell_list: bucket the points into a hashed cell list first so that a centre
+    concatenated along the channel axis.  half: MLP contractions as fp16 single-pass products (pdab_sa_fused_pair_h: the
+    TF32 class of the reference's cuDNN convolutions; same neighbour lists) instead of the fp32-level split products.  cell_list: bucket the points into a hashed cell list first so that a centre
     tests 27 cells instead of the whole cloud (same neighbour lists, bit-identical output); None = for clouds of >= 4096
     points (below that building the list costs more than the scan)."""
     assert xyz.is_cuda and xyz.is_contiguous() and new_xyz.is_contiguous()
@@ -470,7 +472,7 @@ def sa_fused_pair(radii, nsamples, xyz, new_xyz, features, weights, biases, cell
     if cell_list or (cell_list is None and N >= 4096):
         ws = torch.empty(_lib.lib().pdab_sa_grid_workspace_bytes(B, N), dtype=torch.uint8, device=xyz.device)
     with torch.cuda.device(xyz.device):
-        _lib.call("pdab_sa_fused_pair", B, C, N, M, float(radii[0]), int(nsamples[0]), float(radii[1]), int(nsamples[1]),
+        _lib.call("pdab_sa_fused_pair_h" if half else "pdab_sa_fused_pair", B, C, N, M, float(radii[0]), int(nsamples[0]), float(radii[1]), int(nsamples[1]),
                   xyz.data_ptr(), new_xyz.data_ptr(), features.data_ptr() if features is not None else None, da, db,
                   w_a, b_a, out.data_ptr(), ws.data_ptr() if ws is not None else None,
                   torch.cuda.current_stream(xyz.device).cuda_stream)

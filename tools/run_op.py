@@ -40,7 +40,7 @@ elif op == "sa_fused":
     bs = [torch.randn(dims[i + 1], device="cuda") * 0.1 for i in range(3)]
     for _ in range(3):
         ops.sa_fused(r, ns, xyz, xyz[:, :M].contiguous(), feats, ws, bs)
-elif op == "sa_pair":
+elif op in ("sa_pair", "sa_pair_h"):
     import math
     B, N, M = a
     xyz = scene_xyz(N + M, B, N).cuda()
@@ -51,7 +51,7 @@ elif op == "sa_pair":
             ws.append(torch.randn(dims[i + 1], dims[i], device="cuda") / math.sqrt(dims[i]))
             bs.append(torch.randn(dims[i + 1], device="cuda") * 0.1)
     for _ in range(3):
-        ops.sa_fused_pair((0.2, 0.8), (16, 32), xyz, xyz[:, :M].contiguous(), feats, ws, bs)
+        ops.sa_fused_pair((0.2, 0.8), (16, 32), xyz, xyz[:, :M].contiguous(), feats, ws, bs, half=op == "sa_pair_h")
 elif op == "tc_linear":   # rows k nout npass epilogue  (epilogue: 0 store 1 relu 2 add+LN 3 add+maxpool 4 relu+maxpool)
     from pdanet_b200.tc_linear import PackedLinear
     rows, k, nout, npass, epi = a
