@@ -159,12 +159,17 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
     // ---- parameters -> shared memory
     const float *gW1 = p.params, *gb1 = gW1 + H * 12, *gW2t = gb1 + H, *gb2 = gW2t + H * C, *gdens = gb2 + C,
                 *ggamma = gdens + kDensFloats, *gbeta = ggamma + E;
+#pragma unroll 4
     for (int i = t; i < H * kW1Pitch; i += kThreads) {
         const int r = i / kW1Pitch, q = i - r * kW1Pitch;
         sW1[i] = q < 12 ? __ldg(gW1 + r * 12 + q) : 0.f;
     }
-    for (int i = t; i < C * (H / 2); i += kThreads) {      // W2 (C x H) = W2t^T, packed: word (n, j) = inputs 2j, 2j + 1 of output n
-        const int n = i / (H / 2), j = i - n * (H / 2);
+    // W2 (C x H) = W2t^T, packed: word (n, j) = inputs 2j, 2j + 1 of output n.  Consecutive threads take consecutive n: rows of
+    // W2t are read whole (the j-fastest order strode 2 C floats between lanes — 32 sectors per load, 8 % of the kernel's
+    // warp samples sat behind these loads), several loads in flight.
+#pragma unroll 4
+    for (int i = t; i < C * (H / 2); i += kThreads) {
+        const int j = i / C, n = i - j * C;
         unsigned hi, lo;
         split_bf16x2(__ldg(gW2t + (2 * j) * C + n), __ldg(gW2t + (2 * j + 1) * C + n), hi, lo);
         sW2h[n * P2 + j] = hi;
