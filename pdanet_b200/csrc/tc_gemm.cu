@@ -610,31 +610,41 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::v
                     }
         };
         // out16 = 1: fp16 rows; 2: (hi, lo) fp16 planes (p.out, p.out_lo); 0: fp32 rows
+        // One row pointer per (h, j) row and plane, the four column pairs at constant offsets from it; the column bound is
+        // tested once per block (every shape of the model has Nout % 32 == 0).  (The first version rebuilt a 64-bit address
+        // and re-tested both bounds for each of the 16 stores: address arithmetic and branches were half of the
+        // instructions of the LayerNorm kernel's last pass.)
         auto store_tile = [&](const float (&v)[2][16], float *base, int ld, long long grow0, long long nrows, int n0) {
+            const bool full = n0 + 32 <= p.Nout;
 #pragma unroll
             for (int h = 0; h < 2; h++)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     const long long r = grow0 + 16 * h + 8 * j + fr;
+                    if (r >= nrows) continue;
+                    const size_t o = (size_t)r * ld + n0 + fc;
+                    if (out16 == 0) {
+                        float *rowp = base + o;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int col = n0 + 8 * k + fc;
-                        if (r < nrows && col < p.Nout) {
-                            const float a = v[h][k * 4 + j * 2], b = v[h][k * 4 + j * 2 + 1];
-                            if (out16 == 0) {
-                                *reinterpret_cast<float2 *>(base + r * ld + col) = make_float2(a, b);
-                            } else {
-                                const size_t o = (size_t)r * ld + col;
-                                if (out16 == 1) {
-                                    *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(base) + o) = f16x2(a, b);
-                                } else {
-                                    u32 hi, lo;
-                                    f16_split2(a, b, hi, lo);
-                                    *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(base) + o) = hi;
-                                    *reinterpret_cast<u32 *>(reinterpret_cast<__half *>(p.out_lo) + o) = lo;
-                                }
+                        for (int k = 0; k < 4; k++)
+                            if (full || n0 + 8 * k + fc < p.Nout)
+                                *reinterpret_cast<float2 *>(rowp + 8 * k) = make_float2(v[h][k * 4 + j * 2], v[h][k * 4 + j * 2 + 1]);
+                    } else if (out16 == 1) {
+                        __half *rowp = reinterpret_cast<__half *>(base) + o;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (full || n0 + 8 * k + fc < p.Nout)
+                                *reinterpret_cast<u32 *>(rowp + 8 * k) = f16x2(v[h][k * 4 + j * 2], v[h][k * 4 + j * 2 + 1]);
+                    } else {
+                        __half *rowh = reinterpret_cast<__half *>(base) + o, *rowl = reinterpret_cast<__half *>(p.out_lo) + o;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (full || n0 + 8 * k + fc < p.Nout) {
+                                u32 hi, lo;
+                                f16_split2(v[h][k * 4 + j * 2], v[h][k * 4 + j * 2 + 1], hi, lo);
+                                *reinterpret_cast<u32 *>(rowh + 8 * k) = hi;
+                                *reinterpret_cast<u32 *>(rowl + 8 * k) = lo;
                             }
-                        }
                     }
                 }
         };
