@@ -13,7 +13,7 @@ import torch
 import oracle
 from oracle import torch_ops
 from conftest import GOLDEN
-from util import adversarial_boxes, random_boxes, scene_xyz
+from util import adversarial_boxes, boundary_boxes, random_boxes, scene_xyz
 
 pytestmark = pytest.mark.gpu
 
@@ -365,7 +365,8 @@ def test_sa_fused_matches_oracle(ops):
 
 NMS_CASES = [("kitti_256", random_boxes, 256, 0.01, (40.0, 40.0, 2.0)), ("once_1024", random_boxes, 1024, 0.1, (60.0, 60.0, 2.0)),
              ("ragged_1000", random_boxes, 1000, 0.1, (30.0, 30.0, 2.0)), ("dense_4096", random_boxes, 4096, 0.25, (80.0, 80.0, 2.0)),
-             ("tiny_3", random_boxes, 3, 0.1, (2.0, 2.0, 1.0)), ("adversarial_512", adversarial_boxes, 512, 0.1, None)]
+             ("tiny_3", random_boxes, 3, 0.1, (2.0, 2.0, 1.0)), ("adversarial_512", adversarial_boxes, 512, 0.1, None),
+             ("early_out_boundary_1000", boundary_boxes, 1000, 0.05, None)]
 
 
 def _boxes(maker, n, extent, seed):
@@ -399,7 +400,9 @@ def test_iou_close_to_oracle_and_nms_equal_when_clear_of_threshold(nms_utils, ta
     want_iou = torch.zeros(n, n)
     oracle.boxes_iou_bev_cpu(boxes, boxes, want_iou)
     got_iou = nms_utils.boxes_iou_bev(dev(boxes), dev(boxes)).cpu()
-    assert torch.allclose(got_iou, want_iou, atol=2e-5)  # libm vs libdevice trig, FMA contraction on the GPU
+    # libm vs libdevice trig, FMA contraction on the GPU; the boundary case sits at coordinates up to 400 m, where a trig ulp moves
+    # a corner by 3e-5 m and a grazing sliver by more than that (it is bit-compared with the reference kernel above)
+    assert torch.allclose(got_iou, want_iou, atol=1e-3 if tag.startswith("early_out") else 2e-5)
     if ((want_iou - thresh).abs() < 1e-4).any():
         return  # a borderline pair may legitimately flip between CPU and GPU arithmetic
     scores = torch.rand(n, generator=torch.Generator().manual_seed(n))

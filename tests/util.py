@@ -45,6 +45,27 @@ def adversarial_boxes(seed, n):
     return b.contiguous()
 
 
+def boundary_boxes(seed, n):
+    """Pairs of boxes whose separation straddles the far-pair early-out of csrc/nms.cu (axis-aligned squares around the
+    circumscribed circles, 5 cm of slack): corner-to-corner near misses and grazing contacts at every heading."""
+    g = torch.Generator().manual_seed(seed)
+    b = random_boxes(seed, n, extent=(400.0, 400.0, 1.0))
+    half = n // 2
+    a, c = b[:half], b[half:2 * half]
+    ra = 0.5 * torch.sqrt(a[:, 3] ** 2 + a[:, 4] ** 2)
+    rc = 0.5 * torch.sqrt(c[:, 3] ** 2 + c[:, 4] ** 2)
+    reach = (ra + rc) * 1.0001 + 0.05
+    frac = 1.0 + (torch.rand(half, generator=g) - 0.5) * 0.02           # within 1 % of the cut, both sides
+    frac[::5] = 0.7 + 0.3 * torch.rand(frac[::5].shape, generator=g)   # some clearly inside
+    sign = torch.where(torch.rand(half, 2, generator=g) < 0.5, -1.0, 1.0)
+    mode = torch.randint(0, 3, (half,), generator=g)                   # offset along x, along y, or along both
+    off = torch.zeros(half, 2)
+    off[:, 0] = torch.where(mode != 1, reach * frac, torch.rand(half, generator=g) * reach)
+    off[:, 1] = torch.where(mode != 0, reach * frac, torch.rand(half, generator=g) * reach)
+    c[:, :2] = a[:, :2] + sign * off
+    return b.contiguous()
+
+
 def seeded_head_model(cfg, ops=None, nms_utils=None, **kw):
     """The detector whose HEAD parameters the head golden was made with: model under manual_seed(0), then the head
     re-initialised under manual_seed(1) in the reference's construction order, BatchNorm statistics randomised from
