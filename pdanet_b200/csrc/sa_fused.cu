@@ -146,7 +146,9 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], 
 }
 
 // out (C fragments, N/8 tiles) = relu(in (C fragments, K/8 tiles) . W^T + bias); sWh / sWl: packed bf16 pairs, pitch p16(K)
-template <int K, int N>
+// RELU = false: the last layer leaves its ReLU to the max-pool (max and ReLU commute: one FMNMX3 per pooled value instead of
+// one FMNMX per accumulator element)
+template <int K, int N, bool RELU = true>
 __device__ __forceinline__ void mma_layer16(const unsigned *sWh, const unsigned *sWl, const float *sb, int g, int t,
                                             const float (&in)[K / 8][4], float (&out)[N / 8][4]) {
     constexpr int P = p16(K);
@@ -174,6 +176,7 @@ __device__ __forceinline__ void mma_layer16(const unsigned *sWh, const unsigned 
                 mma_bf16(out[nt], pass == 1 ? al : ah, sw[w], sw[w + 4]);
             }
     }
+    if constexpr (RELU)
 #pragma unroll
     for (int nt = 0; nt < N / 8; nt++)
 #pragma unroll
@@ -214,7 +217,7 @@ __device__ __forceinline__ void mma_layer1_h(const unsigned *sW, const float *sb
     }
 }
 
-template <int K, int N>
+template <int K, int N, bool RELU = true>
 __device__ __forceinline__ void mma_layer16_h(const unsigned *sW, const float *sb, int g, int t, const float (&in)[K / 8][4],
                                               float (&out)[N / 8][4]) {
     constexpr int P = p16(K);
@@ -236,6 +239,7 @@ __device__ __forceinline__ void mma_layer16_h(const unsigned *sW, const float *s
             mma_f16(out[nt], a, sW[w], sW[w + 4]);
         }
     }
+    if constexpr (RELU)
 #pragma unroll
     for (int nt = 0; nt < N / 8; nt++)
 #pragma unroll
@@ -277,7 +281,7 @@ __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, c
                 mma_layer1_h<C1>(reinterpret_cast<const unsigned *>(sW1), sb1, g, t, pack_f16x2(in[0][0], in[0][1]),
                                  pack_f16x2(in[1][0], in[1][1]), h1);
                 mma_layer16_h<C1, C2>(sW2, sb2, g, t, h1, h2);
-                mma_layer16_h<C2, C3>(sW3, sb3, g, t, h2, h3);
+                mma_layer16_h<C2, C3, false>(sW3, sb3, g, t, h2, h3);
             } else {
                 mma_layer<C0P, C1>(sW1, sb1, g, t, [&](int, float (&a)[4]) {
                     a[0] = in[0][0];
@@ -286,18 +290,21 @@ __device__ __forceinline__ void mlp_phase(int c, int n, int nsample, int nctr, c
                     a[3] = in[1][1];
                 }, h1);
                 mma_layer16<C1, C2>(sW2, sW2 + C2 * p16(C1), sb2, g, t, h1, h2);
-                mma_layer16<C2, C3>(sW3, sW3 + C3 * p16(C2), sb3, g, t, h2, h3);
+                mma_layer16<C2, C3, false>(sW3, sW3 + C3 * p16(C2), sb3, g, t, h2, h3);
             }
-            // max over the 16 rows of this m-tile: rows g / g+8 in the thread, then over g by shuffles
+            // max over the rows of the centre, ReLU included (floor 0): rows g / g+8 in the thread — for a 32-row centre both
+            // m-tiles first — then over g by shuffles, once per centre
 #pragma unroll
             for (int nt = 0; nt < C3 / 8; nt++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    float x = fmaxf(h3[nt][e], h3[nt][2 + e]);
-                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
-                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
-                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
-                    best[nt][e] = (whole && mt == 1) ? fmaxf(best[nt][e], x) : x;
+                    float x = fmaxf(fmaxf(h3[nt][e], h3[nt][2 + e]), (whole && mt == 1) ? best[nt][e] : 0.f);
+                    if (!whole || mt == 1) {
+                        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
+                        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+                        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+                    }
+                    best[nt][e] = x;
                 }
             if ((!whole || mt == 1) && g == 0) {
 #pragma unroll

@@ -442,14 +442,18 @@ __global__ void __launch_bounds__(Cfg<NPASS, BN, CG, EpiWarps<EPI, CG, ALOAD>::v
             } else {
                 if (item != meta_item) {
                     meta_item = item;
+                    // scene of the tile's first row: ONE 64-bit division per item (it used to be one per row — sixteen
+                    // emulated divisions per thread and item were 44 % of the producer warps' samples); a 128-row tile
+                    // crosses a scene boundary at most every M * ns rows, walked with a compare
+                    const long long rps = (long long)p.M * p.ns;
+                    const long long b0 = m0 / rps;
+                    const long long next0 = (b0 + 1) * rps;        // first row of the next scene
 #pragma unroll
                     for (int i = 0; i < R; i++) {
                         const long long t = m0 + r0 + RSTEP * i;
-                        src_row[i] = -1;
-                        if (t < p.T) {
-                            const long long b = t / ((long long)p.M * p.ns);
-                            src_row[i] = (int)(b * p.Nsrc + __ldg(p.idx + t));
-                        }
+                        int b = (int)b0;
+                        for (long long nx = next0; t >= nx; nx += rps) b++;   // rps < 128 only for toy shapes
+                        src_row[i] = t < p.T ? b * p.Nsrc + __ldg(p.idx + t) : -1;
                     }
                 }
 #pragma unroll

@@ -331,10 +331,11 @@ def test_h16_maxpool_epilogues(ns):
     assert _rel(lin(x16, EPI_ADD_MAXPOOL, residual=res.to(dev), nsample=ns).cpu(), ref) < H_ACC
 
 
-def test_h16_sa_gather_linear():
+@pytest.mark.parametrize("B,M", [(3, 200), (9, 5)])   # tiles that cross one scene boundary / several (80 rows per scene)
+def test_h16_sa_gather_linear(B, M):
     from pdanet_b200.tc_linear import PackedLinear, OUT_F16
     dev = _dev()
-    B, N, M, ns, C, nout = 3, 512, 200, 16, 64, 256
+    N, ns, C, nout = 512, 16, 64, 256
     g = torch.Generator().manual_seed(11)
     xyz = torch.rand(B, N, 3, generator=g) * 10
     new_xyz = torch.rand(B, M, 3, generator=g) * 10
