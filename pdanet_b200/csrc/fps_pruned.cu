@@ -75,30 +75,11 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every 
 }
 
 
-// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): round-to-nearest per half, no flush
-__device__ __forceinline__ unsigned long long pack2(float a, float b) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
+using pdab::pack2;
+using pdab::unpack2;
+using pdab::sub2;
+using pdab::mul2;
+using pdab::fma2;
 
 struct __align__(16) Candidate {
     unsigned long long key;  // [dist bits | ~tiekey]; 0 = no candidate

@@ -328,12 +328,27 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
                         vldg<CPL>(fv[q], features_t + (size_t)kq * C + CPL * lane);
                         vload<CPL>(pv[q], spos + (qb + q) * PP + CPL * lane);
                     }
+                    // LayerNorm on packed fp32 pairs (pdab::f32x2): the same operations per element as the scalar two-pass form,
+                    // two elements per FADD2 / FMUL2 / FFMA2 — the row phase was fp32-issue bound (FADD + FFMA + FMUL = 48 % of
+                    // the kernel's instructions)
+                    constexpr int NP = CPL / 2;
+                    pdab::f32x2 pv2[4][NP], fv2[4][NP], fs2[4][NP], gl2[NP];
+#pragma unroll
+                    for (int e = 0; e < NP; e++) gl2[e] = pdab::pack2(gl[2 * e], gl[2 * e + 1]);
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        float sum = 0.f;
+                        const pdab::f32x2 sc2 = pdab::pack2(scq[q], scq[q]);
+                        pdab::f32x2 acc = pdab::pack2(0.f, 0.f);
 #pragma unroll
-                        for (int e = 0; e < CPL; e++) sum += pv[q][e] + fv[q][e] * scq[q] + fv[q][e] + gl[e];
-                        mean[q] = sum;
+                        for (int e = 0; e < NP; e++) {
+                            pv2[q][e] = pdab::pack2(pv[q][2 * e], pv[q][2 * e + 1]);
+                            fv2[q][e] = pdab::pack2(fv[q][2 * e], fv[q][2 * e + 1]);
+                            fs2[q][e] = pdab::mul2(fv2[q][e], sc2);                       // feat * scale (part 1)
+                            acc = pdab::add2(acc, pdab::add2(pdab::add2(pv2[q][e], fs2[q][e]), pdab::add2(fv2[q][e], gl2[e])));
+                        }
+                        float s0, s1;
+                        pdab::unpack2(acc, s0, s1);
+                        mean[q] = s0 + s1;
                     }
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1)
@@ -342,14 +357,17 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         mean[q] *= 1.0f / E;
-                        float sq = 0.f;
+                        const pdab::f32x2 m2 = pdab::pack2(mean[q], mean[q]);
+                        pdab::f32x2 sq = pdab::pack2(0.f, 0.f);
 #pragma unroll
-                        for (int e = 0; e < CPL; e++) {
-                            const float a = pv[q][e] - mean[q], b = fv[q][e] * scq[q] - mean[q], c = fv[q][e] - mean[q],
-                                        d = gl[e] - mean[q];
-                            sq += (a * a + b * b) + (c * c + d * d);
+                        for (int e = 0; e < NP; e++) {
+                            const pdab::f32x2 a = pdab::sub2(pv2[q][e], m2), b = pdab::sub2(fs2[q][e], m2),
+                                              c = pdab::sub2(fv2[q][e], m2), d = pdab::sub2(gl2[e], m2);
+                            sq = pdab::fma2(a, a, pdab::fma2(b, b, pdab::fma2(c, c, pdab::fma2(d, d, sq))));
                         }
-                        rstd[q] = sq;
+                        float s0, s1;
+                        pdab::unpack2(sq, s0, s1);
+                        rstd[q] = s0 + s1;
                     }
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1)
@@ -366,11 +384,14 @@ __global__ void __launch_bounds__(kThreads, 2) pda_encode_ln_kernel(const EncPar
                         vload<CPL>(bt, sbeta + part * C + CPL * lane);
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
+                            const pdab::f32x2 m2 = pdab::pack2(mean[q], mean[q]), r2 = pdab::pack2(rstd[q], rstd[q]);
                             float y[CPL];
 #pragma unroll
-                            for (int e = 0; e < CPL; e++) {
-                                const float v = part == 0 ? pv[q][e] : part == 1 ? fv[q][e] * scq[q] : part == 2 ? fv[q][e] : gl[e];
-                                y[e] = (v - mean[q]) * rstd[q] * gm[e] + bt[e];
+                            for (int e = 0; e < NP; e++) {
+                                const pdab::f32x2 v = part == 0 ? pv2[q][e] : part == 1 ? fs2[q][e] : part == 2 ? fv2[q][e] : gl2[e];
+                                const pdab::f32x2 o = pdab::fma2(pdab::mul2(pdab::sub2(v, m2), r2), pdab::pack2(gm[2 * e], gm[2 * e + 1]),
+                                                                 pdab::pack2(bt[2 * e], bt[2 * e + 1]));
+                                pdab::unpack2(o, y[2 * e], y[2 * e + 1]);
                             }
                             if (p.out_hi)
                                 vstore_split16<CPL>(p.out_hi + obase_off + row_off + (size_t)q * E + part * C,
