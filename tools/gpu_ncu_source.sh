@@ -1,15 +1,15 @@
 #!/bin/bash
 # source-level ncu capture of the big kernels of one sequential step
 cd "$GRAFT_REPO_ROOT"
-mkdir -p gpurun_out /tmp/ncu gpurun_out/${TAG:-r4m}_src
-T=${TAG:-r4m}
+mkdir -p gpurun_out /tmp/ncu gpurun_out/${TAG:-src}_src
+T=${TAG:-src}
 timeout 300 python tools/run_step.py --steps 2 > gpurun_out/${T}_plain.log 2>&1 || exit 1
 timeout 1500 ncu --set full --import-source on --clock-control none -k regex:"tc_gemm_kernel|ffn_fused|pda_encode|group_attention_h" -s 45 -c 45 -o /tmp/ncu/step python tools/run_step.py --steps 2 > gpurun_out/${T}_ncu.log 2>&1
 ncu -i /tmp/ncu/step.ncu-rep --page raw --csv > gpurun_out/${T}_step_raw.csv 2>/dev/null
 ncu -i /tmp/ncu/step.ncu-rep --page source --csv --print-source sass > /tmp/ncu/all_source.csv 2>/dev/null
 python - <<'PY'
 import csv, re, os, sys
-T=os.environ.get('TAG','r4m')
+T=os.environ.get('TAG','src')
 rows=csv.reader(open('/tmp/ncu/all_source.csv'))
 secs=[]; cur=None
 for r in rows:

@@ -1,3 +1,6 @@
+"""Warp samples, executed instructions and top stall reasons of a kernel between landmark instructions (barriers, exits, ...),
+from the same source-page CSV: a quick phase breakdown of a warp-specialised kernel.
+    python tools/ncu_segments.py kernel.csv [MARK1,MARK2,...]"""
 import csv,collections,sys
 rows=list(csv.reader(open(sys.argv[1])))
 # split into kernel sections

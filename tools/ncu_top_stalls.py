@@ -1,3 +1,6 @@
+"""Most-sampled SASS instructions of one kernel with their dominant stall reason, from the CSV of
+`ncu -i rep --page source --csv --print-source sass` (one kernel section per file, as tools/gpu_ncu_source.sh writes them).
+    python tools/ncu_top_stalls.py kernel.csv [N]"""
 import csv,sys,collections
 f=sys.argv[1]; N=int(sys.argv[2]) if len(sys.argv)>2 else 25
 rows=list(csv.reader(open(f)))
