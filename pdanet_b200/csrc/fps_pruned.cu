@@ -126,7 +126,11 @@ struct __align__(8) RankedCand {
     int blocked;             // a better candidate moves it, or hides a point that may pass it
 };
 constexpr int kMaxList = 32;     // one candidate per lane in the merge
-constexpr int kListLo = 6, kListHi = 20;   // the threshold gap is steered to keep the list length in this band
+#ifndef PDAB_FPS_LIST_LO      // tools/fps_phase_probe.cu sweeps the band; the library build uses the defaults
+#define PDAB_FPS_LIST_LO 6
+#define PDAB_FPS_LIST_HI 20
+#endif
+constexpr int kListLo = PDAB_FPS_LIST_LO, kListHi = PDAB_FPS_LIST_HI;   // the threshold gap is steered to keep the list length in this band
 
 // NB buckets of P Morton-consecutive points PER THREAD, T threads (capacity P * NB * T points per CTA).
 //
