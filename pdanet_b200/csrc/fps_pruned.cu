@@ -24,9 +24,9 @@
 // Insertions only lower min-distances, so under (a) and (b) c_i is the argmax after c_1 .. c_{i-1} went in — the sequence is
 // the one-at-a-time sequence (c_1 is always accepted: it is the global argmax).  The accepted samples are then applied together
 // (fminf commutes, so `temp` is identical too).  tau follows the last accepted value through a multiplicative gap steered to
-// keep 6-20 candidates in the list; an empty or overflowing list (massive ties, all-equal clouds) falls back to the plain
-// 2-level argmax for that round.  On LiDAR-like clouds a round accepts ~9 samples (tools/fps_batch_sim.c replays the rule on
-// the host against the oracle: 16384 -> 4096 in 454 rounds).
+// keep 10-28 candidates in the list; an empty or overflowing list (massive ties, all-equal clouds) falls back to the plain
+// 2-level argmax for that round.  On LiDAR-like clouds a round accepts ~10 samples (tools/fps_batch_sim.c replays the rule on
+// the host against the oracle: 16384 -> 4096 in 385 rounds; a band of 6-20 gave 454 rounds and 7 % more time).
 //
 // Exactness (same contract as fps.cu / include/pdab.h): every distance that IS evaluated uses the
 // reference's compiled fp32 op order; skipping is conservative — a bucket is skipped only when
@@ -127,8 +127,8 @@ struct __align__(8) RankedCand {
 };
 constexpr int kMaxList = 32;     // one candidate per lane in the merge
 #ifndef PDAB_FPS_LIST_LO      // tools/fps_phase_probe.cu sweeps the band; the library build uses the defaults
-#define PDAB_FPS_LIST_LO 6
-#define PDAB_FPS_LIST_HI 20
+#define PDAB_FPS_LIST_LO 10
+#define PDAB_FPS_LIST_HI 28
 #endif
 constexpr int kListLo = PDAB_FPS_LIST_LO, kListHi = PDAB_FPS_LIST_HI;   // the threshold gap is steered to keep the list length in this band
 

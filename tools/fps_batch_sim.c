@@ -56,7 +56,7 @@ int main(int argc, char **argv) {
     const int P = argc > 3 ? atoi(argv[3]) : 16, NB = argc > 4 ? atoi(argv[4]) : 2, T = argc > 5 ? atoi(argv[5]) : 512;
     const int cloud = argc > 6 ? atoi(argv[6]) : 0;
     unsigned s = argc > 7 ? (unsigned)atoi(argv[7]) : 12345u;
-    const int LO = argc > 8 ? atoi(argv[8]) : 6, HI = argc > 9 ? atoi(argv[9]) : 20, MAXC = 32;
+    const int LO = argc > 8 ? atoi(argv[8]) : 6, HI = argc > 9 ? atoi(argv[9]) : 20, MAXC = argc > 10 ? atoi(argv[10]) : 32;
     const int CAP = P * NB * T;
     if (n > CAP) return printf("n > capacity\n"), 1;
     float *xyz = malloc(sizeof(float) * 3 * n);
@@ -116,7 +116,7 @@ int main(int argc, char **argv) {
     px[0] = xyz[0], py[0] = xyz[1], pz[0] = xyz[2];
     idx[0] = 0;
     float vref = 0.f, gap = 0.25f;
-    long rounds = 0, fb_empty = 0, fb_over = 0, sum_nc = 0, hist[40] = {0};
+    long rounds = 0, fb_empty = 0, fb_over = 0, sum_nc = 0, hist[40] = {0}, blk_conf = 0, blk_sec = 0, blk_none = 0;
     while (it < m) {
         for (int r = 0; r < npend; r++)
             for (int k = 0; k < n; k++) d[k] = fminf(sqdist3(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], px[r], py[r], pz[r]), d[k]);
@@ -174,6 +174,19 @@ int main(int argc, char **argv) {
             A = nc;
             for (int i = 0; i < nc; i++)
                 if (blocked[i] && rank[i] < A) A = rank[i];
+            if (A == nc) blk_none++;
+            else
+                for (int i = 0; i < nc; i++)
+                    if (rank[i] == A) {   /* what stopped the round: a conflict or a hidden point? */
+                        float vi;
+                        const unsigned hb = (unsigned)(list[i].key >> 32);
+                        memcpy(&vi, &hb, 4);
+                        int conf = 0;
+                        for (int j = 0; j < nc; j++)
+                            if (list[j].key > list[i].key &&
+                                sqdist3(list[i].x, list[i].y, list[i].z, list[j].x, list[j].y, list[j].z) < vi) conf = 1;
+                        if (conf) blk_conf++; else blk_sec++;
+                    }
             if (A > m - it) A = m - it;
             for (int i = 0; i < nc; i++)
                 if (rank[i] < A) {
@@ -204,6 +217,7 @@ int main(int argc, char **argv) {
     printf("n %d m %d P %d NB %d T %d cloud %d: idx mismatches %d, temp mismatches %d | rounds %ld (%.2f samples/round) fallbacks: empty %ld overflow %ld, mean list %.1f\n",
            n, m, P, NB, T, cloud, bad_i, bad_t, rounds, (double)(m - 1) / rounds, fb_empty, fb_over,
            rounds - fb_empty - fb_over ? (double)sum_nc / (rounds - fb_empty - fb_over) : 0.0);
+    printf("  rounds ended by: list exhausted %ld, conflict %ld, hidden-point bound %ld\n", blk_none, blk_conf, blk_sec);
     printf("  accepted histogram:");
     for (int a = 1; a <= 32; a++)
         if (hist[a]) printf(" %d:%ld", a, hist[a]);
