@@ -259,3 +259,29 @@ def test_three_nn_interpolate_and_points_in_boxes_oracle():
     boxes = torch.tensor([[[0.0, 0.0, 0.0, 4.0, 2.0, 2.0, 0.0], [0.0, 0.0, 0.0, 4.0, 2.0, 2.0, 1.5707964]]])
     pts = torch.tensor([[[1.9, 0.9, 0.9], [0.5, 1.9, 0.0], [3.0, 0.0, 0.0], [0.0, 0.0, 1.1]]])
     assert oracle.points_in_boxes(pts, boxes)[0].tolist() == [0, 1, -1, -1]
+
+
+# ------------------------------------------------------------------ the acceptance rule of the batched FPS kernel, on the host
+
+@pytest.mark.parametrize("n,m,P,NB,T,cloud", [
+    (4096, 1024, 8, 1, 512, 0),      # KITTI L1 shape, LiDAR-like slab
+    (16384, 700, 16, 2, 512, 1),     # KITTI L0 layout, dense clusters + background
+    (2048, 300, 4, 1, 512, 2),       # all points equal: every round falls back to the plain argmax
+    (4096, 500, 8, 1, 512, 3),       # lattice: masses of exactly equal distances (overflowing lists)
+    (1000, 999, 2, 1, 512, 0),       # ragged size, nearly every point sampled
+])
+def test_fps_rounds_acceptance_rule_replayed_on_host(tmp_path, n, m, P, NB, T, cloud):
+    """csrc/fps_pruned.cu takes several samples per barrier: candidates above a threshold are ranked and the longest prefix in
+    which no candidate is moved by an earlier one, nor overtaken by a point hidden behind a thread's best, is accepted.
+    tools/fps_batch_sim.c replays exactly that rule (same keys, same fp32 distance expression, same bucket -> thread layout,
+    same threshold controller) on the host and compares idx AND temp with the oracle's literal emulation of the reference
+    kernel; it exits non-zero on any mismatch."""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "fps_batch_sim"
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(ROOT / "tools" / "fps_batch_sim.c"),
+                           str(ROOT / "oracle" / "pdab_oracle.c"), "-lm"])
+    out = subprocess.run([str(exe), str(n), str(m), str(P), str(NB), str(T), str(cloud), "7", "10", "28"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "idx mismatches 0, temp mismatches 0" in out.stdout
