@@ -23,6 +23,9 @@
 // TMEM (512 columns): [0, 256) accumulator 1 -> fp32 z (parked in place) | [256, 384) accumulator 2 | [256, 512) accumulator 3.
 // Shared memory: 3-stage ring {A 16 KB, W 16 KB} | z / h operand tiles 64 KB | residual ring 48 KB | barriers, parameters.
 #include "tc_common.cuh"
+#ifdef PDAB_FFN_TIMERS
+#include <cstdio>
+#endif
 
 namespace {
 
@@ -171,21 +174,46 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_fused_kernel(const __grid_con
                         pipe.advance<S>();
                     }
                 };
+                // Phase timers of the MMA thread (-DPDAB_FFN_TIMERS, never in the library build).  Measured, cycles per tile of
+                // ~21.6 k: wait tile_free (E3) 4.3 k | issue GEMM1 3.0 k (ring fills) | wait z_ready (GEMM1 + E1) 9.6 k |
+                // issue GEMM2 1.8 k | wait h_ready (GEMM2 + E2) 1.4 k | issue GEMM3 0.9 k.
+#ifdef PDAB_FFN_TIMERS
+                long long ph[6] = {0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
+                int ntile = 0;
+#define FFN_TICK(i) t1 = clock64(); ph[i] += t1 - t0; t0 = t1;
+#else
+#define FFN_TICK(i)
+#endif
                 for (long long tile = pair0; tile < p.n_tiles; tile += npairs) {
                     mbar_wait(tile_free, tp ^ 1);                 // previous tile's last epilogue has left TMEM
                     tc_fence_after();
+                    FFN_TICK(0)
                     gemm(KA1, true, tmem_base, idesc256);         // acc1 = ctx . Wo^T
                     umma_commit<2>(acc_full(0));
+                    FFN_TICK(1)
                     mbar_wait(z_ready, tp);                       // both CTAs' z tiles are in shared memory
                     tc_fence_after();
+                    FFN_TICK(2)
                     gemm(KA2, false, tmem_base + 256, idesc128);  // acc2 = z . W1^T
                     umma_commit<2>(acc_full(1));
+                    FFN_TICK(3)
                     mbar_wait(h_ready, tp);
                     tc_fence_after();
+                    FFN_TICK(4)
                     gemm(KA3, false, tmem_base + 256, idesc256);  // acc3 = h . W2^T
                     umma_commit<2>(acc_full(2));
+                    FFN_TICK(5)
                     tp ^= 1;
+#ifdef PDAB_FFN_TIMERS
+                    ntile++;
+#endif
                 }
+#ifdef PDAB_FFN_TIMERS
+                if (blockIdx.x == 0 && ntile > 0)
+                    printf("FFN cycles/tile (leader MMA thread, %d tiles): wait tile_free %lld | issue GEMM1 %lld | wait z_ready %lld | "
+                           "issue GEMM2 %lld | wait h_ready %lld | issue GEMM3 %lld\n", ntile, ph[0] / ntile, ph[1] / ntile,
+                           ph[2] / ntile, ph[3] / ntile, ph[4] / ntile, ph[5] / ntile);
+#endif
             }
         }
     } else if (warp == 2) {
@@ -196,6 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_fused_kernel(const __grid_con
             Pipe rp;
             for (long long tile = pair0; tile < p.n_tiles; tile += npairs) {
                 const int rrow0 = (int)row0_of(tile);
+                // (An L2 prefetch of the tile's residual slab and ctx atoms from here — cp.async.bulk.prefetch.tensor, half a tile
+                // ahead of their use — shortened E1 by 12 % in an isolated launch and did nothing in the pipelined step.)
                 for (int cb = 0; cb < E / 32; cb++) {
                     mbar_wait(r_empty(rp.stage), rp.phase ^ 1);
                     mbar_arrive_expect_tx(r_full(rp.stage), (u32)kRStage);
