@@ -1,18 +1,19 @@
 // Pruned, batched farthest-point sampling for sm_100a: one CTA per scene for N <= 16384, a thread-block cluster of CL CTAs per
 // scene beyond that (CTA r owns the contiguous slice [r * ceil(N / CL), ...) of the scene, Morton-sorted and pruned locally; the
-// CL local winners of a step are exchanged through distributed shared memory — st.async into every peer's buffer, completion on
-// the receiver's mbarrier, no cluster barrier in the loop — and every CTA picks the same global winner).
+// CTAs' candidates are exchanged through distributed shared memory — st.async into every peer's buffer, completion on the
+// receiver's mbarrier, no cluster barrier in the loop — and every CTA takes the same decisions).
 //
 // FPS is a serial chain of m-1 steps; the plain kernel (fps.cu) touches all N points in every step although a new sample only
 // lowers the min-distance of the points in its own neighbourhood (about N/j of them at step j).  Two things are done about it.
 //
 // PRUNING.  The points of a scene are Morton-sorted once into buckets of P spatially coherent points, ONE BUCKET PER THREAD
-// (min-distances in that thread's registers).  A thread tests its bucket's bounding sphere, then box, against a new sample: if
-// the box is provably farther than the bucket's largest min-distance, no point in it can change and the bucket is skipped;
+// (min-distances in that thread's registers).  A new sample is tested against the bounding sphere of a warp's 32 buckets (lane r
+// tests pending sample r: one test for a whole batch), then every thread tests its bucket's box: if the box is provably
+// farther than the bucket's largest min-distance, no point in it can change and the bucket is skipped;
 // surviving threads update their P points (coordinates from shared memory) and refresh their cached (max, tie-key, position)
 // candidate with no cross-lane traffic.  Total work drops from N*m to about N*ln(m) point updates.
 //
-// ROUNDS (single-CTA kernel).  What is left per step is a fixed latency chain — tests, 2-level argmax, a CTA barrier, the
+// ROUNDS (single CTA, and clusters of 2 / 4 / 8 with the list exchanged over DSMEM).  What is left per step is a fixed latency chain — tests, 2-level argmax, a CTA barrier, the
 // winner's coordinates: ~1 650 cycles however little changes.  The chain is cut by taking SEVERAL samples per barrier, exactly:
 // every thread whose best point reaches a threshold tau pushes it (key, coordinates, and `sec` = the largest min-distance among
 // the thread's OTHER points) into a shared list; after one barrier every warp ranks the <= 32 candidates c_1 > c_2 > ... by the
