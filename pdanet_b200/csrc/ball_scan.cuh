@@ -291,6 +291,7 @@ grid_build_kernel(int n, float inv_edge, const float *__restrict__ xyz_all, unsi
     const int run = warp_sums[kBuildThreads / 32 - 1];
     if (t == kBuildThreads - 1) start[NB] = run;
     __syncthreads();
+#pragma unroll 4   // four atomics with their return values in flight per thread
     for (int k = t; k < n; k += kBuildThreads) {
         const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
         const int pos = atomicAdd(cursor + grid_hash(grid_cell(x, inv_edge), grid_cell(y, inv_edge),
